@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.nn.functional as Fnn
 
-from .onnx_io import Graph, Node, load_model
+from .onnx_io import Graph, Node, _c, load_model
 
 _TORCH_DT = {1: torch.float32, 2: torch.uint8, 3: torch.int8, 6: torch.int32, 7: torch.int64, 9: torch.bool}
 
@@ -67,7 +67,7 @@ class OnnxModel:
 
     def __init__(self, graph_or_path):
         self.graph: Graph = load_model(graph_or_path) if isinstance(graph_or_path, str) else graph_or_path
-        self.consts = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in self.graph.initializers.items()}
+        self.consts = {k: torch.from_numpy(_c(v)) for k, v in self.graph.initializers.items()}
 
     def input_shape(self) -> List[Any]:
         """Fixed dims as int, symbolic dims as str (rten::Dimension)."""
@@ -145,7 +145,7 @@ class OnnxModel:
         if op == "Identity":
             return a[0]
         if op == "Constant":
-            return torch.from_numpy(np.ascontiguousarray(at["value"]))
+            return torch.from_numpy(_c(at["value"]))
         if op == "Shape":
             dims = list(a[0].shape)
             return torch.tensor(dims[at.get("start", 0): at.get("end", len(dims))], dtype=torch.int64)
@@ -191,7 +191,7 @@ class OnnxModel:
             shape = _ints(a[0])
             if val is None:
                 return torch.zeros(shape, dtype=torch.float32)
-            v = torch.from_numpy(np.ascontiguousarray(val)).reshape(-1)[0]
+            v = torch.from_numpy(_c(val)).reshape(-1)[0]
             return torch.full(shape, v.item(), dtype=v.dtype)
         if op == "Pad":
             assert at.get("mode", "constant") == "constant"

@@ -16,6 +16,12 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
+def _c(a):
+    """C-contiguous copy that keeps 0-d arrays 0-d (np.ascontiguousarray would not)."""
+    a = np.asarray(a)
+    return a if a.flags.c_contiguous else a.copy(order="C")
+
+
 # TensorProto.DataType
 FLOAT, UINT8, INT8, INT32, INT64, BOOL = 1, 2, 3, 6, 7, 9
 _NP_OF = {FLOAT: np.float32, UINT8: np.uint8, INT8: np.int8, INT32: np.int32, INT64: np.int64, BOOL: np.bool_}
@@ -144,7 +150,7 @@ class Graph:
 
 # ---- encode ----------------------------------------------------------------------------------
 def _enc_tensor(name: str, arr: np.ndarray) -> bytes:
-    arr = np.ascontiguousarray(arr)
+    arr = _c(arr)
     out = b"".join(_f_varint(1, d) for d in arr.shape)
     out += _f_varint(2, _DT_OF[arr.dtype])
     out += _f_str(8, name)
