@@ -1,0 +1,174 @@
+/* ocrs_b200 -- C ABI of the B200-native OCR hot path.
+ *
+ * Drop-in boundary for robertknight/ocrs @ 4bccf6b (v0.12.2).  Two seams are exported:
+ *
+ *  (1) the inner seam = the reference's `Model` trait (ocrs/src/model.rs:6-17), which
+ *      `TextDetector` / `TextRecognizer` box as `dyn Model` (detection.rs:67, recognition.rs:316):
+ *        ocrs_b200_model_load         <- rten::Model::load_file / ModelOptions::load
+ *                                        (ocrs-cli/src/models.rs:105, ocrs/src/wasm_api.rs:62-64)
+ *        ocrs_b200_model_input_shape  <- Model::input_shape   (model.rs:9; rten impl :20-31)
+ *        ocrs_b200_model_run          <- Model::run           (model.rs:12-16; rten impl :33-40)
+ *
+ *  (2) the outer seam = the public `OcrEngine` methods (ocrs/src/lib.rs:130-300), needed to keep
+ *      pages resident in HBM between stages and to batch pages:
+ *        ocrs_b200_engine_create               <- OcrEngine::new                 (lib.rs:132)
+ *        ocrs_b200_engine_prepare_input        <- OcrEngine::prepare_input       (lib.rs:183)
+ *                                                 + ImageSource::from_bytes/from_tensor
+ *                                                 (preprocess.rs:81,105)
+ *        ocrs_b200_engine_detect_words         <- OcrEngine::detect_words        (lib.rs:193)
+ *        ocrs_b200_engine_detect_text_pixels   <- OcrEngine::detect_text_pixels  (lib.rs:207)
+ *        ocrs_b200_engine_find_text_lines      <- OcrEngine::find_text_lines     (lib.rs:222)
+ *        ocrs_b200_engine_recognize_text       <- OcrEngine::recognize_text      (lib.rs:237)
+ *        ocrs_b200_engine_prepare_recognition_input <- OcrEngine::prepare_recognition_input (lib.rs:268)
+ *        ocrs_b200_engine_detection_threshold  <- OcrEngine::detection_threshold (lib.rs:282)
+ *        ocrs_b200_engine_get_text             <- OcrEngine::get_text            (lib.rs:290)
+ *        ocrs_b200_engine_ocr_batch            <- get_text over a batch of pages (new: configs 2-5)
+ *
+ * All pointers are plain host pointers unless a function says otherwise.  Functions return 0 on
+ * success or a negative ocrs_b200_status; the message is available from ocrs_b200_last_error()
+ * (thread-local).  Nothing throws or unwinds across this boundary.  There is no CPU fallback:
+ * without a CUDA device every entry point that needs one fails with OCRS_B200_ERR_NO_DEVICE.
+ */
+#ifndef OCRS_B200_H_
+#define OCRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ocrs_b200_status {
+  OCRS_B200_OK = 0,
+  OCRS_B200_ERR_INVALID_ARG = -1,
+  OCRS_B200_ERR_UNSUPPORTED_CHANNEL_COUNT = -2, /* ImageSourceError::UnsupportedChannelCount (preprocess.rs:41) */
+  OCRS_B200_ERR_INVALID_DATA_LENGTH = -3,       /* ImageSourceError::InvalidDataLength (preprocess.rs:44) */
+  OCRS_B200_ERR_MODEL_NOT_LOADED = -4,          /* "Detection/Recognition model not loaded" (lib.rs:197,254) */
+  OCRS_B200_ERR_MODEL_LOAD = -5,
+  OCRS_B200_ERR_RUN_FAILED = -6,                /* ModelRunError::RunFailed (errors.rs:8) */
+  OCRS_B200_ERR_WRONG_OUTPUT = -7,              /* ModelRunError::WrongOutput (errors.rs:11) */
+  OCRS_B200_ERR_CUDA = -8,
+  OCRS_B200_ERR_NO_DEVICE = -9,
+  OCRS_B200_ERR_INTERNAL = -10
+} ocrs_b200_status;
+
+typedef struct ocrs_b200_model ocrs_b200_model;   /* impl Model (model.rs) */
+typedef struct ocrs_b200_engine ocrs_b200_engine; /* OcrEngine (lib.rs:111) */
+typedef struct ocrs_b200_input ocrs_b200_input;   /* OcrInput (lib.rs:125), device resident */
+
+/* rten_imageproc::RotatedRect: centre, unit up axis, width (perpendicular to up), height. */
+typedef struct ocrs_b200_rotated_rect {
+  float cx, cy, ux, uy, w, h;
+} ocrs_b200_rotated_rect;
+
+/* rten_imageproc::Rect<i32> */
+typedef struct ocrs_b200_rect {
+  int32_t top, left, bottom, right;
+} ocrs_b200_rect;
+
+/* Vec<Option<TextLine>> flattened (text_items.rs:47-66).  Line i is `None` when
+ * line_present[i] == 0; its characters are [char_offsets[i], char_offsets[i+1]). */
+typedef struct ocrs_b200_text_result {
+  int32_t n_lines;
+  uint8_t* line_present;      /* [n_lines] */
+  int64_t* char_offsets;      /* [n_lines + 1] */
+  uint32_t* chars;            /* Unicode scalar values */
+  ocrs_b200_rect* char_rects; /* TextChar::rect */
+} ocrs_b200_text_result;
+
+enum { OCRS_B200_DTYPE_U8 = 0, OCRS_B200_DTYPE_F32 = 1 };        /* ImagePixels (preprocess.rs:9-14) */
+enum { OCRS_B200_ORDER_HWC = 0, OCRS_B200_ORDER_CHW = 1 };       /* DimOrder (preprocess.rs:50-57) */
+enum { OCRS_B200_DECODE_GREEDY = 0, OCRS_B200_DECODE_BEAM = 1 }; /* DecodeMethod (recognition.rs:199-205) */
+
+/* OcrEngineParams (lib.rs:37-71).  Model buffers hold an .onnx file image; NULL = not loaded. */
+typedef struct ocrs_b200_engine_params {
+  const uint8_t* detection_model;
+  size_t detection_model_len;
+  const uint8_t* recognition_model;
+  size_t recognition_model_len;
+  int32_t debug;
+  int32_t decode_method;
+  uint32_t beam_width;
+  const char* alphabet_utf8;      /* NULL = DEFAULT_ALPHABET (lib.rs:34) */
+  const char* allowed_chars_utf8; /* NULL = every character allowed */
+  int32_t device;
+} ocrs_b200_engine_params;
+
+/* ---- general -------------------------------------------------------------------------------- */
+const char* ocrs_b200_last_error(void);
+int ocrs_b200_device_count(void);
+void ocrs_b200_free(void* p);
+const char* ocrs_b200_version(void);
+
+/* ---- inner seam: trait Model ---------------------------------------------------------------- */
+int ocrs_b200_model_load(const uint8_t* bytes, size_t len, int device, ocrs_b200_model** out);
+int ocrs_b200_model_load_file(const char* path, int device, ocrs_b200_model** out);
+/* dims[i] = -1 for a symbolic dimension (rten::Dimension::Symbolic). */
+int ocrs_b200_model_input_shape(const ocrs_b200_model* m, int64_t dims[8], int* ndim);
+/* Thread-safe on one handle (recognition.rs:465-485 calls run() from rayon workers).
+ * *out is malloc'ed by the library: release with ocrs_b200_free. */
+int ocrs_b200_model_run(const ocrs_b200_model* m, const float* in, const int64_t* in_shape, int in_ndim, float** out,
+                        int64_t out_shape[8], int* out_ndim);
+/* FLOPs executed by the last run on this handle (2*MACs of Conv/ConvTranspose/MatMul/GRU). */
+double ocrs_b200_model_last_flops(const ocrs_b200_model* m);
+void ocrs_b200_model_destroy(ocrs_b200_model* m);
+
+/* ---- outer seam: OcrEngine ------------------------------------------------------------------ */
+int ocrs_b200_engine_create(const ocrs_b200_engine_params* params, ocrs_b200_engine** out);
+void ocrs_b200_engine_destroy(ocrs_b200_engine* e);
+
+/* ImageSource::from_bytes: `len` bytes of HWC u8; channels = len / (width*height). */
+int ocrs_b200_engine_prepare_input_bytes(ocrs_b200_engine* e, const uint8_t* bytes, size_t len, uint32_t width,
+                                         uint32_t height, ocrs_b200_input** out);
+/* ImageSource::from_tensor: u8 or f32, HWC or CHW, 1/3/4 channels. */
+int ocrs_b200_engine_prepare_input(ocrs_b200_engine* e, const void* pixels, int dtype, int order, int height,
+                                   int width, int channels, ocrs_b200_input** out);
+/* Same, but `pixels` already lives in device memory of the engine's GPU. */
+int ocrs_b200_engine_prepare_input_device(ocrs_b200_engine* e, const void* device_pixels, int dtype, int order,
+                                          int height, int width, int channels, ocrs_b200_input** out);
+int ocrs_b200_input_shape(const ocrs_b200_input* in, int* height, int* width);
+/* Copies the [1,H,W] greyscale page to `out` (H*W floats). */
+int ocrs_b200_input_read(ocrs_b200_engine* e, const ocrs_b200_input* in, float* out);
+void ocrs_b200_input_destroy(ocrs_b200_input* in);
+
+/* out: H*W floats. */
+int ocrs_b200_engine_detect_text_pixels(ocrs_b200_engine* e, const ocrs_b200_input* in, float* out);
+/* *rects is malloc'ed (ocrs_b200_free).  Order = contour discovery order, as in the reference. */
+int ocrs_b200_engine_detect_words(ocrs_b200_engine* e, const ocrs_b200_input* in, ocrs_b200_rotated_rect** rects,
+                                  size_t* n);
+/* lines: *out_words holds the words regrouped line by line; line i = [offsets[i], offsets[i+1]). */
+int ocrs_b200_engine_find_text_lines(ocrs_b200_engine* e, const ocrs_b200_input* in,
+                                     const ocrs_b200_rotated_rect* words, size_t n_words,
+                                     ocrs_b200_rotated_rect** out_words, size_t** line_offsets, size_t* n_lines);
+/* Same computation without an engine handle (pure host code; usable without a GPU). */
+int ocrs_b200_find_text_lines(const ocrs_b200_rotated_rect* words, size_t n_words, ocrs_b200_rotated_rect** out_words,
+                              size_t** line_offsets, size_t* n_lines);
+int ocrs_b200_engine_recognize_text(ocrs_b200_engine* e, const ocrs_b200_input* in,
+                                    const ocrs_b200_rotated_rect* words, const size_t* line_offsets, size_t n_lines,
+                                    ocrs_b200_text_result** out);
+void ocrs_b200_text_result_free(ocrs_b200_text_result* r);
+/* *out is malloc'ed [*out_h, *out_w] floats. */
+int ocrs_b200_engine_prepare_recognition_input(ocrs_b200_engine* e, const ocrs_b200_input* in,
+                                               const ocrs_b200_rotated_rect* line_words, size_t n_words, float** out,
+                                               int* out_h, int* out_w);
+float ocrs_b200_engine_detection_threshold(const ocrs_b200_engine* e);
+/* *utf8 is malloc'ed, NUL terminated; lines joined with '\n' (lib.rs:290-300). */
+int ocrs_b200_engine_get_text(ocrs_b200_engine* e, const ocrs_b200_input* in, char** utf8);
+
+/* Batched pipeline over resident pages: detect -> layout -> recognise for every page.
+ * results[i] is a malloc'ed ocrs_b200_text_result for page i (ocrs_b200_text_result_free). */
+int ocrs_b200_engine_ocr_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
+                               ocrs_b200_text_result** results);
+/* Batched detect_words: rects of page i are (*rects)[offsets[i] .. offsets[i+1]). */
+int ocrs_b200_engine_detect_words_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
+                                        ocrs_b200_rotated_rect** rects, size_t** offsets);
+
+/* Counters accumulated since the last reset: [0] detection FLOPs, [1] recognition FLOPs,
+ * [2] words, [3] lines, [4] CTC timesteps, [5] recognition batches. */
+int ocrs_b200_engine_stats(ocrs_b200_engine* e, double out[8], int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCRS_B200_H_ */

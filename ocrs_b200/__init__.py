@@ -1,0 +1,10 @@
+"""ocrs_b200: B200-native OCR hot path behind the public surface of robertknight/ocrs.
+
+The package holds the CUDA/C++ library sources (`csrc/`), its C ABI binding (`_lib.py`) and a
+host-side mirror of the reference API (`engine.py`).  Importing it loads
+`libocrs_b200.so`; there is no CPU fallback."""
+from .engine import (  # noqa: F401
+    DEFAULT_ALPHABET, DecodeMethod, DimOrder, ImageSource, ImageSourceError, Model, OcrEngine, OcrEngineParams,
+    OcrInput, Rect, RotatedRect, TextChar, TextLine, device_count, find_text_lines,
+)
+from ._lib import OcrsError, LIB_PATH  # noqa: F401

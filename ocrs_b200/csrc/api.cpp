@@ -1,0 +1,464 @@
+// extern "C" boundary (include/ocrs_b200.h).  Exceptions never cross it.
+#include "../../include/ocrs_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+
+#include "engine.h"
+#include "executor.h"
+#include "layout.h"
+
+using namespace ocrs;
+
+namespace {
+thread_local std::string g_last_error;
+
+template <typename F>
+int guard(F&& f) {
+  try {
+    g_last_error.clear();
+    f();
+    return OCRS_B200_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "out of host memory";
+    return OCRS_B200_ERR_INTERNAL;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return OCRS_B200_ERR_INTERNAL;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return OCRS_B200_ERR_INTERNAL;
+  }
+}
+
+template <typename T>
+T* cmalloc(size_t n) {
+  T* p = static_cast<T*>(std::malloc(std::max<size_t>(n, 1) * sizeof(T)));
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+
+void require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  OCRS_CHECK(e == cudaSuccess && n > 0, kNoDevice,
+             std::string("no CUDA device available: ocrs_b200 has no CPU fallback (") + cudaGetErrorString(e) + ")");
+}
+
+ocrs_b200_text_result* make_text_result(const std::vector<TextLine>& lines) {
+  auto* r = cmalloc<ocrs_b200_text_result>(1);
+  size_t n = lines.size(), total = 0;
+  for (const auto& l : lines) total += l.present ? l.chars.size() : 0;
+  r->n_lines = (int32_t)n;
+  r->line_present = cmalloc<uint8_t>(n);
+  r->char_offsets = cmalloc<int64_t>(n + 1);
+  r->chars = cmalloc<uint32_t>(total);
+  r->char_rects = cmalloc<ocrs_b200_rect>(total);
+  size_t k = 0;
+  for (size_t i = 0; i < n; ++i) {
+    r->line_present[i] = lines[i].present ? 1 : 0;
+    r->char_offsets[i] = (int64_t)k;
+    if (!lines[i].present) continue;
+    for (const auto& c : lines[i].chars) {
+      r->chars[k] = c.ch;
+      r->char_rects[k] = ocrs_b200_rect{c.rect.top, c.rect.left, c.rect.bottom, c.rect.right};
+      ++k;
+    }
+  }
+  r->char_offsets[n] = (int64_t)k;
+  return r;
+}
+
+std::vector<geom::RotatedRect> to_rects(const ocrs_b200_rotated_rect* p, size_t n) {
+  std::vector<geom::RotatedRect> v(n);
+  static_assert(sizeof(geom::RotatedRect) == sizeof(ocrs_b200_rotated_rect), "layout mismatch");
+  if (n) std::memcpy(v.data(), p, n * sizeof(geom::RotatedRect));
+  return v;
+}
+}  // namespace
+
+struct ocrs_b200_model {
+  std::unique_ptr<Model> model;
+  double last_flops = 0;
+  std::mutex mu;
+};
+struct ocrs_b200_engine {
+  std::unique_ptr<Engine> engine;
+};
+struct ocrs_b200_input {
+  std::unique_ptr<OcrInput> input;
+};
+
+extern "C" {
+
+const char* ocrs_b200_last_error(void) { return g_last_error.c_str(); }
+const char* ocrs_b200_version(void) { return "ocrs_b200 0.1.0 (sm_100a; reference ocrs 0.12.2 @ 4bccf6b)"; }
+
+int ocrs_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void ocrs_b200_free(void* p) { std::free(p); }
+
+int ocrs_b200_model_load(const uint8_t* bytes, size_t len, int device, ocrs_b200_model** out) {
+  return guard([&] {
+    OCRS_CHECK(out != nullptr && bytes != nullptr, kInvalidArg, "null argument");
+    *out = nullptr;
+    require_device();
+    auto* m = new ocrs_b200_model();
+    try {
+      m->model = Model::load(bytes, len, device);
+    } catch (...) {
+      delete m;
+      throw;
+    }
+    *out = m;
+  });
+}
+
+int ocrs_b200_model_load_file(const char* path, int device, ocrs_b200_model** out) {
+  return guard([&] {
+    OCRS_CHECK(path != nullptr && out != nullptr, kInvalidArg, "null argument");
+    std::ifstream f(path, std::ios::binary);
+    OCRS_CHECK(f.good(), kModelLoad, std::string("cannot open model file: ") + path);
+    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    int rc = ocrs_b200_model_load(buf.data(), buf.size(), device, out);
+    if (rc != 0) throw Error(rc, g_last_error);
+  });
+}
+
+int ocrs_b200_model_input_shape(const ocrs_b200_model* m, int64_t dims[8], int* ndim) {
+  return guard([&] {
+    OCRS_CHECK(m && dims && ndim, kInvalidArg, "null argument");
+    const auto& s = m->model->input_shape();
+    OCRS_CHECK(s.size() <= 8, kInternal, "input rank > 8");
+    *ndim = (int)s.size();
+    for (size_t i = 0; i < s.size(); ++i) dims[i] = s[i];
+  });
+}
+
+int ocrs_b200_model_run(const ocrs_b200_model* cm, const float* in, const int64_t* in_shape, int in_ndim, float** out,
+                        int64_t out_shape[8], int* out_ndim) {
+  return guard([&] {
+    OCRS_CHECK(cm && in && in_shape && out && out_shape && out_ndim, kInvalidArg, "null argument");
+    OCRS_CHECK(in_ndim > 0 && in_ndim <= 8, kInvalidArg, "bad input rank");
+    auto* m = const_cast<ocrs_b200_model*>(cm);
+    OCRS_CUDA_CHECK(cudaSetDevice(m->model->device()));
+    // one private stream per call: re-entrant on a shared handle
+    cudaStream_t st;
+    OCRS_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    try {
+      std::vector<int64_t> shape(in_shape, in_shape + in_ndim);
+      int64_t n = 1;
+      for (auto d : shape) {
+        OCRS_CHECK(d >= 0, kInvalidArg, "negative dimension");
+        n *= d;
+      }
+      DTensor x;
+      x.shape = shape;
+      x.storage = std::make_shared<Storage>((size_t)n * 4, st);
+      x.data = reinterpret_cast<float*>(x.storage->ptr);
+      OCRS_CUDA_CHECK(cudaMemcpyAsync(x.data, in, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+      ModelCost cost;
+      DTensor y = m->model->run(x, st, &cost);
+      OCRS_CHECK(y.shape.size() <= 8, kWrongOutput, "output rank > 8");
+      float* host = cmalloc<float>((size_t)y.numel());
+      cudaError_t e = cudaMemcpyAsync(host, y.data, (size_t)y.numel() * 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        std::free(host);
+        throw Error(kCuda, std::string("CUDA error ") + cudaGetErrorString(e));
+      }
+      *out = host;
+      *out_ndim = (int)y.shape.size();
+      for (size_t i = 0; i < y.shape.size(); ++i) out_shape[i] = y.shape[i];
+      {
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->last_flops = cost.flops;
+      }
+      x = DTensor();
+      y = DTensor();
+      cudaStreamSynchronize(st);
+    } catch (...) {
+      cudaStreamSynchronize(st);
+      cudaStreamDestroy(st);
+      throw;
+    }
+    cudaStreamDestroy(st);
+  });
+}
+
+double ocrs_b200_model_last_flops(const ocrs_b200_model* m) { return m ? m->last_flops : 0.0; }
+
+void ocrs_b200_model_destroy(ocrs_b200_model* m) {
+  guard([&] { delete m; });
+}
+
+int ocrs_b200_engine_create(const ocrs_b200_engine_params* p, ocrs_b200_engine** out) {
+  return guard([&] {
+    OCRS_CHECK(p && out, kInvalidArg, "null argument");
+    *out = nullptr;
+    require_device();
+    EngineParams ep;
+    ep.detection_model = p->detection_model;
+    ep.detection_model_len = p->detection_model_len;
+    ep.recognition_model = p->recognition_model;
+    ep.recognition_model_len = p->recognition_model_len;
+    ep.debug = p->debug != 0;
+    OCRS_CHECK(p->decode_method == OCRS_B200_DECODE_GREEDY || p->decode_method == OCRS_B200_DECODE_BEAM, kInvalidArg,
+               "unknown decode method");
+    ep.decode_method = p->decode_method == OCRS_B200_DECODE_BEAM ? DecodeMethod::kBeamSearch : DecodeMethod::kGreedy;
+    ep.beam_width = p->beam_width;
+    if (p->alphabet_utf8) { ep.has_alphabet = true; ep.alphabet_utf8 = p->alphabet_utf8; }
+    if (p->allowed_chars_utf8) { ep.has_allowed_chars = true; ep.allowed_chars_utf8 = p->allowed_chars_utf8; }
+    ep.device = p->device;
+    auto* e = new ocrs_b200_engine();
+    try {
+      e->engine = std::make_unique<Engine>(ep);
+    } catch (...) {
+      delete e;
+      throw;
+    }
+    *out = e;
+  });
+}
+
+void ocrs_b200_engine_destroy(ocrs_b200_engine* e) {
+  guard([&] { delete e; });
+}
+
+int ocrs_b200_engine_prepare_input_bytes(ocrs_b200_engine* e, const uint8_t* bytes, size_t len, uint32_t width,
+                                         uint32_t height, ocrs_b200_input** out) {
+  return guard([&] {
+    OCRS_CHECK(e && out, kInvalidArg, "null argument");
+    *out = nullptr;
+    // ImageSource::from_bytes (preprocess.rs:81-102)
+    size_t channel_len = (size_t)width * height;
+    OCRS_CHECK(channel_len != 0, kUnsupportedChannelCount, "channel count is not 1, 3 or 4");
+    OCRS_CHECK(len % channel_len == 0, kInvalidDataLength, "data length is not a multiple of `width * height`");
+    size_t channels = len / channel_len;
+    OCRS_CHECK(channels == 1 || channels == 3 || channels == 4, kUnsupportedChannelCount,
+               "channel count is not 1, 3 or 4");
+    auto in = e->engine->prepare_input(bytes, 0, 0, (int)height, (int)width, (int)channels);
+    auto* h = new ocrs_b200_input();
+    h->input = std::move(in);
+    *out = h;
+  });
+}
+
+static int prepare_input_common(ocrs_b200_engine* e, const void* pixels, int dtype, int order, int height, int width,
+                                int channels, bool on_device, ocrs_b200_input** out) {
+  return guard([&] {
+    OCRS_CHECK(e && out, kInvalidArg, "null argument");
+    *out = nullptr;
+    auto in = e->engine->prepare_input(pixels, dtype, order, height, width, channels, on_device);
+    auto* h = new ocrs_b200_input();
+    h->input = std::move(in);
+    *out = h;
+  });
+}
+
+int ocrs_b200_engine_prepare_input(ocrs_b200_engine* e, const void* pixels, int dtype, int order, int height,
+                                   int width, int channels, ocrs_b200_input** out) {
+  return prepare_input_common(e, pixels, dtype, order, height, width, channels, false, out);
+}
+int ocrs_b200_engine_prepare_input_device(ocrs_b200_engine* e, const void* pixels, int dtype, int order, int height,
+                                          int width, int channels, ocrs_b200_input** out) {
+  return prepare_input_common(e, pixels, dtype, order, height, width, channels, true, out);
+}
+
+int ocrs_b200_input_shape(const ocrs_b200_input* in, int* height, int* width) {
+  return guard([&] {
+    OCRS_CHECK(in && height && width, kInvalidArg, "null argument");
+    *height = in->input->H;
+    *width = in->input->W;
+  });
+}
+
+int ocrs_b200_input_read(ocrs_b200_engine* e, const ocrs_b200_input* in, float* out) {
+  return guard([&] {
+    OCRS_CHECK(e && in && out, kInvalidArg, "null argument");
+    e->engine->synchronize();
+    OCRS_CUDA_CHECK(cudaMemcpy(out, in->input->grey.ptr, (size_t)in->input->H * in->input->W * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+void ocrs_b200_input_destroy(ocrs_b200_input* in) {
+  guard([&] { delete in; });
+}
+
+int ocrs_b200_engine_detect_text_pixels(ocrs_b200_engine* e, const ocrs_b200_input* in, float* out) {
+  return guard([&] {
+    OCRS_CHECK(e && in && out, kInvalidArg, "null argument");
+    std::vector<float> p = e->engine->detect_text_pixels(*in->input);
+    std::memcpy(out, p.data(), p.size() * 4);
+  });
+}
+
+int ocrs_b200_engine_detect_words(ocrs_b200_engine* e, const ocrs_b200_input* in, ocrs_b200_rotated_rect** rects,
+                                  size_t* n) {
+  return guard([&] {
+    OCRS_CHECK(e && in && rects && n, kInvalidArg, "null argument");
+    auto r = e->engine->detect_words({in->input.get()});
+    *n = r[0].size();
+    *rects = cmalloc<ocrs_b200_rotated_rect>(*n);
+    if (*n) std::memcpy(*rects, r[0].data(), *n * sizeof(ocrs_b200_rotated_rect));
+  });
+}
+
+int ocrs_b200_engine_detect_words_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
+                                        ocrs_b200_rotated_rect** rects, size_t** offsets) {
+  return guard([&] {
+    OCRS_CHECK(e && (inputs || n_pages == 0) && rects && offsets, kInvalidArg, "null argument");
+    std::vector<const OcrInput*> pages(n_pages);
+    for (size_t i = 0; i < n_pages; ++i) {
+      OCRS_CHECK(inputs[i] != nullptr, kInvalidArg, "null input");
+      pages[i] = inputs[i]->input.get();
+    }
+    auto r = e->engine->detect_words(pages);
+    size_t total = 0;
+    for (auto& v : r) total += v.size();
+    *rects = cmalloc<ocrs_b200_rotated_rect>(total);
+    *offsets = cmalloc<size_t>(n_pages + 1);
+    size_t k = 0;
+    for (size_t i = 0; i < n_pages; ++i) {
+      (*offsets)[i] = k;
+      if (!r[i].empty()) std::memcpy(*rects + k, r[i].data(), r[i].size() * sizeof(ocrs_b200_rotated_rect));
+      k += r[i].size();
+    }
+    (*offsets)[n_pages] = k;
+  });
+}
+
+int ocrs_b200_find_text_lines(const ocrs_b200_rotated_rect* words, size_t n_words, ocrs_b200_rotated_rect** out_words,
+                              size_t** line_offsets, size_t* n_lines) {
+  return guard([&] {
+    OCRS_CHECK((words || n_words == 0) && out_words && line_offsets && n_lines, kInvalidArg, "null argument");
+    auto lines = layout::find_text_lines(to_rects(words, n_words));
+    size_t total = 0;
+    for (auto& l : lines) total += l.size();
+    *out_words = cmalloc<ocrs_b200_rotated_rect>(total);
+    *line_offsets = cmalloc<size_t>(lines.size() + 1);
+    size_t k = 0;
+    for (size_t i = 0; i < lines.size(); ++i) {
+      (*line_offsets)[i] = k;
+      std::memcpy(*out_words + k, lines[i].data(), lines[i].size() * sizeof(ocrs_b200_rotated_rect));
+      k += lines[i].size();
+    }
+    (*line_offsets)[lines.size()] = k;
+    *n_lines = lines.size();
+  });
+}
+
+int ocrs_b200_engine_find_text_lines(ocrs_b200_engine* e, const ocrs_b200_input* in,
+                                     const ocrs_b200_rotated_rect* words, size_t n_words,
+                                     ocrs_b200_rotated_rect** out_words, size_t** line_offsets, size_t* n_lines) {
+  (void)in;  // unused by the reference as well (lib.rs:224)
+  if (!e) {
+    g_last_error = "null argument";
+    return OCRS_B200_ERR_INVALID_ARG;
+  }
+  return ocrs_b200_find_text_lines(words, n_words, out_words, line_offsets, n_lines);
+}
+
+int ocrs_b200_engine_recognize_text(ocrs_b200_engine* e, const ocrs_b200_input* in,
+                                    const ocrs_b200_rotated_rect* words, const size_t* line_offsets, size_t n_lines,
+                                    ocrs_b200_text_result** out) {
+  return guard([&] {
+    OCRS_CHECK(e && in && out && (n_lines == 0 || (words && line_offsets)), kInvalidArg, "null argument");
+    std::vector<std::vector<geom::RotatedRect>> lines(n_lines);
+    for (size_t i = 0; i < n_lines; ++i) {
+      OCRS_CHECK(line_offsets[i + 1] >= line_offsets[i], kInvalidArg, "line offsets must be non-decreasing");
+      lines[i] = to_rects(words + line_offsets[i], line_offsets[i + 1] - line_offsets[i]);
+    }
+    auto r = e->engine->recognize_text({in->input.get()}, {lines});
+    *out = make_text_result(r[0]);
+  });
+}
+
+void ocrs_b200_text_result_free(ocrs_b200_text_result* r) {
+  if (!r) return;
+  std::free(r->line_present);
+  std::free(r->char_offsets);
+  std::free(r->chars);
+  std::free(r->char_rects);
+  std::free(r);
+}
+
+int ocrs_b200_engine_prepare_recognition_input(ocrs_b200_engine* e, const ocrs_b200_input* in,
+                                               const ocrs_b200_rotated_rect* line_words, size_t n_words, float** out,
+                                               int* out_h, int* out_w) {
+  return guard([&] {
+    OCRS_CHECK(e && in && line_words && out && out_h && out_w, kInvalidArg, "null argument");
+    std::vector<float> img = e->engine->prepare_recognition_input(*in->input, to_rects(line_words, n_words), out_h, out_w);
+    *out = cmalloc<float>(img.size());
+    std::memcpy(*out, img.data(), img.size() * 4);
+  });
+}
+
+float ocrs_b200_engine_detection_threshold(const ocrs_b200_engine* e) {
+  return e ? e->engine->detection_threshold() : 0.2f;  // TextDetectorParams::default (detection.rs:34)
+}
+
+int ocrs_b200_engine_get_text(ocrs_b200_engine* e, const ocrs_b200_input* in, char** utf8) {
+  return guard([&] {
+    OCRS_CHECK(e && in && utf8, kInvalidArg, "null argument");
+    auto r = e->engine->ocr_pages({in->input.get()});
+    std::string text;
+    bool first = true;
+    for (const auto& l : r[0]) {
+      if (!l.present) continue;
+      if (!first) text.push_back('\n');
+      first = false;
+      std::vector<uint32_t> cps;
+      for (const auto& c : l.chars) cps.push_back(c.ch);
+      text += codepoints_to_utf8(cps);
+    }
+    *utf8 = cmalloc<char>(text.size() + 1);
+    std::memcpy(*utf8, text.c_str(), text.size() + 1);
+  });
+}
+
+int ocrs_b200_engine_ocr_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
+                               ocrs_b200_text_result** results) {
+  return guard([&] {
+    OCRS_CHECK(e && (inputs || n_pages == 0) && results, kInvalidArg, "null argument");
+    std::vector<const OcrInput*> pages(n_pages);
+    for (size_t i = 0; i < n_pages; ++i) {
+      OCRS_CHECK(inputs[i] != nullptr, kInvalidArg, "null input");
+      pages[i] = inputs[i]->input.get();
+      results[i] = nullptr;
+    }
+    auto r = e->engine->ocr_pages(pages);
+    for (size_t i = 0; i < n_pages; ++i) results[i] = make_text_result(r[i]);
+  });
+}
+
+int ocrs_b200_engine_stats(ocrs_b200_engine* e, double out[8], int reset) {
+  return guard([&] {
+    OCRS_CHECK(e && out, kInvalidArg, "null argument");
+    auto s = e->engine->stats();
+    out[0] = s.det_flops;
+    out[1] = s.rec_flops;
+    out[2] = (double)s.n_words;
+    out[3] = (double)s.n_lines;
+    out[4] = (double)s.n_timesteps;
+    out[5] = (double)s.rec_batches;
+    out[6] = 0;
+    out[7] = 0;
+    if (reset) e->engine->reset_stats();
+  });
+}
+
+}  // extern "C"

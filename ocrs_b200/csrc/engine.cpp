@@ -1,0 +1,530 @@
+// OcrEngine orchestration on one GPU.  See engine.h.
+#include "engine.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+#include "layout.h"
+
+namespace ocrs {
+
+using geom::PointI;
+using geom::RectI;
+using geom::RotatedRect;
+
+// lib.rs:34 (the character before "ABCDE" is a plain 'E' in the reference source at this commit)
+static const char kDefaultAlphabet[] =
+    " 0123456789!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~EABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz";
+
+std::vector<uint32_t> utf8_to_codepoints(const std::string& s) {
+  std::vector<uint32_t> out;
+  size_t i = 0, n = s.size();
+  while (i < n) {
+    uint8_t c = (uint8_t)s[i];
+    uint32_t cp;
+    int extra;
+    if (c < 0x80) { cp = c; extra = 0; }
+    else if ((c >> 5) == 0x6) { cp = c & 0x1F; extra = 1; }
+    else if ((c >> 4) == 0xE) { cp = c & 0x0F; extra = 2; }
+    else if ((c >> 3) == 0x1E) { cp = c & 0x07; extra = 3; }
+    else { cp = 0xFFFD; extra = 0; }
+    ++i;
+    for (int k = 0; k < extra && i < n; ++k, ++i) cp = (cp << 6) | ((uint8_t)s[i] & 0x3F);
+    out.push_back(cp);
+  }
+  return out;
+}
+
+std::string codepoints_to_utf8(const std::vector<uint32_t>& cps) {
+  std::string s;
+  for (uint32_t cp : cps) {
+    if (cp < 0x80) s.push_back((char)cp);
+    else if (cp < 0x800) { s.push_back((char)(0xC0 | (cp >> 6))); s.push_back((char)(0x80 | (cp & 0x3F))); }
+    else if (cp < 0x10000) {
+      s.push_back((char)(0xE0 | (cp >> 12)));
+      s.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+      s.push_back((char)(0x80 | (cp & 0x3F)));
+    } else {
+      s.push_back((char)(0xF0 | (cp >> 18)));
+      s.push_back((char)(0x80 | ((cp >> 12) & 0x3F)));
+      s.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+      s.push_back((char)(0x80 | (cp & 0x3F)));
+    }
+  }
+  return s;
+}
+
+struct Engine::PageScratch {
+  int cap_hw = 0;
+  DeviceBuffer mask, prob, labels, comp_roots, counters, pts, simp_idx, stack, fpts, hull, rects, rect_root;
+  img::ComponentBuffers bufs{};
+};
+
+Engine::PageScratch& Engine::scratch_for(int slot, int H, int W) {
+  while ((int)scratch_.size() <= slot) scratch_.push_back(std::make_unique<PageScratch>());
+  PageScratch& s = *scratch_[slot];
+  int64_t hw = (int64_t)H * W;
+  if (hw > s.cap_hw || s.bufs.labels == nullptr) {
+    int64_t pool = 2 * hw + 16;
+    int32_t max_comps = (int32_t)(((int64_t)(H + 1) / 2) * ((W + 1) / 2) + 1);
+    s.mask.reserve((size_t)hw);
+    s.labels.reserve((size_t)(hw + 1) * 4);
+    s.comp_roots.reserve((size_t)max_comps * 4);
+    s.counters.reserve(8 * 4);
+    s.pts.reserve((size_t)pool * 2 * sizeof(int16_t));
+    s.simp_idx.reserve((size_t)pool * 4);
+    s.stack.reserve((size_t)pool * 3 * 4);
+    s.fpts.reserve((size_t)pool * 2 * 4);
+    s.hull.reserve((size_t)pool * 2 * 4);
+    s.rects.reserve((size_t)max_comps * sizeof(RotatedRect));
+    s.rect_root.reserve((size_t)max_comps * 4);
+    s.cap_hw = (int)hw;
+    s.bufs.labels = s.labels.as<int32_t>();
+    s.bufs.comp_roots = s.comp_roots.as<int32_t>();
+    s.bufs.counters = s.counters.as<int32_t>();
+    s.bufs.pts = s.pts.as<int16_t>();
+    s.bufs.simp_idx = s.simp_idx.as<int32_t>();
+    s.bufs.stack = s.stack.as<int32_t>();
+    s.bufs.fpts = s.fpts.as<float>();
+    s.bufs.hull = s.hull.as<float>();
+    s.bufs.rects = s.rects.as<RotatedRect>();
+    s.bufs.rect_root = s.rect_root.as<int32_t>();
+    s.bufs.pool_cap = pool;
+    s.bufs.max_comps = max_comps;
+  }
+  return s;
+}
+
+Engine::Engine(const EngineParams& p) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  OCRS_CHECK(e == cudaSuccess && ndev > 0, kNoDevice,
+             "no CUDA device available: ocrs_b200 has no CPU fallback (cudaGetDeviceCount: " +
+                 std::string(cudaGetErrorString(e)) + ")");
+  OCRS_CHECK(p.device >= 0 && p.device < ndev, kInvalidArg, "device index out of range");
+  device_ = p.device;
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  configure_device_pool(device_);
+  OCRS_CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+  if (p.detection_model) det_ = Model::load(p.detection_model, p.detection_model_len, device_);
+  if (p.recognition_model) rec_ = Model::load(p.recognition_model, p.recognition_model_len, device_);
+  debug_ = p.debug;
+  decode_method_ = p.decode_method;
+  beam_width_ = p.beam_width;
+  alphabet_ = utf8_to_codepoints(p.has_alphabet ? p.alphabet_utf8 : std::string(kDefaultAlphabet));  // lib.rs:149-151
+  if (p.has_allowed_chars) {  // lib.rs:153-170
+    std::vector<uint32_t> allowed = utf8_to_codepoints(p.allowed_chars_utf8);
+    excluded_mask_.assign(alphabet_.size() + 1, 0);
+    for (size_t i = 0; i < alphabet_.size(); ++i) {
+      bool ok = std::find(allowed.begin(), allowed.end(), alphabet_[i]) != allowed.end();
+      if (!ok) excluded_mask_[i + 1] = 1;
+    }
+    has_excluded_ = true;
+    d_excluded_.reserve(excluded_mask_.size());
+    OCRS_CUDA_CHECK(cudaMemcpy(d_excluded_.ptr, excluded_mask_.data(), excluded_mask_.size(), cudaMemcpyHostToDevice));
+  }
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (st_) {
+    cudaStreamSynchronize(st_);
+  }
+  det_.reset();
+  rec_.reset();
+  if (st_) cudaStreamDestroy(st_);
+}
+
+void Engine::synchronize() {
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+}
+
+uint32_t Engine::rec_input_height() const {  // recognition.rs:332-337
+  OCRS_CHECK(rec_ != nullptr, kModelNotLoaded, "Recognition model not loaded");
+  const auto& s = rec_->input_shape();
+  if (s.size() > 2 && s[2] >= 0) return (uint32_t)s[2];
+  return 50;
+}
+
+std::unique_ptr<OcrInput> Engine::prepare_input(const void* pixels, int dtype, int order, int H, int W, int C,
+                                                bool on_device) {
+  // ImageSource::from_bytes / from_tensor validation (preprocess.rs:81-123)
+  OCRS_CHECK(pixels != nullptr, kInvalidArg, "pixels is null");
+  OCRS_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be 0 (u8) or 1 (f32)");
+  OCRS_CHECK(order == 0 || order == 1, kInvalidArg, "order must be 0 (HWC) or 1 (CHW)");
+  OCRS_CHECK(H >= 0 && W >= 0, kInvalidArg, "negative image size");
+  OCRS_CHECK(C == 1 || C == 3 || C == 4, kUnsupportedChannelCount, "channel count is not 1, 3 or 4");
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  auto in = std::make_unique<OcrInput>();
+  in->H = H;
+  in->W = W;
+  in->device = device_;
+  size_t hw = (size_t)H * W;
+  in->grey.reserve(std::max<size_t>(hw, 1) * sizeof(float));
+  if (hw == 0) return in;
+  size_t bytes = hw * C * (dtype == 0 ? 1 : 4);
+  const void* dpx = pixels;
+  if (!on_device) {
+    staging_.reserve(bytes);
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(staging_.ptr, pixels, bytes, cudaMemcpyHostToDevice, st_));
+    dpx = staging_.ptr;
+  }
+  img::prepare_image(dpx, dtype, order, H, W, C, in->grey.as<float>(), st_);
+  stats_.kernel_launches += 1;
+  // the staging buffer is reused by the next call: order it behind this kernel
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  return in;
+}
+
+namespace {
+DTensor wrap_tensor(float* ptr, std::vector<int64_t> shape) {
+  DTensor t;
+  int64_t n = 1;
+  for (auto d : shape) n *= d;
+  t.storage = std::make_shared<Storage>(ptr, (size_t)n * 4);
+  t.data = ptr;
+  t.shape = std::move(shape);
+  return t;
+}
+}  // namespace
+
+std::vector<float> Engine::detect_text_pixels(const OcrInput& in) {
+  OCRS_CHECK(det_ != nullptr, kModelNotLoaded, "Detection model not loaded");  // lib.rs:211
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  const auto& shp = det_->input_shape();
+  OCRS_CHECK(shp.size() == 4 && shp[2] >= 0 && shp[3] >= 0, kRunFailed, "failed to get model dims");  // detection.rs:143
+  int in_h = (int)shp[2], in_w = (int)shp[3];
+  int H = in.H, W = in.W;
+  int pad_bottom = std::max(in_h - H, 0), pad_right = std::max(in_w - W, 0);
+  det_in_.reserve((size_t)in_h * in_w * 4);
+  img::resize_padded(in.grey.as<float>(), H, W, H + pad_bottom, W + pad_right, img::kBlackValue, det_in_.as<float>(),
+                     in_h, in_w, 1, 0, 0, st_);
+  DTensor out = det_->run(wrap_tensor(det_in_.as<float>(), {1, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_);
+  OCRS_CHECK(out.shape.size() == 4 && out.numel() == (int64_t)in_h * in_w, kWrongOutput,
+             "detection output must be [1,1,H,W]");
+  PageScratch& s = scratch_for(0, H, W);
+  s.prob.reserve((size_t)H * W * 4 + 4);
+  img::resize_threshold(out.data, in_h, in_w, in_h - pad_bottom, in_w - pad_right, s.prob.as<float>(),
+                        s.mask.as<uint8_t>(), H, W, text_threshold_, st_);
+  std::vector<float> host((size_t)H * W);
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(host.data(), s.prob.ptr, host.size() * 4, cudaMemcpyDeviceToHost, st_));
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  return host;
+}
+
+std::vector<std::vector<RotatedRect>> Engine::detect_words(const std::vector<const OcrInput*>& pages) {
+  OCRS_CHECK(det_ != nullptr, kModelNotLoaded, "Detection model not loaded");  // lib.rs:197
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  const int N = (int)pages.size();
+  std::vector<std::vector<RotatedRect>> result((size_t)N);
+  if (N == 0) return result;
+  const auto& shp = det_->input_shape();
+  OCRS_CHECK(shp.size() == 4 && shp[2] >= 0 && shp[3] >= 0, kRunFailed, "failed to get model dims");
+  const int in_h = (int)shp[2], in_w = (int)shp[3];
+  const int64_t plane = (int64_t)in_h * in_w;
+  det_in_.reserve((size_t)N * plane * 4);
+  for (int i = 0; i < N; ++i) {
+    const OcrInput& in = *pages[i];
+    OCRS_CHECK(in.device == device_, kInvalidArg, "input lives on another device");
+    int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
+    img::resize_padded(in.grey.as<float>(), in.H, in.W, in.H + pb, in.W + pr, img::kBlackValue,
+                       det_in_.as<float>() + i * plane, in_h, in_w, 1, 0, 0, st_);
+  }
+  ModelCost cost;
+  DTensor out = det_->run(wrap_tensor(det_in_.as<float>(), {N, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_, &cost);
+  stats_.det_flops += cost.flops;
+  OCRS_CHECK(out.shape.size() == 4 && out.numel() == (int64_t)N * plane, kWrongOutput,
+             "detection output must be [N,1,H,W]");
+  h_pin_.reserve((size_t)N * 8 * 4);
+  int32_t* h_counters = h_pin_.as<int32_t>();
+  for (int i = 0; i < N; ++i) {
+    const OcrInput& in = *pages[i];
+    PageScratch& s = scratch_for(i, in.H, in.W);
+    int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
+    img::resize_threshold(out.data + i * plane, in_h, in_w, in_h - pb, in_w - pr, nullptr, s.mask.as<uint8_t>(),
+                          in.H, in.W, text_threshold_, st_);
+    img::find_component_rects(s.mask.as<uint8_t>(), in.H, in.W, 2.0f /* detection.rs:50 */,
+                              3.0f /* detection.rs:116 */, min_area_, s.bufs, st_);
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(h_counters + 8 * i, s.bufs.counters, 8 * 4, cudaMemcpyDeviceToHost, st_));
+  }
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  std::vector<std::vector<int32_t>> roots((size_t)N);
+  for (int i = 0; i < N; ++i) {
+    const int32_t* c = h_counters + 8 * i;
+    OCRS_CHECK(c[2] == 0, kRunFailed,
+               c[2] == 1 ? "component table overflow" : "contour point pool overflow (mask too fragmented)");
+    int n = c[3];
+    result[i].resize((size_t)n);
+    roots[i].resize((size_t)n);
+    if (n > 0) {
+      PageScratch& s = *scratch_[i];
+      OCRS_CUDA_CHECK(cudaMemcpyAsync(result[i].data(), s.bufs.rects, (size_t)n * sizeof(RotatedRect),
+                                      cudaMemcpyDeviceToHost, st_));
+      OCRS_CUDA_CHECK(cudaMemcpyAsync(roots[i].data(), s.bufs.rect_root, (size_t)n * 4, cudaMemcpyDeviceToHost, st_));
+    }
+  }
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  for (int i = 0; i < N; ++i) {
+    // restore contour discovery (raster) order: layout depends on it (layout_analysis.rs:116-119)
+    size_t n = result[i].size();
+    std::vector<size_t> order(n);
+    for (size_t k = 0; k < n; ++k) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return roots[i][a] < roots[i][b]; });
+    std::vector<RotatedRect> sorted(n);
+    for (size_t k = 0; k < n; ++k) sorted[k] = result[i][order[k]];
+    result[i].swap(sorted);
+    stats_.n_words += (int64_t)n;
+  }
+  return result;
+}
+
+std::vector<std::vector<RotatedRect>> Engine::find_text_lines(const std::vector<RotatedRect>& words) const {
+  return layout::find_text_lines(words);
+}
+
+namespace {
+struct RecLine {
+  int page, index;
+  std::vector<PointI> poly;
+  RectI rect;  // polygon bounding rect
+  uint32_t resized_width;
+  int group_width;
+};
+}  // namespace
+
+std::vector<std::vector<TextLine>> Engine::recognize_text(
+    const std::vector<const OcrInput*>& pages,
+    const std::vector<std::vector<std::vector<RotatedRect>>>& lines_per_page) {
+  OCRS_CHECK(rec_ != nullptr, kModelNotLoaded, "Recognition model not loaded");  // lib.rs:254
+  OCRS_CHECK(pages.size() == lines_per_page.size(), kInvalidArg, "pages / lines size mismatch");
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  const int n_pages = (int)pages.size();
+  const int rec_h = (int)rec_input_height();
+  std::vector<std::vector<TextLine>> result((size_t)n_pages);
+
+  // ---- host: per-line geometry (recognition.rs:429-446) ----
+  std::vector<RecLine> lines;
+  for (int p = 0; p < n_pages; ++p) {
+    result[p].resize(lines_per_page[p].size());
+    for (size_t li = 0; li < lines_per_page[p].size(); ++li) {
+      const auto& words = lines_per_page[p][li];
+      OCRS_CHECK(!words.empty(), kInvalidArg, "line has no words");  // recognition.rs:433 (expect)
+      RectI line_rect;
+      layout::line_integral_rect(words, &line_rect);
+      RecLine rl;
+      rl.page = p;
+      rl.index = (int)li;
+      rl.resized_width = layout::resized_line_width(geom::rwidth(line_rect), geom::rheight(line_rect), rec_h);
+      rl.group_width = (int)(((rl.resized_width + 49u) / 50u) * 50u);  // next_multiple_of(50) (:437)
+      rl.poly = layout::line_polygon(words);
+      rl.rect = layout::polygon_bounding_rect(rl.poly);
+      lines.push_back(std::move(rl));
+    }
+  }
+  const int n_lines = (int)lines.size();
+  if (n_lines == 0) return result;
+  OCRS_CHECK(n_lines <= 65535, kInvalidArg, "too many lines in one call (max 65535)");
+
+  // group by padded width (ascending); keep line order inside a group
+  std::vector<int> order((size_t)n_lines);
+  for (int i = 0; i < n_lines; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lines[a].group_width < lines[b].group_width; });
+
+  // ---- device line descriptors ----
+  std::vector<img::LineDesc> descs((size_t)n_lines);
+  std::vector<int32_t> poly_xy;
+  int64_t dst_total = 0, cross_total = 0;
+  int max_gw = 0, max_rows = 0;
+  for (int k = 0; k < n_lines; ++k) {
+    const RecLine& rl = lines[order[k]];
+    img::LineDesc& d = descs[k];
+    d.poly_off = (int32_t)(poly_xy.size() / 2);
+    d.poly_n = (int32_t)rl.poly.size();
+    int non_horizontal = 0;
+    for (size_t v = 0; v < rl.poly.size(); ++v) {
+      poly_xy.push_back(rl.poly[v].x);
+      poly_xy.push_back(rl.poly[v].y);
+      if (rl.poly[v].y != rl.poly[(v + 1) % rl.poly.size()].y) ++non_horizontal;
+    }
+    d.top = rl.rect.top;
+    d.left = rl.rect.left;
+    d.lh = std::max(geom::rheight(rl.rect), 0);
+    d.lw = std::max(geom::rwidth(rl.rect), 0);
+    d.resized_width = (int32_t)rl.resized_width;
+    d.group_width = rl.group_width;
+    d.dst_off = dst_total;
+    d.cross_off = cross_total;
+    d.max_cross = non_horizontal;
+    d.page = rl.page;
+    dst_total += (int64_t)rec_h * rl.group_width;
+    cross_total += (int64_t)d.lh * (non_horizontal + 1);
+    max_gw = std::max(max_gw, rl.group_width);
+    max_rows = std::max(max_rows, d.lh);
+  }
+  // page table
+  std::vector<const float*> page_ptrs((size_t)n_pages);
+  std::vector<int> page_hw((size_t)2 * n_pages);
+  for (int p = 0; p < n_pages; ++p) {
+    OCRS_CHECK(pages[p]->device == device_, kInvalidArg, "input lives on another device");
+    page_ptrs[p] = pages[p]->grey.as<float>();
+    page_hw[p] = pages[p]->H;
+    page_hw[n_pages + p] = pages[p]->W;
+  }
+  size_t tab_bytes = (size_t)n_pages * (sizeof(float*) + 2 * sizeof(int));
+  page_tab_.reserve(tab_bytes);
+  line_desc_.reserve(descs.size() * sizeof(img::LineDesc));
+  poly_.reserve(poly_xy.size() * 4 + 4);
+  cross_.reserve((size_t)cross_total * 4 + 4);
+  rec_batch_.reserve((size_t)dst_total * 4);
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(page_tab_.ptr, page_ptrs.data(), n_pages * sizeof(float*), cudaMemcpyHostToDevice, st_));
+  int* d_page_hw = reinterpret_cast<int*>(page_tab_.as<char>() + n_pages * sizeof(float*));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(d_page_hw, page_hw.data(), 2 * n_pages * sizeof(int), cudaMemcpyHostToDevice, st_));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(line_desc_.ptr, descs.data(), descs.size() * sizeof(img::LineDesc), cudaMemcpyHostToDevice, st_));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(poly_.ptr, poly_xy.data(), poly_xy.size() * 4, cudaMemcpyHostToDevice, st_));
+  img::crop_lines(page_tab_.as<const float*>(), d_page_hw, d_page_hw + n_pages, line_desc_.as<img::LineDesc>(),
+                  n_lines, poly_.as<int32_t>(), cross_.as<int32_t>(), rec_batch_.as<float>(), rec_h, max_gw, max_rows,
+                  st_);
+  // host vectors must outlive the async copies
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+
+  // ---- recognition network + CTC per (group, chunk) ----
+  struct Chunk { int first, count, gw, T; int64_t out_off; };
+  std::vector<Chunk> chunks;
+  const int64_t kMaxActBytes = (int64_t)3 << 30;  // bound for the largest activation of one run
+  int64_t out_total = 0;
+  for (int k = 0; k < n_lines;) {
+    int gw = descs[k].group_width;
+    int e = k;
+    while (e < n_lines && descs[e].group_width == gw) ++e;
+    int64_t per_line = (int64_t)32 * rec_h * gw * 4;
+    int max_b = (int)std::max<int64_t>(1, kMaxActBytes / std::max<int64_t>(per_line, 1));
+    for (int s = k; s < e; s += max_b) chunks.push_back(Chunk{s, std::min(max_b, e - s), gw, 0, 0});
+    k = e;
+  }
+  const size_t n_classes = alphabet_.size() + 1;
+  // device output layout per chunk: labels [B*Tmax], pos [B*Tmax], counts [B]; Tmax = gw (>= T)
+  for (auto& c : chunks) {
+    c.out_off = out_total;
+    out_total += (int64_t)c.count * c.gw * 2 + c.count;
+  }
+  ctc_out_.reserve((size_t)out_total * 4);
+  h_pin_.reserve((size_t)out_total * 4);
+  for (auto& c : chunks) {
+    float* in_ptr = rec_batch_.as<float>() + descs[c.first].dst_off;
+    ModelCost cost;
+    DTensor logits = rec_->run(wrap_tensor(in_ptr, {c.count, 1, rec_h, c.gw}), st_, &cost);
+    stats_.rec_flops += cost.flops;
+    stats_.rec_batches += 1;
+    OCRS_CHECK(logits.shape.size() == 3, kWrongOutput,
+               "expected recognition output to have 3 dims but it has " + std::to_string(logits.shape.size()));  // :350
+    OCRS_CHECK(logits.shape[1] == c.count, kWrongOutput, "recognition output batch dim mismatch");
+    OCRS_CHECK((size_t)logits.shape[2] == n_classes, kWrongOutput,
+               "output column count (" + std::to_string(logits.shape[2]) + ") does not match alphabet size (" +
+                   std::to_string(n_classes) + ")");  // recognition.rs:487-493
+    c.T = (int)logits.shape[0];
+    OCRS_CHECK(c.T <= c.gw, kWrongOutput, "recognition output longer than its input");
+    stats_.n_timesteps += (int64_t)c.T * c.count;
+    ctc_scratch_.reserve((size_t)c.count * c.T * 4 + 4);
+    int32_t* o = ctc_out_.as<int32_t>() + c.out_off;
+    img::ctc_greedy(logits.data, c.T, c.count, (int)n_classes, has_excluded_ ? d_excluded_.as<uint8_t>() : nullptr,
+                    ctc_scratch_.as<int32_t>(), o, o + (int64_t)c.count * c.gw, o + (int64_t)c.count * c.gw * 2, st_);
+    // ctc_scratch_ is reused by the next chunk on the same stream: ordering is preserved.
+  }
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(h_pin_.ptr, ctc_out_.ptr, (size_t)out_total * 4, cudaMemcpyDeviceToHost, st_));
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+
+  // ---- host: CTC steps -> characters with boxes (recognition.rs:241-311) ----
+  const int32_t* h = h_pin_.as<int32_t>();
+  for (const auto& c : chunks) {
+    const int32_t* lab = h + c.out_off;
+    const int32_t* pos = lab + (int64_t)c.count * c.gw;
+    const int32_t* cnt = pos + (int64_t)c.count * c.gw;
+    for (int b = 0; b < c.count; ++b) {
+      const RecLine& rl = lines[order[c.first + b]];
+      const RectI line_rect = rl.rect;
+      float x_scale = (float)geom::rwidth(line_rect) / (float)rl.resized_width;
+      uint32_t downsample = geom::f2u(roundf((float)c.gw / (float)c.T));  // :254-255
+      int n_steps = cnt[b];
+      TextLine tl;
+      for (int i = 0; i < n_steps; ++i) {
+        uint32_t label = (uint32_t)lab[(int64_t)b * c.T + i];
+        uint32_t start_u = (uint32_t)pos[(int64_t)b * c.T + i] * downsample;
+        uint32_t end_u = (i + 1 < n_steps) ? (uint32_t)pos[(int64_t)b * c.T + i + 1] * downsample : rl.resized_width;
+        int start_x = line_rect.left + geom::f2i((float)start_u * x_scale);  // :271-272
+        int end_x = line_rect.left + geom::f2i((float)end_u * x_scale);
+        if (start_x >= line_rect.right) continue;  // :278
+        uint32_t ch = (label >= 1 && label - 1 < alphabet_.size()) ? alphabet_[label - 1] : (uint32_t)'?';
+        RectI r;
+        bool ok = layout::polygon_slice_bounding_rect(rl.poly, start_x, end_x, &r);
+        OCRS_CHECK(ok, kInternal, "invalid X coords");  // recognition.rs:299 (expect)
+        tl.chars.push_back(TextChar{ch, r});
+      }
+      tl.present = !tl.chars.empty();
+      result[rl.page][rl.index] = std::move(tl);
+      stats_.n_lines += 1;
+    }
+  }
+  return result;
+}
+
+std::vector<float> Engine::prepare_recognition_input(const OcrInput& in, const std::vector<RotatedRect>& line,
+                                                     int* out_h, int* out_w) {
+  OCRS_CHECK(rec_ != nullptr, kModelNotLoaded, "Recognition model not loaded");  // lib.rs:274
+  OCRS_CHECK(!line.empty(), kInvalidArg, "line has no words");
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  const int rec_h = (int)rec_input_height();
+  RectI line_rect;
+  layout::line_integral_rect(line, &line_rect);
+  uint32_t rw = layout::resized_line_width(geom::rwidth(line_rect), geom::rheight(line_rect), rec_h);
+  std::vector<PointI> poly = layout::line_polygon(line);
+  RectI pr = layout::polygon_bounding_rect(poly);
+  img::LineDesc d{};
+  std::vector<int32_t> poly_xy;
+  int non_horizontal = 0;
+  for (size_t v = 0; v < poly.size(); ++v) {
+    poly_xy.push_back(poly[v].x);
+    poly_xy.push_back(poly[v].y);
+    if (poly[v].y != poly[(v + 1) % poly.size()].y) ++non_horizontal;
+  }
+  d.poly_off = 0; d.poly_n = (int32_t)poly.size();
+  d.top = pr.top; d.left = pr.left;
+  d.lh = std::max(geom::rheight(pr), 0); d.lw = std::max(geom::rwidth(pr), 0);
+  d.resized_width = (int32_t)rw; d.group_width = (int32_t)rw;
+  d.dst_off = 0; d.cross_off = 0; d.max_cross = non_horizontal; d.page = 0;
+  const float* page_ptr = in.grey.as<float>();
+  int hw[2] = {in.H, in.W};
+  page_tab_.reserve(sizeof(float*) + 2 * sizeof(int));
+  line_desc_.reserve(sizeof(d));
+  poly_.reserve(poly_xy.size() * 4 + 4);
+  cross_.reserve((size_t)d.lh * (non_horizontal + 1) * 4 + 4);
+  rec_batch_.reserve((size_t)rec_h * rw * 4 + 4);
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(page_tab_.ptr, &page_ptr, sizeof(float*), cudaMemcpyHostToDevice, st_));
+  int* d_hw = reinterpret_cast<int*>(page_tab_.as<char>() + sizeof(float*));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(d_hw, hw, sizeof(hw), cudaMemcpyHostToDevice, st_));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(line_desc_.ptr, &d, sizeof(d), cudaMemcpyHostToDevice, st_));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(poly_.ptr, poly_xy.data(), poly_xy.size() * 4, cudaMemcpyHostToDevice, st_));
+  img::crop_lines(page_tab_.as<const float*>(), d_hw, d_hw + 1, line_desc_.as<img::LineDesc>(), 1, poly_.as<int32_t>(),
+                  cross_.as<int32_t>(), rec_batch_.as<float>(), rec_h, (int)rw, d.lh, st_);
+  std::vector<float> out((size_t)rec_h * rw);
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(out.data(), rec_batch_.ptr, out.size() * 4, cudaMemcpyDeviceToHost, st_));
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  *out_h = rec_h;
+  *out_w = (int)rw;
+  return out;
+}
+
+std::vector<std::vector<TextLine>> Engine::ocr_pages(const std::vector<const OcrInput*>& pages) {
+  auto words = detect_words(pages);
+  std::vector<std::vector<std::vector<RotatedRect>>> lines(pages.size());
+  for (size_t p = 0; p < pages.size(); ++p) lines[p] = layout::find_text_lines(words[p]);
+  return recognize_text(pages, lines);
+}
+
+}  // namespace ocrs

@@ -1,0 +1,128 @@
+// OcrEngine on one B200: the reference's public pipeline surface (ocrs/src/lib.rs:111-301) with
+// device-resident pages and batched stages.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "executor.h"
+#include "geom.h"
+#include "image_kernels.h"
+
+namespace ocrs {
+
+enum class DecodeMethod { kGreedy = 0, kBeamSearch = 1 };  // recognition.rs:199-205
+
+struct EngineParams {  // lib.rs:37-71
+  const uint8_t* detection_model = nullptr;
+  size_t detection_model_len = 0;
+  const uint8_t* recognition_model = nullptr;
+  size_t recognition_model_len = 0;
+  bool debug = false;
+  DecodeMethod decode_method = DecodeMethod::kGreedy;
+  uint32_t beam_width = 100;
+  bool has_alphabet = false;
+  std::string alphabet_utf8;
+  bool has_allowed_chars = false;
+  std::string allowed_chars_utf8;
+  int device = 0;
+};
+
+// `OcrInput` (lib.rs:125-128): greyscale page in [-0.5, 0.5], resident in HBM.
+struct OcrInput {
+  DeviceBuffer grey;  // f32 [H*W]
+  int H = 0, W = 0;
+  int device = 0;
+};
+
+struct TextChar {  // text_items.rs:47-53
+  uint32_t ch;     // Unicode scalar value
+  geom::RectI rect;
+};
+struct TextLine {  // Option<TextLine>: present == false <-> None
+  bool present = false;
+  std::vector<TextChar> chars;
+};
+
+struct StageTimes {  // milliseconds, CUDA-event timed when `debug`
+  float detect_ms = 0, recog_ms = 0;
+};
+
+class Engine {
+ public:
+  explicit Engine(const EngineParams& p);
+  ~Engine();
+
+  bool has_detector() const { return det_ != nullptr; }
+  bool has_recognizer() const { return rec_ != nullptr; }
+  int device() const { return device_; }
+  float detection_threshold() const { return text_threshold_; }  // lib.rs:282-287
+  const Model* detection_model() const { return det_.get(); }
+  const Model* recognition_model() const { return rec_.get(); }
+
+  // lib.rs:183 / preprocess.rs:149.  `pixels` is a host pointer (or a device pointer when
+  // `pixels_on_device`).  dtype 0 = u8, 1 = f32; order 0 = HWC, 1 = CHW.
+  std::unique_ptr<OcrInput> prepare_input(const void* pixels, int dtype, int order, int H, int W, int C,
+                                          bool pixels_on_device = false);
+
+  // lib.rs:207 / detection.rs:131-200 (host copy of the H x W probability map)
+  std::vector<float> detect_text_pixels(const OcrInput& in);
+  // lib.rs:193 / detection.rs:104-122, batched over pages; rects in contour-discovery order.
+  std::vector<std::vector<geom::RotatedRect>> detect_words(const std::vector<const OcrInput*>& pages);
+  // lib.rs:222
+  std::vector<std::vector<geom::RotatedRect>> find_text_lines(const std::vector<geom::RotatedRect>& words) const;
+  // lib.rs:237 / recognition.rs:404-540, batched over pages.
+  std::vector<std::vector<TextLine>> recognize_text(
+      const std::vector<const OcrInput*>& pages,
+      const std::vector<std::vector<std::vector<geom::RotatedRect>>>& lines_per_page);
+  // lib.rs:268 / recognition.rs:366-393: returns [input_height, resized_width] row-major.
+  std::vector<float> prepare_recognition_input(const OcrInput& in, const std::vector<geom::RotatedRect>& line,
+                                               int* out_h, int* out_w);
+
+  // Whole pipeline on a batch of resident pages (detect -> layout -> recognise).
+  std::vector<std::vector<TextLine>> ocr_pages(const std::vector<const OcrInput*>& pages);
+
+  const std::vector<uint32_t>& alphabet() const { return alphabet_; }
+  uint32_t rec_input_height() const;  // recognition.rs:332-337
+
+  // statistics of the last recognize_text / detect_words call (for bench / roofline math)
+  struct Stats {
+    double det_flops = 0, rec_flops = 0;
+    int64_t n_lines = 0, n_words = 0, n_timesteps = 0, rec_batches = 0;
+    int64_t kernel_launches = 0;
+  };
+  Stats stats() const { return stats_; }
+  void reset_stats() { stats_ = Stats(); }
+  void synchronize();
+
+ private:
+  struct PageScratch;  // per concurrent page: mask, labels, pools
+  PageScratch& scratch_for(int slot, int H, int W);
+
+  int device_ = 0;
+  cudaStream_t st_ = nullptr;
+  std::unique_ptr<Model> det_, rec_;
+  float text_threshold_ = 0.2f;  // detection.rs:34
+  float min_area_ = 100.0f;      // detection.rs:31
+  bool debug_ = false;
+  DecodeMethod decode_method_ = DecodeMethod::kGreedy;
+  uint32_t beam_width_ = 100;
+  std::vector<uint32_t> alphabet_;
+  bool has_excluded_ = false;
+  std::vector<uint8_t> excluded_mask_;  // per class label (index 0 = blank)
+  DeviceBuffer d_excluded_;
+  std::vector<std::unique_ptr<PageScratch>> scratch_;
+  DeviceBuffer det_in_, staging_, line_desc_, poly_, cross_, rec_batch_, ctc_scratch_, ctc_out_, page_tab_;
+  PinnedBuffer h_pin_;
+  std::mutex mu_;
+  Stats stats_;
+};
+
+std::vector<uint32_t> utf8_to_codepoints(const std::string& s);
+std::string codepoints_to_utf8(const std::vector<uint32_t>& cps);
+
+}  // namespace ocrs

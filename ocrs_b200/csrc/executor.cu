@@ -1,0 +1,681 @@
+// ONNX graph executor (host orchestration; kernels live in nn_kernels.cu).
+#include "executor.h"
+
+#include <algorithm>
+#include <cstring>
+#include <set>
+
+#include "nn_kernels.h"
+
+namespace ocrs {
+
+using onnx::Attr;
+using onnx::Node;
+using onnx::TensorData;
+
+Storage::Storage(size_t n, cudaStream_t st) : bytes(n), stream(st) {
+  if (n == 0) n = 4;
+  OCRS_CUDA_CHECK(cudaMallocAsync(&ptr, n, st));
+}
+Storage::~Storage() {
+  if (ptr && owned) cudaFreeAsync(ptr, stream);
+}
+
+void configure_device_pool(int device) {
+  cudaMemPool_t pool;
+  OCRS_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  OCRS_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+}
+
+namespace {
+
+struct Value {
+  bool is_int = false;
+  std::vector<int64_t> shape;   // for ints: shape of the int tensor
+  std::vector<int64_t> ivals;   // host ints
+  DTensor t;                    // device floats (shape mirrors `shape`)
+  const TensorData* host_f32 = nullptr;  // host copy for float initializers (pad value etc.)
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+DTensor alloc_tensor(const std::vector<int64_t>& shape, cudaStream_t st) {
+  DTensor t;
+  t.shape = shape;
+  t.storage = std::make_shared<Storage>((size_t)t.numel() * sizeof(float), st);
+  t.data = reinterpret_cast<float*>(t.storage->ptr);
+  return t;
+}
+
+Value dev_value(DTensor t) {
+  Value v;
+  v.shape = t.shape;
+  v.t = std::move(t);
+  return v;
+}
+Value int_value(std::vector<int64_t> vals, std::vector<int64_t> shape) {
+  Value v;
+  v.is_int = true;
+  v.ivals = std::move(vals);
+  v.shape = std::move(shape);
+  return v;
+}
+
+int64_t norm_axis(int64_t a, int64_t nd) {
+  if (a < 0) a += nd;
+  OCRS_CHECK(a >= 0 && a < nd, kRunFailed, "axis out of range");
+  return a;
+}
+
+std::shared_ptr<Storage> upload(const void* host, size_t bytes) {
+  auto s = std::make_shared<Storage>(bytes, (cudaStream_t) nullptr);
+  OCRS_CUDA_CHECK(cudaMemcpy(s->ptr, host, bytes, cudaMemcpyHostToDevice));
+  return s;
+}
+
+}  // namespace
+
+struct Model::Impl {
+  // per GRU node: Wb [D][3H], Rb [D][3H]
+  std::map<int, std::pair<std::shared_ptr<Storage>, std::shared_ptr<Storage>>> gru_bias;
+  std::vector<std::string> out_rename;  // per node: published name of output 0 ("" = own name)
+};
+
+Model::Model() = default;
+Model::~Model() = default;
+
+std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device) {
+  std::unique_ptr<Model> m(new Model());
+  m->graph_ = onnx::parse_model(bytes, len);
+  m->device_ = device;
+  OCRS_CUDA_CHECK(cudaSetDevice(device));
+  configure_device_pool(device);
+  const auto& g = m->graph_;
+  OCRS_CHECK(!g.inputs.empty(), kModelLoad, "model has no inputs");  // model.rs:24
+  OCRS_CHECK(!g.outputs.empty(), kModelLoad, "model has no outputs");
+  OCRS_CHECK(!g.inputs[0].dims.empty(), kModelLoad, "model does not specify expected input shape");  // model.rs:28
+  m->input_shape_ = g.inputs[0].dims;
+
+  static const std::set<std::string> kSupported = {
+      "Add", "AveragePool", "Cast", "Concat", "ConstantOfShape", "Conv", "ConvTranspose", "GRU", "Gather",
+      "LogSoftmax", "MatMul", "MaxPool", "Pad", "Relu", "Reshape", "Shape", "Sigmoid", "Slice", "Transpose",
+      "Unsqueeze", "Squeeze", "Identity", "Constant", "Tanh"};
+  for (const auto& n : g.nodes)
+    OCRS_CHECK(kSupported.count(n.op), kModelLoad, "unsupported ONNX operator: " + n.op);
+
+  auto impl = std::make_unique<Impl>();
+  const int nn_ = (int)g.nodes.size();
+  m->fuse_relu_.assign(nn_, 0);
+  m->skip_.assign(nn_, 0);
+  m->fused_bias_.assign(nn_, "");
+  impl->out_rename.assign(nn_, "");
+
+  // consumer counts over the raw graph
+  std::map<std::string, int> consumers;
+  std::map<std::string, int> consumer_node;  // last consumer node index (valid when count == 1)
+  for (int i = 0; i < nn_; ++i)
+    for (const auto& in : g.nodes[i].inputs)
+      if (!in.empty()) { consumers[in]++; consumer_node[in] = i; }
+  std::set<std::string> graph_outs;
+  for (const auto& o : g.outputs) graph_outs.insert(o.name);
+
+  // fusions: Conv/ConvTranspose -> Relu ; MatMul -> Add(const bias)
+  for (int i = 0; i < nn_; ++i) {
+    const Node& n = g.nodes[i];
+    if (n.outputs.empty()) continue;
+    const std::string& out = n.outputs[0];
+    if (consumers[out] != 1 || graph_outs.count(out)) continue;
+    int j = consumer_node[out];
+    const Node& c = g.nodes[j];
+    if ((n.op == "Conv" || n.op == "ConvTranspose") && c.op == "Relu") {
+      m->fuse_relu_[i] = 1;
+      m->skip_[j] = 1;
+      impl->out_rename[i] = c.outputs[0];
+    } else if (n.op == "MatMul" && c.op == "Add" && c.inputs.size() == 2) {
+      const std::string& other = c.inputs[0] == out ? c.inputs[1] : c.inputs[0];
+      auto it = g.initializers.find(other);
+      auto wit = n.inputs.size() == 2 ? g.initializers.find(n.inputs[1]) : g.initializers.end();
+      if (it != g.initializers.end() && it->second.dtype == onnx::kFloat && it->second.dims.size() == 1 &&
+          wit != g.initializers.end() && wit->second.dims.size() == 2 &&
+          wit->second.dims[1] == it->second.dims[0]) {
+        m->fused_bias_[i] = other;
+        m->skip_[j] = 1;
+        impl->out_rename[i] = c.outputs[0];
+      }
+    }
+  }
+
+  // remaining-use counts for the fused schedule
+  for (int i = 0; i < nn_; ++i) {
+    if (m->skip_[i]) continue;
+    for (const auto& in : g.nodes[i].inputs)
+      if (!in.empty()) m->use_count_[in]++;
+  }
+  for (const auto& o : g.outputs) m->use_count_[o.name] += 1 << 20;
+
+  // upload float initializers
+  for (const auto& kv : g.initializers) {
+    if (kv.second.dtype != onnx::kFloat) continue;
+    m->dev_weights_[kv.first] = upload(kv.second.raw.data(), std::max<size_t>(kv.second.raw.size(), 4));
+    m->weight_bytes_ += kv.second.raw.size();
+  }
+  // per-node weight re-layouts
+  for (int i = 0; i < nn_; ++i) {
+    const Node& n = g.nodes[i];
+    if (n.op == "MatMul" && n.inputs.size() == 2) {
+      auto it = g.initializers.find(n.inputs[1]);
+      if (it != g.initializers.end() && it->second.dims.size() == 2 && !m->dev_weights_t_.count(n.inputs[1])) {
+        int64_t K = it->second.dims[0], N = it->second.dims[1];
+        std::vector<float> t((size_t)(K * N));
+        const float* w = it->second.f32();
+        for (int64_t k = 0; k < K; ++k)
+          for (int64_t c = 0; c < N; ++c) t[(size_t)(c * K + k)] = w[k * N + c];
+        m->dev_weights_t_[n.inputs[1]] = upload(t.data(), t.size() * 4);
+      }
+    } else if (n.op == "GRU") {
+      OCRS_CHECK(n.inputs.size() >= 3, kModelLoad, "GRU: missing inputs");
+      auto wit = g.initializers.find(n.inputs[1]);
+      auto rit = g.initializers.find(n.inputs[2]);
+      OCRS_CHECK(wit != g.initializers.end() && rit != g.initializers.end(), kModelLoad,
+                 "GRU: W and R must be initializers");
+      int64_t D = wit->second.dims[0], H3 = wit->second.dims[1];
+      std::vector<float> wb((size_t)(D * H3), 0.f), rb((size_t)(D * H3), 0.f);
+      if (n.inputs.size() > 3 && !n.inputs[3].empty()) {
+        auto bit = g.initializers.find(n.inputs[3]);
+        OCRS_CHECK(bit != g.initializers.end(), kModelLoad, "GRU: B must be an initializer");
+        const float* b = bit->second.f32();
+        for (int64_t d = 0; d < D; ++d) {
+          std::memcpy(&wb[(size_t)(d * H3)], b + d * 2 * H3, (size_t)H3 * 4);
+          std::memcpy(&rb[(size_t)(d * H3)], b + d * 2 * H3 + H3, (size_t)H3 * 4);
+        }
+      }
+      impl->gru_bias[i] = {upload(wb.data(), wb.size() * 4), upload(rb.data(), rb.size() * 4)};
+      OCRS_CHECK(n.attr_i("linear_before_reset", 0) != 0, kModelLoad,
+                 "GRU with linear_before_reset=0 is not supported (PyTorch exports use 1)");
+    }
+  }
+  m->impl_ = std::move(impl);
+  return m;
+}
+
+DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost) const {
+  const Impl* impl = impl_.get();
+  const auto& g = graph_;
+  OCRS_CHECK(input.shape.size() == input_shape_.size(), kRunFailed,
+             "input rank " + std::to_string(input.shape.size()) + " does not match model input rank " +
+                 std::to_string(input_shape_.size()));
+  for (size_t d = 0; d < input_shape_.size(); ++d)
+    OCRS_CHECK(input_shape_[d] < 0 || input_shape_[d] == input.shape[d], kRunFailed,
+               "input dim " + std::to_string(d) + " = " + std::to_string(input.shape[d]) + " but model expects " +
+                   std::to_string(input_shape_[d]));
+
+  std::map<std::string, Value> env;
+  std::map<std::string, int> remaining = use_count_;
+  env[g.inputs[0].name] = dev_value(input);
+  double flops = 0;
+
+  auto get = [&](const std::string& name) -> Value {
+    auto it = env.find(name);
+    if (it != env.end()) return it->second;
+    auto ii = g.initializers.find(name);
+    OCRS_CHECK(ii != g.initializers.end(), kRunFailed, "value not found: " + name);
+    const TensorData& td = ii->second;
+    if (td.dtype == onnx::kFloat) {
+      Value v;
+      v.shape = td.dims;
+      v.t.shape = td.dims;
+      v.t.storage = dev_weights_.at(name);
+      v.t.data = reinterpret_cast<float*>(v.t.storage->ptr);
+      v.host_f32 = &td;
+      return v;
+    }
+    return int_value(td.as_int64(), td.dims);
+  };
+
+  for (int ni = 0; ni < (int)g.nodes.size(); ++ni) {
+    if (skip_[ni]) continue;
+    const Node& n = g.nodes[ni];
+    std::vector<Value> in;
+    std::vector<bool> present;
+    for (const auto& name : n.inputs) {
+      present.push_back(!name.empty());
+      in.push_back(name.empty() ? Value() : get(name));
+    }
+    auto has = [&](size_t i) { return i < in.size() && present[i]; };
+    std::vector<Value> out;
+    const std::string& op = n.op;
+
+    if (op == "Conv") {
+      const Value& X = in[0];
+      const Value& W = in[1];
+      OCRS_CHECK(!X.is_int && X.shape.size() == 4 && W.shape.size() == 4, kRunFailed, "Conv: expected 4-D x/w");
+      OCRS_CHECK(n.attr_s("auto_pad", "NOTSET") == "NOTSET", kRunFailed, "Conv: auto_pad unsupported");
+      auto pads = n.attr_ints("pads", {0, 0, 0, 0});
+      auto strides = n.attr_ints("strides", {1, 1});
+      auto dil = n.attr_ints("dilations", {1, 1});
+      nn::ConvParams p;
+      p.N = (int)X.shape[0]; p.C = (int)X.shape[1]; p.H = (int)X.shape[2]; p.W = (int)X.shape[3];
+      p.K = (int)W.shape[0]; p.R = (int)W.shape[2]; p.S = (int)W.shape[3];
+      p.groups = (int)n.attr_i("group", 1);
+      OCRS_CHECK(W.shape[1] * p.groups == p.C, kRunFailed, "Conv: channel mismatch");
+      p.stride_h = (int)strides[0]; p.stride_w = (int)strides[1];
+      p.pad_t = (int)pads[0]; p.pad_l = (int)pads[1];
+      p.dil_h = (int)dil[0]; p.dil_w = (int)dil[1];
+      p.OH = (int)((p.H + pads[0] + pads[2] - dil[0] * (p.R - 1) - 1) / strides[0] + 1);
+      p.OW = (int)((p.W + pads[1] + pads[3] - dil[1] * (p.S - 1) - 1) / strides[1] + 1);
+      p.relu = fuse_relu_[ni];
+      DTensor Y = alloc_tensor({p.N, p.K, p.OH, p.OW}, st);
+      nn::conv2d(X.t.data, W.t.data, has(2) ? in[2].t.data : nullptr, Y.data, p, st);
+      flops += 2.0 * p.N * p.K * p.OH * p.OW * (double)(p.C / p.groups) * p.R * p.S;
+      out.push_back(dev_value(Y));
+    } else if (op == "ConvTranspose") {
+      const Value& X = in[0];
+      const Value& W = in[1];
+      OCRS_CHECK(X.shape.size() == 4 && W.shape.size() == 4, kRunFailed, "ConvTranspose: expected 4-D x/w");
+      auto pads = n.attr_ints("pads", {0, 0, 0, 0});
+      auto strides = n.attr_ints("strides", {1, 1});
+      auto opad = n.attr_ints("output_padding", {0, 0});
+      auto dil = n.attr_ints("dilations", {1, 1});
+      OCRS_CHECK(dil[0] == 1 && dil[1] == 1, kRunFailed, "ConvTranspose: dilation unsupported");
+      nn::ConvTParams p;
+      p.N = (int)X.shape[0]; p.C = (int)X.shape[1]; p.H = (int)X.shape[2]; p.W = (int)X.shape[3];
+      p.groups = (int)n.attr_i("group", 1);
+      p.K = (int)W.shape[1] * p.groups; p.R = (int)W.shape[2]; p.S = (int)W.shape[3];
+      OCRS_CHECK(W.shape[0] == p.C, kRunFailed, "ConvTranspose: channel mismatch");
+      p.stride_h = (int)strides[0]; p.stride_w = (int)strides[1];
+      p.pad_t = (int)pads[0]; p.pad_l = (int)pads[1];
+      p.OH = (int)((p.H - 1) * strides[0] - pads[0] - pads[2] + p.R + opad[0]);
+      p.OW = (int)((p.W - 1) * strides[1] - pads[1] - pads[3] + p.S + opad[1]);
+      p.relu = fuse_relu_[ni];
+      DTensor Y = alloc_tensor({p.N, p.K, p.OH, p.OW}, st);
+      nn::conv_transpose2d(X.t.data, W.t.data, has(2) ? in[2].t.data : nullptr, Y.data, p, st);
+      flops += 2.0 * p.N * p.C * p.H * p.W * (double)(p.K / p.groups) * p.R * p.S;
+      out.push_back(dev_value(Y));
+    } else if (op == "MaxPool" || op == "AveragePool") {
+      const Value& X = in[0];
+      OCRS_CHECK(X.shape.size() == 4, kRunFailed, op + ": expected 4-D input");
+      OCRS_CHECK(n.attr_i("ceil_mode", 0) == 0, kRunFailed, op + ": ceil_mode unsupported");
+      auto ks = n.attr_ints("kernel_shape", {});
+      OCRS_CHECK(ks.size() == 2, kRunFailed, op + ": kernel_shape must be 2-D");
+      auto pads = n.attr_ints("pads", {0, 0, 0, 0});
+      auto strides = n.attr_ints("strides", {1, 1});
+      nn::PoolParams p;
+      p.NC = (int)(X.shape[0] * X.shape[1]); p.H = (int)X.shape[2]; p.W = (int)X.shape[3];
+      p.R = (int)ks[0]; p.S = (int)ks[1];
+      p.stride_h = (int)strides[0]; p.stride_w = (int)strides[1];
+      p.pad_t = (int)pads[0]; p.pad_l = (int)pads[1];
+      p.OH = (int)((p.H + pads[0] + pads[2] - p.R) / strides[0] + 1);
+      p.OW = (int)((p.W + pads[1] + pads[3] - p.S) / strides[1] + 1);
+      p.count_include_pad = (int)n.attr_i("count_include_pad", 0);
+      DTensor Y = alloc_tensor({X.shape[0], X.shape[1], p.OH, p.OW}, st);
+      if (op == "MaxPool") nn::max_pool2d(X.t.data, Y.data, p, st);
+      else nn::avg_pool2d(X.t.data, Y.data, p, st);
+      out.push_back(dev_value(Y));
+    } else if (op == "Relu" || op == "Sigmoid" || op == "Tanh") {
+      const Value& X = in[0];
+      DTensor Y = alloc_tensor(X.shape, st);
+      if (op == "Relu") nn::relu(X.t.data, Y.data, X.numel(), st);
+      else if (op == "Sigmoid") nn::sigmoid(X.t.data, Y.data, X.numel(), st);
+      else nn::tanh_op(X.t.data, Y.data, X.numel(), st);
+      out.push_back(dev_value(Y));
+    } else if (op == "Add") {
+      if (in[0].is_int && in[1].is_int) {
+        const Value& A = in[0].numel() >= in[1].numel() ? in[0] : in[1];
+        const Value& B = in[0].numel() >= in[1].numel() ? in[1] : in[0];
+        OCRS_CHECK(B.numel() > 0 && A.numel() % B.numel() == 0, kRunFailed, "Add: int broadcast unsupported");
+        std::vector<int64_t> r(A.ivals);
+        for (size_t i = 0; i < r.size(); ++i) r[i] += B.ivals[i % B.ivals.size()];
+        out.push_back(int_value(r, A.shape));
+      } else {
+        const Value& A = in[0].numel() >= in[1].numel() ? in[0] : in[1];
+        const Value& B = in[0].numel() >= in[1].numel() ? in[1] : in[0];
+        OCRS_CHECK(!A.is_int && !B.is_int, kRunFailed, "Add: mixed int/float");
+        // B's shape must be a suffix of A's (after stripping leading 1s)
+        std::vector<int64_t> bs = B.shape;
+        while (!bs.empty() && bs.front() == 1) bs.erase(bs.begin());
+        OCRS_CHECK(bs.size() <= A.shape.size() &&
+                       std::equal(bs.rbegin(), bs.rend(), A.shape.rbegin()),
+                   kRunFailed, "Add: only suffix broadcasting is supported");
+        DTensor Y = alloc_tensor(A.shape, st);
+        nn::add_bcast_suffix(A.t.data, B.t.data, Y.data, A.numel(), std::max<int64_t>(B.numel(), 1), st);
+        out.push_back(dev_value(Y));
+      }
+    } else if (op == "MatMul") {
+      const Value& A = in[0];
+      const Value& B = in[1];
+      OCRS_CHECK(!A.is_int && !B.is_int && B.shape.size() == 2 && !A.shape.empty(), kRunFailed,
+                 "MatMul: expected [..., K] x [K, N]");
+      int64_t K = B.shape[0], N = B.shape[1];
+      OCRS_CHECK(A.shape.back() == K, kRunFailed, "MatMul: inner dimension mismatch");
+      int64_t M = A.numel() / K;
+      std::vector<int64_t> oshape(A.shape.begin(), A.shape.end() - 1);
+      oshape.push_back(N);
+      DTensor Y = alloc_tensor(oshape, st);
+      const float* Bt;
+      DTensor tmp;
+      auto wt = dev_weights_t_.find(n.inputs[1]);
+      if (wt != dev_weights_t_.end()) {
+        Bt = reinterpret_cast<const float*>(wt->second->ptr);
+      } else {
+        tmp = alloc_tensor({N, K}, st);
+        int perm[2] = {1, 0};
+        nn::permute(B.t.data, tmp.data, B.shape.data(), perm, 2, st);
+        Bt = tmp.data;
+      }
+      const float* bias = nullptr;
+      if (!fused_bias_[ni].empty()) bias = reinterpret_cast<const float*>(dev_weights_.at(fused_bias_[ni])->ptr);
+      nn::sgemm_nt(A.t.data, Bt, bias, Y.data, (int)M, (int)N, (int)K, 0, st);
+      flops += 2.0 * M * N * K;
+      out.push_back(dev_value(Y));
+    } else if (op == "LogSoftmax") {
+      const Value& X = in[0];
+      int64_t axis = norm_axis(n.attr_i("axis", -1), (int64_t)X.shape.size());
+      OCRS_CHECK(axis == (int64_t)X.shape.size() - 1, kRunFailed, "LogSoftmax: only the last axis is supported");
+      DTensor Y = alloc_tensor(X.shape, st);
+      int cols = (int)X.shape.back();
+      nn::log_softmax_lastdim(X.t.data, Y.data, X.numel() / std::max(cols, 1), cols, st);
+      out.push_back(dev_value(Y));
+    } else if (op == "Concat") {
+      OCRS_CHECK(!in.empty(), kRunFailed, "Concat: no inputs");
+      if (in[0].is_int) {
+        std::vector<int64_t> r;
+        for (auto& v : in) {
+          OCRS_CHECK(v.is_int && v.shape.size() <= 1, kRunFailed, "Concat: int inputs must be 1-D");
+          r.insert(r.end(), v.ivals.begin(), v.ivals.end());
+        }
+        int64_t len = (int64_t)r.size();
+        out.push_back(int_value(std::move(r), {len}));
+      } else {
+        int64_t nd = (int64_t)in[0].shape.size();
+        int64_t axis = norm_axis(n.attr_i("axis", 0), nd);
+        std::vector<int64_t> oshape = in[0].shape;
+        oshape[axis] = 0;
+        for (auto& v : in) {
+          OCRS_CHECK(!v.is_int && (int64_t)v.shape.size() == nd, kRunFailed, "Concat: rank mismatch");
+          for (int64_t d = 0; d < nd; ++d)
+            OCRS_CHECK(d == axis || v.shape[d] == in[0].shape[d], kRunFailed, "Concat: shape mismatch");
+          oshape[axis] += v.shape[axis];
+        }
+        DTensor Y = alloc_tensor(oshape, st);
+        int64_t outer = 1, inner = 1;
+        for (int64_t d = 0; d < axis; ++d) outer *= oshape[d];
+        for (int64_t d = axis + 1; d < nd; ++d) inner *= oshape[d];
+        int64_t off = 0;
+        for (auto& v : in) {
+          nn::concat_copy(v.t.data, Y.data, outer, v.shape[axis], oshape[axis], off, inner, st);
+          off += v.shape[axis];
+        }
+        out.push_back(dev_value(Y));
+      }
+    } else if (op == "Transpose") {
+      const Value& X = in[0];
+      int nd = (int)X.shape.size();
+      std::vector<int64_t> dflt;
+      for (int d = nd - 1; d >= 0; --d) dflt.push_back(d);
+      auto perm64 = n.attr_ints("perm", dflt);
+      OCRS_CHECK((int)perm64.size() == nd && !X.is_int, kRunFailed, "Transpose: bad perm");
+      std::vector<int> perm(perm64.begin(), perm64.end());
+      std::vector<int64_t> oshape(nd);
+      for (int d = 0; d < nd; ++d) oshape[d] = X.shape[perm[d]];
+      DTensor Y = alloc_tensor(oshape, st);
+      nn::permute(X.t.data, Y.data, X.shape.data(), perm.data(), nd, st);
+      out.push_back(dev_value(Y));
+    } else if (op == "Reshape") {
+      const Value& X = in[0];
+      OCRS_CHECK(in[1].is_int, kRunFailed, "Reshape: shape must be an int tensor");
+      std::vector<int64_t> shp = in[1].ivals;
+      bool allowzero = n.attr_i("allowzero", 0) != 0;
+      int64_t known = 1, infer = -1;
+      for (size_t d = 0; d < shp.size(); ++d) {
+        if (shp[d] == 0 && !allowzero) {
+          OCRS_CHECK(d < X.shape.size(), kRunFailed, "Reshape: 0 dim out of range");
+          shp[d] = X.shape[d];
+        }
+        if (shp[d] == -1) infer = (int64_t)d;
+        else known *= shp[d];
+      }
+      if (infer >= 0) shp[infer] = known ? X.numel() / known : 0;
+      Value v = X;
+      v.shape = shp;
+      int64_t cnt = 1;
+      for (auto d : shp) cnt *= d;
+      OCRS_CHECK(cnt == X.numel(), kRunFailed, "Reshape: element count mismatch");
+      if (!v.is_int) v.t.shape = shp;
+      out.push_back(v);
+    } else if (op == "Identity") {
+      out.push_back(in[0]);
+    } else if (op == "Constant") {
+      const Attr* a = n.find("value");
+      OCRS_CHECK(a && a->kind == Attr::kTensor, kRunFailed, "Constant: only tensor values are supported");
+      if (a->t.dtype == onnx::kFloat) {
+        DTensor Y = alloc_tensor(a->t.dims, st);
+        OCRS_CUDA_CHECK(cudaMemcpyAsync(Y.data, a->t.raw.data(), a->t.raw.size(), cudaMemcpyHostToDevice, st));
+        OCRS_CUDA_CHECK(cudaStreamSynchronize(st));
+        Value v = dev_value(Y);
+        v.host_f32 = &a->t;
+        out.push_back(v);
+      } else {
+        out.push_back(int_value(a->t.as_int64(), a->t.dims));
+      }
+    } else if (op == "Shape") {
+      const Value& X = in[0];
+      int64_t nd = (int64_t)X.shape.size();
+      int64_t s = n.attr_i("start", 0), e = n.attr_i("end", nd);
+      if (s < 0) s += nd;
+      if (e < 0) e += nd;
+      s = std::min(std::max<int64_t>(s, 0), nd);
+      e = std::min(std::max<int64_t>(e, 0), nd);
+      std::vector<int64_t> r(X.shape.begin() + s, X.shape.begin() + std::max(s, e));
+      int64_t len = (int64_t)r.size();
+      out.push_back(int_value(std::move(r), {len}));
+    } else if (op == "Gather") {
+      OCRS_CHECK(in[0].is_int && in[1].is_int && in[0].shape.size() == 1, kRunFailed,
+                 "Gather: only 1-D integer data is supported (shape arithmetic)");
+      OCRS_CHECK(norm_axis(n.attr_i("axis", 0), 1) == 0, kRunFailed, "Gather: bad axis");
+      std::vector<int64_t> r;
+      for (auto idx : in[1].ivals) {
+        if (idx < 0) idx += (int64_t)in[0].ivals.size();
+        OCRS_CHECK(idx >= 0 && idx < (int64_t)in[0].ivals.size(), kRunFailed, "Gather: index out of range");
+        r.push_back(in[0].ivals[(size_t)idx]);
+      }
+      out.push_back(int_value(std::move(r), in[1].shape));
+    } else if (op == "Unsqueeze" || op == "Squeeze") {
+      Value v = in[0];
+      std::vector<int64_t> axes;
+      if (has(1)) axes = in[1].ivals;
+      else axes = n.attr_ints("axes", {});
+      std::vector<int64_t> shp = v.shape;
+      if (op == "Unsqueeze") {
+        int64_t nd = (int64_t)shp.size() + (int64_t)axes.size();
+        for (auto& a : axes) a = norm_axis(a, nd);
+        std::sort(axes.begin(), axes.end());
+        for (auto a : axes) shp.insert(shp.begin() + a, 1);
+      } else {
+        int64_t nd = (int64_t)shp.size();
+        if (axes.empty()) {
+          std::vector<int64_t> s2;
+          for (auto d : shp) if (d != 1) s2.push_back(d);
+          shp = s2;
+        } else {
+          for (auto& a : axes) a = norm_axis(a, nd);
+          std::sort(axes.rbegin(), axes.rend());
+          for (auto a : axes) {
+            OCRS_CHECK(shp[a] == 1, kRunFailed, "Squeeze: dim is not 1");
+            shp.erase(shp.begin() + a);
+          }
+        }
+      }
+      v.shape = shp;
+      if (!v.is_int) v.t.shape = shp;
+      out.push_back(v);
+    } else if (op == "Slice") {
+      const Value& X = in[0];
+      OCRS_CHECK(has(1) && has(2) && in[1].is_int && in[2].is_int, kRunFailed, "Slice: starts/ends required");
+      size_t k = in[1].ivals.size();
+      std::vector<int64_t> axes(k), steps(k, 1);
+      for (size_t i = 0; i < k; ++i) axes[i] = (int64_t)i;
+      if (has(3)) axes = in[3].ivals;
+      if (has(4)) steps = in[4].ivals;
+      int64_t nd = (int64_t)X.shape.size();
+      std::vector<int64_t> begin(nd, 0), size = X.shape;
+      for (size_t i = 0; i < k; ++i) {
+        OCRS_CHECK(steps[i] == 1, kRunFailed, "Slice: only step 1 is supported");
+        int64_t ax = norm_axis(axes[i], nd), dim = X.shape[ax];
+        int64_t s = in[1].ivals[i], e = in[2].ivals[i];
+        if (s < 0) s += dim;
+        if (e < 0) e += dim;
+        s = std::min(std::max<int64_t>(s, 0), dim);
+        e = std::min(std::max<int64_t>(e, 0), dim);
+        begin[ax] = s;
+        size[ax] = std::max<int64_t>(e - s, 0);
+      }
+      if (X.is_int) {
+        OCRS_CHECK(nd == 1, kRunFailed, "Slice: int data must be 1-D");
+        std::vector<int64_t> r(X.ivals.begin() + begin[0], X.ivals.begin() + begin[0] + size[0]);
+        out.push_back(int_value(std::move(r), {size[0]}));
+      } else {
+        OCRS_CHECK(nd <= 4, kRunFailed, "Slice: rank > 4");
+        int64_t ish[4] = {1, 1, 1, 1}, osh[4] = {1, 1, 1, 1}, bg[4] = {0, 0, 0, 0};
+        for (int64_t d = 0; d < nd; ++d) {
+          ish[4 - nd + d] = X.shape[d];
+          osh[4 - nd + d] = size[d];
+          bg[4 - nd + d] = -begin[d];
+        }
+        DTensor Y = alloc_tensor(size, st);
+        nn::pad4d(X.t.data, Y.data, ish, bg, osh, 0.f, st);
+        out.push_back(dev_value(Y));
+      }
+    } else if (op == "Cast") {
+      int64_t to = n.attr_i("to", onnx::kFloat);
+      const Value& X = in[0];
+      if (X.is_int) {
+        OCRS_CHECK(to == onnx::kInt64 || to == onnx::kInt32, kRunFailed, "Cast: int -> float unsupported");
+        out.push_back(X);
+      } else {
+        OCRS_CHECK(to == onnx::kFloat, kRunFailed, "Cast: float -> int unsupported");
+        out.push_back(X);
+      }
+    } else if (op == "ConstantOfShape") {
+      OCRS_CHECK(in[0].is_int, kRunFailed, "ConstantOfShape: shape must be ints");
+      const Attr* a = n.find("value");
+      if (a && a->kind == Attr::kTensor && a->t.dtype != onnx::kFloat) {
+        int64_t cnt = 1;
+        for (auto d : in[0].ivals) cnt *= d;
+        auto vals = a->t.as_int64();
+        out.push_back(int_value(std::vector<int64_t>((size_t)cnt, vals.empty() ? 0 : vals[0]), in[0].ivals));
+      } else {
+        float v = (a && a->kind == Attr::kTensor && a->t.numel() > 0) ? a->t.f32()[0] : 0.f;
+        DTensor Y = alloc_tensor(in[0].ivals, st);
+        nn::fill(Y.data, v, Y.numel(), st);
+        out.push_back(dev_value(Y));
+      }
+    } else if (op == "Pad") {
+      const Value& X = in[0];
+      OCRS_CHECK(n.attr_s("mode", "constant") == "constant", kRunFailed, "Pad: only constant mode");
+      std::vector<int64_t> pads;
+      if (has(1)) pads = in[1].ivals;
+      else pads = n.attr_ints("pads", {});
+      float value = n.attr_f("value", 0.f);
+      if (has(2)) {
+        OCRS_CHECK(in[2].host_f32 != nullptr, kRunFailed, "Pad: constant_value must be an initializer");
+        if (in[2].host_f32->numel() > 0) value = in[2].host_f32->f32()[0];
+      }
+      int64_t nd = (int64_t)X.shape.size();
+      OCRS_CHECK(nd <= 4 && !X.is_int, kRunFailed, "Pad: rank > 4");
+      std::vector<int64_t> axes;
+      if (has(3)) axes = in[3].ivals;
+      else for (int64_t d = 0; d < nd; ++d) axes.push_back(d);
+      OCRS_CHECK(pads.size() == 2 * axes.size(), kRunFailed, "Pad: pads size mismatch");
+      std::vector<int64_t> begin(nd, 0), end(nd, 0);
+      for (size_t i = 0; i < axes.size(); ++i) {
+        int64_t ax = norm_axis(axes[i], nd);
+        begin[ax] = pads[i];
+        end[ax] = pads[i + axes.size()];
+      }
+      std::vector<int64_t> oshape(nd);
+      int64_t ish[4] = {1, 1, 1, 1}, osh[4] = {1, 1, 1, 1}, bg[4] = {0, 0, 0, 0};
+      for (int64_t d = 0; d < nd; ++d) {
+        oshape[d] = X.shape[d] + begin[d] + end[d];
+        OCRS_CHECK(oshape[d] >= 0, kRunFailed, "Pad: negative output dim");
+        ish[4 - nd + d] = X.shape[d];
+        osh[4 - nd + d] = oshape[d];
+        bg[4 - nd + d] = begin[d];
+      }
+      DTensor Y = alloc_tensor(oshape, st);
+      nn::pad4d(X.t.data, Y.data, ish, bg, osh, value, st);
+      out.push_back(dev_value(Y));
+    } else if (op == "GRU") {
+      const Value& X = in[0];
+      const Value& W = in[1];
+      const Value& R = in[2];
+      OCRS_CHECK(X.shape.size() == 3 && W.shape.size() == 3 && R.shape.size() == 3, kRunFailed, "GRU: bad ranks");
+      OCRS_CHECK(!has(4), kRunFailed, "GRU: sequence_lens unsupported");
+      OCRS_CHECK(n.attr_i("layout", 0) == 0, kRunFailed, "GRU: layout=1 unsupported");
+      int T = (int)X.shape[0], N = (int)X.shape[1], I = (int)X.shape[2];
+      int D = (int)W.shape[0], H = (int)n.attr_i("hidden_size", W.shape[1] / 3);
+      OCRS_CHECK(W.shape[1] == 3 * H && W.shape[2] == I && R.shape[1] == 3 * H && R.shape[2] == H, kRunFailed,
+                 "GRU: weight shape mismatch");
+      std::string dir = n.attr_s("direction", "forward");
+      OCRS_CHECK((dir == "bidirectional") == (D == 2), kRunFailed, "GRU: direction/num_directions mismatch");
+      int rev[2] = {dir == "reverse" ? 1 : 0, 1};
+      const auto& gb = impl->gru_bias.at(ni);
+      const float* Wb = reinterpret_cast<const float*>(gb.first->ptr);
+      const float* Rb = reinterpret_cast<const float*>(gb.second->ptr);
+      DTensor xw = alloc_tensor({D, (int64_t)T * N, 3 * H}, st);
+      for (int d = 0; d < D; ++d)
+        nn::sgemm_nt(X.t.data, W.t.data + (int64_t)d * 3 * H * I, Wb + (int64_t)d * 3 * H,
+                     xw.data + (int64_t)d * T * N * 3 * H, T * N, 3 * H, I, 0, st);
+      DTensor hA = alloc_tensor({D, N, H}, st), hB = alloc_tensor({D, N, H}, st);
+      if (has(5)) {
+        OCRS_CHECK(in[5].numel() == (int64_t)D * N * H, kRunFailed, "GRU: initial_h shape mismatch");
+        OCRS_CUDA_CHECK(cudaMemcpyAsync(hA.data, in[5].t.data, sizeof(float) * D * N * H, cudaMemcpyDeviceToDevice, st));
+      } else {
+        nn::fill(hA.data, 0.f, (int64_t)D * N * H, st);
+      }
+      DTensor Y = alloc_tensor({T, D, N, H}, st);
+      float* hin = hA.data;
+      float* hout = hB.data;
+      for (int s = 0; s < T; ++s) {
+        nn::gru_step(xw.data, R.t.data, Rb, hin, hout, Y.data, D, T, N, H, s, rev, 1, st);
+        std::swap(hin, hout);
+      }
+      flops += 2.0 * D * T * N * 3.0 * H * (I + H);
+      out.push_back(dev_value(Y));
+      if (n.outputs.size() > 1 && !n.outputs[1].empty() && remaining.count(n.outputs[1])) {
+        DTensor Yh = alloc_tensor({D, N, H}, st);
+        OCRS_CUDA_CHECK(cudaMemcpyAsync(Yh.data, hin, sizeof(float) * D * N * H, cudaMemcpyDeviceToDevice, st));
+        out.push_back(dev_value(Yh));
+      }
+    } else {
+      throw Error(kRunFailed, "unsupported operator at run time: " + op);
+    }
+
+    // publish outputs
+    for (size_t k = 0; k < out.size() && k < n.outputs.size(); ++k) {
+      std::string name = n.outputs[k];
+      if (k == 0 && !impl->out_rename[ni].empty()) name = impl->out_rename[ni];
+      if (!name.empty()) env[name] = std::move(out[k]);
+    }
+    // release inputs whose last consumer just ran
+    for (const auto& name : n.inputs) {
+      if (name.empty()) continue;
+      auto it = remaining.find(name);
+      if (it != remaining.end() && --it->second <= 0) env.erase(name);
+    }
+  }
+  auto it = env.find(g.outputs[0].name);
+  OCRS_CHECK(it != env.end() && !it->second.is_int, kWrongOutput, "graph output was not produced");
+  if (cost) {
+    cost->flops = flops;
+    cost->min_bytes = 4.0 * (double)(input.numel() + it->second.t.numel()) + (double)weight_bytes_;
+  }
+  DTensor result = it->second.t;
+  result.shape = it->second.shape;
+  return result;
+}
+
+}  // namespace ocrs

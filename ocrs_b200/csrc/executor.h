@@ -1,0 +1,87 @@
+// Graph executor: runs an ONNX graph on one GPU with the kernels in nn_kernels.cu.
+// This is the B200 implementation of the reference's `Model` seam (ocrs/src/model.rs:6-17):
+//   input_shape()  <->  Model::input_shape   (model.rs:9, rten impl :20-31)
+//   run()          <->  Model::run           (model.rs:12-16, rten impl :33-40)
+// The executor is graph-driven: operators, shapes and fusions are derived from the loaded file.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "onnx_reader.h"
+
+namespace ocrs {
+
+// Stream-ordered device allocation (cudaMallocAsync); freed on the same stream.
+struct Storage {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaStream_t stream = nullptr;
+  bool owned = true;
+  Storage(size_t n, cudaStream_t st);
+  Storage(void* p, size_t n) : ptr(p), bytes(n), owned(false) {}
+  ~Storage();
+  Storage(const Storage&) = delete;
+  Storage& operator=(const Storage&) = delete;
+};
+
+struct DTensor {
+  std::shared_ptr<Storage> storage;
+  float* data = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+struct ModelCost {
+  double flops = 0;        // 2 * MACs of Conv / ConvTranspose / MatMul / GRU for the last run
+  double min_bytes = 0;    // input + output + weights
+};
+
+class Model {
+ public:
+  // Parses an ONNX file image and uploads weights to `device`.
+  static std::unique_ptr<Model> load(const uint8_t* bytes, size_t len, int device);
+  ~Model();
+
+  // Declared shape of the first graph input; -1 = symbolic (rten::Dimension::Symbolic).
+  const std::vector<int64_t>& input_shape() const { return input_shape_; }
+  int device() const { return device_; }
+
+  // Runs the graph.  `input` lives on the device; the result is stream-ordered on `st`.
+  // Re-entrant: any number of threads may call run() on one Model with distinct streams.
+  DTensor run(const DTensor& input, cudaStream_t st, ModelCost* cost = nullptr) const;
+
+  size_t weight_bytes() const { return weight_bytes_; }
+  const onnx::Graph& graph() const { return graph_; }
+
+ private:
+  Model();
+  struct Impl;
+  std::unique_ptr<Impl> impl_;
+  onnx::Graph graph_;
+  std::vector<int64_t> input_shape_;
+  int device_ = 0;
+  size_t weight_bytes_ = 0;
+  // device copies of float initializers (name -> buffer); some re-laid-out per consumer
+  std::map<std::string, std::shared_ptr<Storage>> dev_weights_;
+  std::map<std::string, std::shared_ptr<Storage>> dev_weights_t_;  // transposed MatMul rhs
+  std::map<std::string, int> use_count_;
+  std::vector<int> fuse_relu_;     // per node: fuse a following Relu
+  std::vector<int> skip_;          // per node: folded into its producer
+  std::vector<std::string> fused_bias_;  // per MatMul node: name of bias initializer folded from Add
+  std::map<std::string, std::string> alias_;  // output name -> producer output it aliases
+};
+
+// Configures the device's default mempool to keep freed blocks cached.
+void configure_device_pool(int device);
+
+}  // namespace ocrs

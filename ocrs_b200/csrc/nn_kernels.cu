@@ -1,0 +1,562 @@
+// fp32 CUDA-core operator kernels (sm_100a).  First-generation implementations: correct and
+// coalesced; the dense 3x3 convolutions and the GRU are superseded by the tcgen05 kernels in
+// conv_tc.cu / gru_tc.cu when those are enabled (DESIGN.md "Kernels").
+#include "nn_kernels.h"
+
+#include <cfloat>
+
+#include "common.h"
+
+namespace ocrs {
+namespace nn {
+
+namespace {
+
+constexpr int kThreads = 256;
+inline int grid1d(int64_t n, int threads = kThreads) { return (int)ceil_div(n, threads); }
+
+// ---------------------------------------------------------------------------------------------
+// Generic direct convolution (any groups): one thread per output element.
+// ---------------------------------------------------------------------------------------------
+__global__ void conv_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ b, float* __restrict__ y, ConvParams p) {
+  int64_t total = (int64_t)p.N * p.K * p.OH * p.OW;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ow = idx % p.OW;
+  int oh = (idx / p.OW) % p.OH;
+  int k = (idx / ((int64_t)p.OW * p.OH)) % p.K;
+  int n = idx / ((int64_t)p.OW * p.OH * p.K);
+  int cpg = p.C / p.groups;  // in channels per group
+  int kpg = p.K / p.groups;
+  int g = k / kpg;
+  float acc = b ? b[k] : 0.f;
+  const float* wk = w + (int64_t)k * cpg * p.R * p.S;
+  for (int c = 0; c < cpg; ++c) {
+    const float* xc = x + ((int64_t)n * p.C + g * cpg + c) * p.H * p.W;
+    for (int r = 0; r < p.R; ++r) {
+      int ih = oh * p.stride_h - p.pad_t + r * p.dil_h;
+      if (ih < 0 || ih >= p.H) continue;
+      for (int s = 0; s < p.S; ++s) {
+        int iw = ow * p.stride_w - p.pad_l + s * p.dil_w;
+        if (iw < 0 || iw >= p.W) continue;
+        acc = fmaf(xc[(int64_t)ih * p.W + iw], wk[(c * p.R + r) * p.S + s], acc);
+      }
+    }
+  }
+  if (p.relu) acc = fmaxf(acc, 0.f);
+  y[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution, groups == 1.  M = K (out channels), N = pixels, Kdim = C*R*S.
+// 64x64 tile, BK = 16, 256 threads, 4x4 register block.
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) conv_igemm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ b, float* __restrict__ y,
+                                                         ConvParams p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int64_t npix = (int64_t)p.N * p.OH * p.OW;
+  const int64_t n0 = (int64_t)blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int RS = p.R * p.S;
+  const int CRS = p.C * RS;
+  const int64_t HW = (int64_t)p.H * p.W;
+
+  // B-tile loader: fixed pixel column per thread
+  const int ln = tid % BN;
+  const int lk0 = tid / BN;  // 0..3
+  const int64_t lpix = n0 + ln;
+  const bool lvalid = lpix < npix;
+  int l_img = 0, l_ih0 = 0, l_iw0 = 0;
+  if (lvalid) {
+    int ow = lpix % p.OW;
+    int oh = (lpix / p.OW) % p.OH;
+    l_img = lpix / ((int64_t)p.OW * p.OH);
+    l_ih0 = oh * p.stride_h - p.pad_t;
+    l_iw0 = ow * p.stride_w - p.pad_l;
+  }
+  const float* xin = x + (int64_t)l_img * p.C * HW;
+
+  // A-tile loader
+  const int ak = tid % BK;
+  const int am0 = tid / BK;  // 0..15
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < CRS; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m = am0 + i * 16;
+      int kk = k0 + ak;
+      float v = 0.f;
+      if (m0 + m < p.K && kk < CRS) v = w[(int64_t)(m0 + m) * CRS + kk];
+      As[ak][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int kk = lk0 + i * 4;
+      int kidx = k0 + kk;
+      float v = 0.f;
+      if (lvalid && kidx < CRS) {
+        int c = kidx / RS;
+        int rs = kidx - c * RS;
+        int r = rs / p.S;
+        int s = rs - r * p.S;
+        int ih = l_ih0 + r * p.dil_h;
+        int iw = l_iw0 + s * p.dil_w;
+        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = xin[(int64_t)c * HW + (int64_t)ih * p.W + iw];
+      }
+      Bs[kk][ln] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const int64_t OHW = (int64_t)p.OH * p.OW;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int64_t pix = n0 + tx * 4 + j;
+    if (pix >= npix) continue;
+    int64_t img = pix / OHW;
+    int64_t rem = pix - img * OHW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int k = m0 + ty * 4 + i;
+      if (k >= p.K) continue;
+      float v = acc[i][j] + (b ? b[k] : 0.f);
+      if (p.relu) v = fmaxf(v, 0.f);
+      y[(img * p.K + k) * OHW + rem] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void conv_transpose_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                      const float* __restrict__ b, float* __restrict__ y, ConvTParams p) {
+  int64_t total = (int64_t)p.N * p.K * p.OH * p.OW;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ow = idx % p.OW;
+  int oh = (idx / p.OW) % p.OH;
+  int k = (idx / ((int64_t)p.OW * p.OH)) % p.K;
+  int n = idx / ((int64_t)p.OW * p.OH * p.K);
+  int kpg = p.K / p.groups, cpg = p.C / p.groups;
+  int g = k / kpg, kk = k - g * kpg;
+  float acc = b ? b[k] : 0.f;
+  for (int r = 0; r < p.R; ++r) {
+    int th = oh + p.pad_t - r;
+    if (th < 0 || th % p.stride_h) continue;
+    int ih = th / p.stride_h;
+    if (ih >= p.H) continue;
+    for (int s = 0; s < p.S; ++s) {
+      int tw = ow + p.pad_l - s;
+      if (tw < 0 || tw % p.stride_w) continue;
+      int iw = tw / p.stride_w;
+      if (iw >= p.W) continue;
+      for (int c = 0; c < cpg; ++c) {
+        int ci = g * cpg + c;
+        float xv = x[(((int64_t)n * p.C + ci) * p.H + ih) * p.W + iw];
+        float wv = w[(((int64_t)ci * kpg + kk) * p.R + r) * p.S + s];
+        acc = fmaf(xv, wv, acc);
+      }
+    }
+  }
+  if (p.relu) acc = fmaxf(acc, 0.f);
+  y[idx] = acc;
+}
+
+template <bool kMax>
+__global__ void pool_kernel(const float* __restrict__ x, float* __restrict__ y, PoolParams p) {
+  int64_t total = (int64_t)p.NC * p.OH * p.OW;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ow = idx % p.OW;
+  int oh = (idx / p.OW) % p.OH;
+  int64_t nc = idx / ((int64_t)p.OW * p.OH);
+  const float* xc = x + nc * p.H * p.W;
+  float acc = kMax ? -FLT_MAX : 0.f;
+  if (kMax) acc = -INFINITY;
+  int cnt = 0;
+  for (int r = 0; r < p.R; ++r) {
+    int ih = oh * p.stride_h - p.pad_t + r;
+    if (ih < 0 || ih >= p.H) continue;
+    for (int s = 0; s < p.S; ++s) {
+      int iw = ow * p.stride_w - p.pad_l + s;
+      if (iw < 0 || iw >= p.W) continue;
+      float v = xc[(int64_t)ih * p.W + iw];
+      if (kMax) acc = fmaxf(acc, v);
+      else acc += v;
+      ++cnt;
+    }
+  }
+  if (!kMax) acc = acc / (float)(p.count_include_pad ? p.R * p.S : cnt);
+  y[idx] = acc;
+}
+
+enum class Unary { kRelu, kSigmoid, kTanh };
+template <Unary U>
+__global__ void unary_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  if (U == Unary::kRelu) v = fmaxf(v, 0.f);
+  else if (U == Unary::kSigmoid) v = 1.f / (1.f + expf(-v));
+  else v = tanhf(v);
+  y[i] = v;
+}
+
+__global__ void add_bcast_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                 int64_t n, int64_t nb) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = a[i] + b[i % nb];
+}
+
+__global__ void fill_kernel(float* y, float v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C[M,N] = A[M,K] * B[N,K]^T + bias.  64x64x16 tile, 4x4 per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                       const float* __restrict__ bias, float* __restrict__ C, int M,
+                                                       int N, int K, int relu) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int lk = tid % BK, lr0 = tid / BK;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int r = lr0 + i * 16;
+      int kk = k0 + lk;
+      As[lk][r] = (m0 + r < M && kk < K) ? A[(int64_t)(m0 + r) * K + kk] : 0.f;
+      Bs[lk][r] = (n0 + r < N && kk < K) ? B[(int64_t)(n0 + r) * K + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      C[(int64_t)m * N + n] = v;
+    }
+  }
+}
+
+struct PermuteArgs {
+  int64_t out_shape[6];
+  int64_t in_stride[6];  // stride of the input dim that feeds output dim i
+  int ndim;
+};
+__global__ void permute_kernel(const float* __restrict__ x, float* __restrict__ y, PermuteArgs a, int64_t total) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int64_t rem = idx, src = 0;
+  for (int d = a.ndim - 1; d >= 0; --d) {
+    int64_t c = rem % a.out_shape[d];
+    rem /= a.out_shape[d];
+    src += c * a.in_stride[d];
+  }
+  y[idx] = x[src];
+}
+
+__global__ void concat_copy_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t outer,
+                                   int64_t len_src, int64_t len_dst, int64_t dst_off, int64_t inner) {
+  int64_t total = outer * len_src * inner;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int64_t in_i = idx % inner;
+  int64_t l = (idx / inner) % len_src;
+  int64_t o = idx / (inner * len_src);
+  y[(o * len_dst + dst_off + l) * inner + in_i] = x[idx];
+}
+
+struct Pad4Args {
+  int64_t in_shape[4], begin[4], out_shape[4];
+};
+__global__ void pad4d_kernel(const float* __restrict__ x, float* __restrict__ y, Pad4Args a, float value,
+                             int64_t total) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int64_t rem = idx;
+  int64_t c[4];
+  for (int d = 3; d >= 0; --d) {
+    c[d] = rem % a.out_shape[d];
+    rem /= a.out_shape[d];
+  }
+  int64_t src = 0;
+  bool inside = true;
+  for (int d = 0; d < 4; ++d) {
+    int64_t s = c[d] - a.begin[d];
+    if (s < 0 || s >= a.in_shape[d]) inside = false;
+    src = src * a.in_shape[d] + s;
+  }
+  y[idx] = inside ? x[src] : value;
+}
+
+// one warp per row
+__global__ void log_softmax_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int cols) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float* xr = x + row * cols;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, xr[c]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += expf(xr[c] - m);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float lse = m + logf(s);
+  for (int c = lane; c < cols; c += 32) y[row * cols + c] = xr[c] - lse;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GRU step: tile = 16 lines x 64 hidden units, K chunks of 32.
+// ---------------------------------------------------------------------------------------------
+constexpr int GL = 16, GJ = 64, GK = 32;
+__global__ void __launch_bounds__(256) gru_step_kernel(const float* __restrict__ xw, const float* __restrict__ R,
+                                                       const float* __restrict__ Rb, const float* __restrict__ h_in,
+                                                       float* __restrict__ h_out, float* __restrict__ Y, int D, int T,
+                                                       int N, int H, int t0, int t1, int lbr) {
+  __shared__ float hs[GL][GK];
+  __shared__ float Rs[3][GJ][GK + 1];
+  const int d = blockIdx.z;
+  const int t = d == 0 ? t0 : t1;
+  const int l0 = blockIdx.x * GL, j0 = blockIdx.y * GJ;
+  const int tid = threadIdx.x;
+  const int tj = tid % GJ, tl = tid / GJ;  // tl in 0..3 -> lines tl*4 .. tl*4+3
+  const float* Rd = R + (int64_t)d * 3 * H * H;
+  const float* hd = h_in + (int64_t)d * N * H;
+  float acc[3][4];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
+  for (int k0 = 0; k0 < H; k0 += GK) {
+    // h tile: 16 x 32 = 512 elements
+    for (int e = tid; e < GL * GK; e += 256) {
+      int l = e / GK, kk = e % GK;
+      hs[l][kk] = (l0 + l < N && k0 + kk < H) ? hd[(int64_t)(l0 + l) * H + k0 + kk] : 0.f;
+    }
+    // R tile: 3 x 64 x 32 = 6144 elements
+    for (int e = tid; e < 3 * GJ * GK; e += 256) {
+      int kk = e % GK;
+      int j = (e / GK) % GJ;
+      int g = e / (GK * GJ);
+      Rs[g][j][kk] = (j0 + j < H && k0 + kk < H) ? Rd[((int64_t)g * H + j0 + j) * H + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < GK; ++kk) {
+      float rz = Rs[0][tj][kk], rr = Rs[1][tj][kk], rn = Rs[2][tj][kk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float hv = hs[tl * 4 + i][kk];
+        acc[0][i] = fmaf(hv, rz, acc[0][i]);
+        acc[1][i] = fmaf(hv, rr, acc[1][i]);
+        acc[2][i] = fmaf(hv, rn, acc[2][i]);
+      }
+    }
+    __syncthreads();
+  }
+  const int j = j0 + tj;
+  if (j >= H) return;
+  const float* rb = Rb + (int64_t)d * 3 * H;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int n = l0 + tl * 4 + i;
+    if (n >= N) continue;
+    const float* xg = xw + (((int64_t)d * T + t) * N + n) * 3 * H;
+    float hp = hd[(int64_t)n * H + j];
+    float z = 1.f / (1.f + expf(-(xg[j] + acc[0][i] + rb[j])));
+    float r = 1.f / (1.f + expf(-(xg[H + j] + acc[1][i] + rb[H + j])));
+    float nn_;
+    if (lbr) nn_ = tanhf(xg[2 * H + j] + r * (acc[2][i] + rb[2 * H + j]));
+    else nn_ = tanhf(xg[2 * H + j] + acc[2][i] + rb[2 * H + j]);  // (r*h) R^T handled by caller when !lbr
+    float hnew = (1.f - z) * nn_ + z * hp;
+    h_out[((int64_t)d * N + n) * H + j] = hnew;
+    Y[(((int64_t)t * D + d) * N + n) * H + j] = hnew;
+  }
+}
+
+}  // namespace
+
+void conv2d(const float* x, const float* w, const float* b, float* y, const ConvParams& p, cudaStream_t st) {
+  int64_t total = (int64_t)p.N * p.K * p.OH * p.OW;
+  if (total == 0) return;
+  if (p.groups == 1 && p.C * p.R * p.S >= 16 && p.K >= 16) {
+    int64_t npix = (int64_t)p.N * p.OH * p.OW;
+    dim3 grid((unsigned)ceil_div(npix, BN), (unsigned)ceil_div(p.K, BM));
+    conv_igemm_kernel<<<grid, 256, 0, st>>>(x, w, b, y, p);
+  } else {
+    conv_direct_kernel<<<grid1d(total), kThreads, 0, st>>>(x, w, b, y, p);
+  }
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void conv_transpose2d(const float* x, const float* w, const float* b, float* y, const ConvTParams& p,
+                      cudaStream_t st) {
+  int64_t total = (int64_t)p.N * p.K * p.OH * p.OW;
+  if (total == 0) return;
+  conv_transpose_kernel<<<grid1d(total), kThreads, 0, st>>>(x, w, b, y, p);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void max_pool2d(const float* x, float* y, const PoolParams& p, cudaStream_t st) {
+  int64_t total = (int64_t)p.NC * p.OH * p.OW;
+  if (total == 0) return;
+  pool_kernel<true><<<grid1d(total), kThreads, 0, st>>>(x, y, p);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+void avg_pool2d(const float* x, float* y, const PoolParams& p, cudaStream_t st) {
+  int64_t total = (int64_t)p.NC * p.OH * p.OW;
+  if (total == 0) return;
+  pool_kernel<false><<<grid1d(total), kThreads, 0, st>>>(x, y, p);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void relu(const float* x, float* y, int64_t n, cudaStream_t st) {
+  if (!n) return;
+  unary_kernel<Unary::kRelu><<<grid1d(n), kThreads, 0, st>>>(x, y, n);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+void sigmoid(const float* x, float* y, int64_t n, cudaStream_t st) {
+  if (!n) return;
+  unary_kernel<Unary::kSigmoid><<<grid1d(n), kThreads, 0, st>>>(x, y, n);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+void tanh_op(const float* x, float* y, int64_t n, cudaStream_t st) {
+  if (!n) return;
+  unary_kernel<Unary::kTanh><<<grid1d(n), kThreads, 0, st>>>(x, y, n);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+void add_bcast_suffix(const float* a, const float* b, float* y, int64_t n, int64_t nb, cudaStream_t st) {
+  if (!n) return;
+  add_bcast_kernel<<<grid1d(n), kThreads, 0, st>>>(a, b, y, n, nb);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+void fill(float* y, float v, int64_t n, cudaStream_t st) {
+  if (!n) return;
+  fill_kernel<<<grid1d(n), kThreads, 0, st>>>(y, v, n);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void sgemm_nt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int relu,
+              cudaStream_t st) {
+  if (M == 0 || N == 0) return;
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM));
+  sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, B, bias, C, M, N, K, relu);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void permute(const float* x, float* y, const int64_t* shape, const int* perm, int ndim, cudaStream_t st) {
+  OCRS_CHECK(ndim <= 6, kInternal, "permute: rank > 6");
+  int64_t in_stride[6];
+  int64_t s = 1;
+  for (int d = ndim - 1; d >= 0; --d) {
+    in_stride[d] = s;
+    s *= shape[d];
+  }
+  if (s == 0) return;
+  PermuteArgs a;
+  a.ndim = ndim;
+  for (int d = 0; d < ndim; ++d) {
+    a.out_shape[d] = shape[perm[d]];
+    a.in_stride[d] = in_stride[perm[d]];
+  }
+  permute_kernel<<<grid1d(s), kThreads, 0, st>>>(x, y, a, s);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void concat_copy(const float* x, float* y, int64_t outer, int64_t len_src, int64_t len_dst, int64_t dst_off,
+                 int64_t inner, cudaStream_t st) {
+  int64_t total = outer * len_src * inner;
+  if (!total) return;
+  concat_copy_kernel<<<grid1d(total), kThreads, 0, st>>>(x, y, outer, len_src, len_dst, dst_off, inner);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void pad4d(const float* x, float* y, const int64_t in_shape[4], const int64_t begin[4], const int64_t out_shape[4],
+           float value, cudaStream_t st) {
+  Pad4Args a;
+  int64_t total = 1;
+  for (int d = 0; d < 4; ++d) {
+    a.in_shape[d] = in_shape[d];
+    a.begin[d] = begin[d];
+    a.out_shape[d] = out_shape[d];
+    total *= out_shape[d];
+  }
+  if (!total) return;
+  pad4d_kernel<<<grid1d(total), kThreads, 0, st>>>(x, y, a, value, total);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void log_softmax_lastdim(const float* x, float* y, int64_t rows, int cols, cudaStream_t st) {
+  if (!rows) return;
+  log_softmax_kernel<<<grid1d(rows * 32), kThreads, 0, st>>>(x, y, rows, cols);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void gru_step(const float* xw, const float* R, const float* Rb, const float* h_in, float* h_out, float* Y, int D,
+              int T, int N, int H, int step, const int* dir_reverse_host, int lbr, cudaStream_t st) {
+  if (N == 0) return;
+  int t0 = dir_reverse_host[0] ? T - 1 - step : step;
+  int t1 = (D > 1) ? (dir_reverse_host[1] ? T - 1 - step : step) : 0;
+  dim3 grid((unsigned)ceil_div(N, GL), (unsigned)ceil_div(H, GJ), (unsigned)D);
+  gru_step_kernel<<<grid, 256, 0, st>>>(xw, R, Rb, h_in, h_out, Y, D, T, N, H, t0, t1, lbr);
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace nn
+}  // namespace ocrs

@@ -1,0 +1,394 @@
+"""Host-side mirror of the reference's public API (ocrs/src/lib.rs) over the C ABI.
+
+Same names, argument meaning and error behaviour as the Rust crate so that the parity tests read
+like the reference's own tests:
+
+    engine = OcrEngine(OcrEngineParams(detection_model=..., recognition_model=...))
+    inp    = engine.prepare_input(ImageSource.from_bytes(data, (w, h)))
+    words  = engine.detect_words(inp)
+    lines  = engine.find_text_lines(inp, words)
+    texts  = engine.recognize_text(inp, lines)
+
+Everything numerical happens inside libocrs_b200.so on the GPU; this module only marshals."""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineParamsC, OcrsError, RectC, RotatedRectC, TextResultC, check, lib
+
+# lib.rs:34
+DEFAULT_ALPHABET = " 0123456789!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~EABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz"
+
+
+class DimOrder(enum.IntEnum):
+    """preprocess.rs:50-57"""
+    Hwc = 0
+    Chw = 1
+
+
+class DecodeMethod(enum.IntEnum):
+    """recognition.rs:199-205"""
+    Greedy = 0
+    BeamSearch = 1
+
+
+class ImageSourceError(ValueError):
+    """preprocess.rs:37-46"""
+
+
+class ImageSource:
+    """preprocess.rs:61-124: a validated view of caller pixels (u8 or f32; HWC or CHW)."""
+
+    def __init__(self, data: np.ndarray, order: DimOrder):
+        self.data = data
+        self.order = order
+
+    @staticmethod
+    def from_bytes(data, dimensions: Tuple[int, int]) -> "ImageSource":
+        """`ImageSource::from_bytes(bytes, (width, height))` (preprocess.rs:81-102)."""
+        width, height = dimensions
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data.reshape(-1)
+        channel_len = int(width) * int(height)
+        if channel_len == 0:
+            raise ImageSourceError("channel count is not 1, 3 or 4")
+        if buf.size % channel_len != 0:
+            raise ImageSourceError("data length is not a multiple of `width * height`")
+        return ImageSource.from_tensor(buf.reshape(height, width, buf.size // channel_len), DimOrder.Hwc)
+
+    @staticmethod
+    def from_tensor(data: np.ndarray, order: DimOrder) -> "ImageSource":
+        """`ImageSource::from_tensor` (preprocess.rs:105-123)."""
+        if data.ndim != 3 or data.dtype not in (np.uint8, np.float32):
+            raise ImageSourceError("expected a 3-D u8 or f32 tensor")
+        channels = data.shape[2] if order == DimOrder.Hwc else data.shape[0]
+        if channels not in (1, 3, 4):
+            raise ImageSourceError("channel count is not 1, 3 or 4")
+        return ImageSource(np.ascontiguousarray(data), DimOrder(order))
+
+
+@dataclass
+class RotatedRect:
+    """rten_imageproc::RotatedRect as plain floats (centre, unit up axis, width, height)."""
+    cx: float
+    cy: float
+    ux: float
+    uy: float
+    w: float
+    h: float
+
+    def raw(self):
+        return (self.cx, self.cy, self.ux, self.uy, self.w, self.h)
+
+
+@dataclass
+class Rect:
+    top: int
+    left: int
+    bottom: int
+    right: int
+
+    def tlbr(self):
+        return (self.top, self.left, self.bottom, self.right)
+
+
+@dataclass
+class TextChar:
+    """text_items.rs:47-53"""
+    char: str
+    rect: Rect
+
+
+@dataclass
+class TextLine:
+    """text_items.rs:59-66"""
+    chars: List[TextChar]
+
+    def __str__(self) -> str:
+        return "".join(c.char for c in self.chars)
+
+    def words(self) -> List[List[TextChar]]:
+        """text_items.rs:76-82"""
+        out, cur = [], []
+        for c in self.chars:
+            if c.char == " ":
+                if cur:
+                    out.append(cur)
+                cur = []
+            else:
+                cur.append(c)
+        if cur:
+            out.append(cur)
+        return out
+
+
+@dataclass
+class OcrEngineParams:
+    """lib.rs:37-71.  Models are `.onnx` file images (bytes) or paths."""
+    detection_model: Optional[object] = None
+    recognition_model: Optional[object] = None
+    debug: bool = False
+    decode_method: DecodeMethod = DecodeMethod.Greedy
+    beam_width: int = 100
+    alphabet: Optional[str] = None
+    allowed_chars: Optional[str] = None
+    device: int = 0
+
+
+def _model_bytes(m) -> Optional[bytes]:
+    if m is None:
+        return None
+    if isinstance(m, (bytes, bytearray, memoryview)):
+        return bytes(m)
+    with open(m, "rb") as fp:
+        return fp.read()
+
+
+def _rects_to_c(rects: Sequence[RotatedRect]):
+    arr = (RotatedRectC * max(len(rects), 1))()
+    for i, r in enumerate(rects):
+        arr[i] = RotatedRectC(*r.raw())
+    return arr
+
+
+def _rects_from_c(ptr, n: int) -> List[RotatedRect]:
+    return [RotatedRect(ptr[i].cx, ptr[i].cy, ptr[i].ux, ptr[i].uy, ptr[i].w, ptr[i].h) for i in range(n)]
+
+
+def _text_result(res_ptr) -> List[Optional[TextLine]]:
+    r = res_ptr.contents
+    out: List[Optional[TextLine]] = []
+    for i in range(r.n_lines):
+        if not r.line_present[i]:
+            out.append(None)
+            continue
+        chars = []
+        for k in range(r.char_offsets[i], r.char_offsets[i + 1]):
+            rc = r.char_rects[k]
+            chars.append(TextChar(chr(r.chars[k]), Rect(rc.top, rc.left, rc.bottom, rc.right)))
+        out.append(TextLine(chars))
+    return out
+
+
+class OcrInput:
+    """lib.rs:125-128: the prepared greyscale page, resident in GPU memory."""
+
+    def __init__(self, engine: "OcrEngine", handle):
+        self._engine = engine
+        self._h = handle
+
+    @property
+    def shape(self) -> Tuple[int, int, int]:
+        h, w = C.c_int(), C.c_int()
+        check(lib.ocrs_b200_input_shape(self._h, C.byref(h), C.byref(w)))
+        return (1, h.value, w.value)
+
+    def image(self) -> np.ndarray:
+        """Host copy of the CHW f32 tensor (`OcrInput::image`)."""
+        _, h, w = self.shape
+        out = np.empty((1, h, w), dtype=np.float32)
+        check(lib.ocrs_b200_input_read(self._engine._h, self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.ocrs_b200_input_destroy(self._h)
+            self._h = None
+
+
+class Model:
+    """The inner seam (`trait Model`, model.rs:6-17): input_shape() + run()."""
+
+    def __init__(self, model, device: int = 0):
+        data = _model_bytes(model)
+        self._h = C.c_void_p()
+        self._buf = data
+        check(lib.ocrs_b200_model_load(data, len(data), device, C.byref(self._h)))
+
+    def input_shape(self) -> List[object]:
+        dims = (C.c_int64 * 8)()
+        nd = C.c_int()
+        check(lib.ocrs_b200_model_input_shape(self._h, dims, C.byref(nd)))
+        return [int(dims[i]) if dims[i] >= 0 else "sym" for i in range(nd.value)]
+
+    def run(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        shape = (C.c_int64 * 8)(*x.shape)
+        out = C.POINTER(C.c_float)()
+        oshape = (C.c_int64 * 8)()
+        ond = C.c_int()
+        check(lib.ocrs_b200_model_run(self._h, x.ctypes.data_as(C.c_void_p), shape, x.ndim, C.byref(out), oshape,
+                                      C.byref(ond)))
+        shp = tuple(int(oshape[i]) for i in range(ond.value))
+        n = int(np.prod(shp)) if shp else 1
+        res = np.ctypeslib.as_array(out, shape=(n,)).copy().reshape(shp)
+        lib.ocrs_b200_free(out)
+        return res
+
+    def last_flops(self) -> float:
+        return float(lib.ocrs_b200_model_last_flops(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.ocrs_b200_model_destroy(self._h)
+            self._h = None
+
+
+class OcrEngine:
+    """lib.rs:111-301"""
+
+    def __init__(self, params: OcrEngineParams):
+        self._det = _model_bytes(params.detection_model)
+        self._rec = _model_bytes(params.recognition_model)
+        p = EngineParamsC()
+        p.detection_model = C.cast(C.c_char_p(self._det), C.c_void_p) if self._det else None
+        p.detection_model_len = len(self._det) if self._det else 0
+        p.recognition_model = C.cast(C.c_char_p(self._rec), C.c_void_p) if self._rec else None
+        p.recognition_model_len = len(self._rec) if self._rec else 0
+        p.debug = int(params.debug)
+        p.decode_method = int(params.decode_method)
+        p.beam_width = int(params.beam_width)
+        p.alphabet_utf8 = params.alphabet.encode("utf-8") if params.alphabet is not None else None
+        p.allowed_chars_utf8 = params.allowed_chars.encode("utf-8") if params.allowed_chars is not None else None
+        p.device = int(params.device)
+        self._h = C.c_void_p()
+        check(lib.ocrs_b200_engine_create(C.byref(p), C.byref(self._h)))
+        self.alphabet = params.alphabet if params.alphabet is not None else DEFAULT_ALPHABET
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.ocrs_b200_engine_destroy(self._h)
+            self._h = None
+
+    # -- lib.rs:183
+    def prepare_input(self, image: ImageSource) -> OcrInput:
+        a = image.data
+        if image.order == DimOrder.Hwc:
+            h, w, c = a.shape
+        else:
+            c, h, w = a.shape
+        dtype = 0 if a.dtype == np.uint8 else 1
+        out = C.c_void_p()
+        check(lib.ocrs_b200_engine_prepare_input(self._h, a.ctypes.data_as(C.c_void_p), dtype, int(image.order), h, w, c,
+                                                 C.byref(out)))
+        return OcrInput(self, out)
+
+    def prepare_input_device(self, device_ptr: int, dtype: int, order: DimOrder, h: int, w: int, c: int) -> OcrInput:
+        """Pixels already in this GPU's memory (used to time the HBM-resident path)."""
+        out = C.c_void_p()
+        check(lib.ocrs_b200_engine_prepare_input_device(self._h, C.c_void_p(device_ptr), dtype, int(order), h, w, c,
+                                                        C.byref(out)))
+        return OcrInput(self, out)
+
+    # -- lib.rs:193
+    def detect_words(self, inp: OcrInput) -> List[RotatedRect]:
+        rects = C.POINTER(RotatedRectC)()
+        n = C.c_size_t()
+        check(lib.ocrs_b200_engine_detect_words(self._h, inp._h, C.byref(rects), C.byref(n)))
+        out = _rects_from_c(rects, n.value)
+        lib.ocrs_b200_free(rects)
+        return out
+
+    def detect_words_batch(self, inputs: Sequence[OcrInput]) -> List[List[RotatedRect]]:
+        hs = (C.c_void_p * max(len(inputs), 1))(*[i._h for i in inputs])
+        rects = C.POINTER(RotatedRectC)()
+        offs = C.POINTER(C.c_size_t)()
+        check(lib.ocrs_b200_engine_detect_words_batch(self._h, hs, len(inputs), C.byref(rects), C.byref(offs)))
+        out = []
+        for i in range(len(inputs)):
+            s, e = offs[i], offs[i + 1]
+            out.append([RotatedRect(rects[k].cx, rects[k].cy, rects[k].ux, rects[k].uy, rects[k].w, rects[k].h)
+                        for k in range(s, e)])
+        lib.ocrs_b200_free(rects)
+        lib.ocrs_b200_free(offs)
+        return out
+
+    # -- lib.rs:207
+    def detect_text_pixels(self, inp: OcrInput) -> np.ndarray:
+        _, h, w = inp.shape
+        out = np.empty((h, w), dtype=np.float32)
+        check(lib.ocrs_b200_engine_detect_text_pixels(self._h, inp._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # -- lib.rs:222
+    def find_text_lines(self, inp: Optional[OcrInput], words: Sequence[RotatedRect]) -> List[List[RotatedRect]]:
+        return find_text_lines(words)
+
+    # -- lib.rs:237
+    def recognize_text(self, inp: OcrInput, lines: Sequence[Sequence[RotatedRect]]) -> List[Optional[TextLine]]:
+        flat = [w for line in lines for w in line]
+        arr = _rects_to_c(flat)
+        offs = (C.c_size_t * (len(lines) + 1))()
+        k = 0
+        for i, line in enumerate(lines):
+            offs[i] = k
+            k += len(line)
+        offs[len(lines)] = k
+        res = C.POINTER(TextResultC)()
+        check(lib.ocrs_b200_engine_recognize_text(self._h, inp._h, arr, offs, len(lines), C.byref(res)))
+        out = _text_result(res)
+        lib.ocrs_b200_text_result_free(res)
+        return out
+
+    # -- lib.rs:268
+    def prepare_recognition_input(self, inp: OcrInput, line: Sequence[RotatedRect]) -> np.ndarray:
+        arr = _rects_to_c(line)
+        out = C.POINTER(C.c_float)()
+        h, w = C.c_int(), C.c_int()
+        check(lib.ocrs_b200_engine_prepare_recognition_input(self._h, inp._h, arr, len(line), C.byref(out), C.byref(h),
+                                                             C.byref(w)))
+        res = np.ctypeslib.as_array(out, shape=(h.value * w.value,)).copy().reshape(h.value, w.value)
+        lib.ocrs_b200_free(out)
+        return res
+
+    # -- lib.rs:282
+    def detection_threshold(self) -> float:
+        return float(lib.ocrs_b200_engine_detection_threshold(self._h))
+
+    # -- lib.rs:290
+    def get_text(self, inp: OcrInput) -> str:
+        s = C.c_char_p()
+        check(lib.ocrs_b200_engine_get_text(self._h, inp._h, C.byref(s)))
+        text = s.value.decode("utf-8")
+        lib.ocrs_b200_free(s)
+        return text
+
+    # -- batched pipeline (configs 2-5)
+    def ocr_batch(self, inputs: Sequence[OcrInput]) -> List[List[Optional[TextLine]]]:
+        hs = (C.c_void_p * max(len(inputs), 1))(*[i._h for i in inputs])
+        res = (C.POINTER(TextResultC) * max(len(inputs), 1))()
+        check(lib.ocrs_b200_engine_ocr_batch(self._h, hs, len(inputs), res))
+        out = []
+        for i in range(len(inputs)):
+            out.append(_text_result(res[i]))
+            lib.ocrs_b200_text_result_free(res[i])
+        return out
+
+    def stats(self, reset: bool = False) -> dict:
+        buf = (C.c_double * 8)()
+        check(lib.ocrs_b200_engine_stats(self._h, buf, int(reset)))
+        return {"det_flops": buf[0], "rec_flops": buf[1], "words": int(buf[2]), "lines": int(buf[3]),
+                "timesteps": int(buf[4]), "rec_batches": int(buf[5])}
+
+
+def find_text_lines(words: Sequence[RotatedRect]) -> List[List[RotatedRect]]:
+    """layout_analysis.rs:158 through the C ABI (host code; needs no GPU)."""
+    arr = _rects_to_c(words)
+    out_words = C.POINTER(RotatedRectC)()
+    offs = C.POINTER(C.c_size_t)()
+    n_lines = C.c_size_t()
+    check(lib.ocrs_b200_find_text_lines(arr, len(words), C.byref(out_words), C.byref(offs), C.byref(n_lines)))
+    lines = [[RotatedRect(out_words[k].cx, out_words[k].cy, out_words[k].ux, out_words[k].uy, out_words[k].w,
+                          out_words[k].h) for k in range(offs[i], offs[i + 1])] for i in range(n_lines.value)]
+    lib.ocrs_b200_free(out_words)
+    lib.ocrs_b200_free(offs)
+    return lines
+
+
+def device_count() -> int:
+    return int(lib.ocrs_b200_device_count())

@@ -1,0 +1,74 @@
+"""End-to-end parity on synthetic pages (BASELINE.json configs 1-3), staged so that every integer
+stage is compared bit-exactly on identical inputs and every floating-point stage to tolerance:
+
+  prepare_input              bit-exact
+  detection prob map         <= 1e-4 vs torch-CPU; mask may differ only where |p - 0.2| <= 1e-4
+  mask -> word rects         bit-exact (oracle fed the GPU's own prob map)
+  find_text_lines            bit-exact (oracle fed the GPU's rects)
+  recognise                  strings and char boxes identical (oracle fed the GPU's lines)
+"""
+import numpy as np
+import pytest
+
+import ocrs_b200 as ob
+from oracle.engine import OcrEngine as OEngine, OcrEngineParams as OParams, find_connected_component_rects
+from oracle.imageops import threshold_mask
+from oracle.onnx_eval import OnnxModel
+from tests.gpu_util import (
+    char_boxes, lines_raw, model_paths, oracle_char_boxes, oracle_text_of, raw32, text_of, to_oracle_rects,
+)
+from tools.synth import make_page
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines():
+    det, rec = model_paths()
+    eng = ob.OcrEngine(ob.OcrEngineParams(detection_model=det, recognition_model=rec))
+    ora = OEngine(OParams(detection_model=OnnxModel(det), recognition_model=OnnxModel(rec)))
+    return eng, ora
+
+
+def _staged_check(eng, ora, page):
+    inp = eng.prepare_input(ob.ImageSource.from_tensor(page, ob.DimOrder.Hwc))
+    oimg = ora.prepare_input(page, "hwc")
+    assert np.array_equal(inp.image(), oimg)
+
+    prob = eng.detect_text_pixels(inp)
+    oprob = ora.detect_text_pixels(oimg)
+    assert np.abs(prob - oprob).max() < 1e-4
+    diff = threshold_mask(prob) != threshold_mask(oprob)
+    assert np.all(np.abs(oprob[diff] - np.float32(0.2)) <= 1e-4)
+
+    words = eng.detect_words(inp)
+    owords = find_connected_component_rects(threshold_mask(prob), 3.0, 100.0)
+    assert raw32(words) == [tuple(np.float32(v) for v in r.raw()) for r in owords]
+
+    lines = eng.find_text_lines(inp, words)
+    olines = ora.find_text_lines(oimg, to_oracle_rects(words))
+    assert lines_raw(lines) == [[tuple(np.float32(v) for v in r.raw()) for r in l] for l in olines]
+
+    texts = eng.recognize_text(inp, lines)
+    otexts = ora.recognize_text(oimg, olines)
+    assert text_of(texts) == oracle_text_of(otexts)
+    assert char_boxes(texts) == oracle_char_boxes(otexts)
+    return words, lines, texts
+
+
+def test_config1_640x480(engines):
+    eng, ora = engines
+    page, _ = make_page(1, 480, 640)
+    _staged_check(eng, ora, page)
+
+
+@pytest.mark.parametrize("seed", [200, 201])
+def test_config3_1024x768(engines, seed):
+    eng, ora = engines
+    page, _ = make_page(seed)
+    words, lines, texts = _staged_check(eng, ora, page)
+    # batched entry point returns the same thing as the staged calls
+    inp = eng.prepare_input(ob.ImageSource.from_tensor(page, ob.DimOrder.Hwc))
+    batched = eng.ocr_batch([inp, inp])
+    assert text_of(batched[0]) == text_of(texts) == text_of(batched[1])
+    assert eng.get_text(inp) == "\n".join(t for t in text_of(texts) if t is not None)

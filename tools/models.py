@@ -313,3 +313,29 @@ def ensure_models(model_dir: str | None = None, verbose: bool = False):
 
 if __name__ == "__main__":
     print(ensure_models(sys.argv[1] if len(sys.argv) > 1 else None, verbose=True))
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's fake models (lib.rs:335-422) expressed as ONNX graphs, so that its known-answer
+# integration tests run through the real loader + CUDA executor.
+# ---------------------------------------------------------------------------------------------
+def export_fake_detection(path: str, in_hw=(200, 100)) -> None:
+    """lib.rs:339-362: output = input + 0.5, input [batch,1,H,W]."""
+    b = _Builder()
+    b.node("Add", ["image", b.const("half", np.array([0.5], dtype=np.float32))])
+    b.nodes[-1].outputs[0] = "mask"
+    g = Graph(b.nodes, b.inits, [ValueInfo("image", FLOAT, ["batch", 1, in_hw[0], in_hw[1]])],
+              [ValueInfo("mask", FLOAT, ["batch", 1, in_hw[0], in_hw[1]])], name="fake-detection")
+    save_model(g, path)
+
+
+def export_fake_recognition(path: str, height: int = 64) -> None:
+    """lib.rs:372-422: max-pool width by 4, reinterpret the 64 rows as class scores -> [W/4, N, 64]."""
+    b = _Builder()
+    x = b.node("MaxPool", ["line_images"], {"kernel_shape": [1, 4], "strides": [1, 4], "pads": [0, 0, 0, 0], "ceil_mode": 0})
+    x = b.node("Reshape", [x, b.const("shape", np.array([0, height, -1], dtype=np.int64))])
+    x = b.node("Transpose", [x], {"perm": [2, 0, 1]})
+    b.nodes[-1].outputs[0] = "scores"
+    g = Graph(b.nodes, b.inits, [ValueInfo("line_images", FLOAT, ["batch", 1, height, "seq"])],
+              [ValueInfo("scores", FLOAT, ["out_seq", "batch", height])], name="fake-recognition")
+    save_model(g, path)
