@@ -168,6 +168,19 @@ int ocrs_b200_engine_detect_words_batch(ocrs_b200_engine* e, const ocrs_b200_inp
  * [2] words, [3] lines, [4] CTC timesteps, [5] recognition batches. */
 int ocrs_b200_engine_stats(ocrs_b200_engine* e, double out[8], int reset);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
+/* CUDA-event profiling of pipeline stages and of every operator of the two networks. */
+int ocrs_b200_engine_set_profiling(ocrs_b200_engine* e, int enable);
+/* *json is malloc'ed: {"stage/...": {"ms", "calls", "launches", "flops", "bytes"}, "rec/Conv": ...} */
+int ocrs_b200_engine_profile_json(ocrs_b200_engine* e, char** json, int reset);
+/* cudaEvent timer on the engine's stream: start records, stop records + waits + returns ms. */
+int ocrs_b200_engine_timer_start(ocrs_b200_engine* e);
+int ocrs_b200_engine_timer_stop(ocrs_b200_engine* e, float* ms);
+/* Host<->device traffic of the engine since creation: out[0] = H2D bytes, out[1] = D2H bytes. */
+int ocrs_b200_engine_transfer_bytes(ocrs_b200_engine* e, int64_t out[2]);
+/* Kernels launched by the library in this process so far. */
+int64_t ocrs_b200_kernel_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

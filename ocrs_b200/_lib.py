@@ -98,6 +98,12 @@ SIGNATURES = {
     "ocrs_b200_engine_detect_words_batch": (C.c_int, [C.c_void_p, P(C.c_void_p), C.c_size_t, P(P(RotatedRectC)),
                                                       P(P(C.c_size_t))]),
     "ocrs_b200_engine_stats": (C.c_int, [C.c_void_p, P(C.c_double), C.c_int]),
+    "ocrs_b200_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "ocrs_b200_engine_profile_json": (C.c_int, [C.c_void_p, P(C.c_char_p), C.c_int]),
+    "ocrs_b200_engine_timer_start": (C.c_int, [C.c_void_p]),
+    "ocrs_b200_engine_timer_stop": (C.c_int, [C.c_void_p, P(C.c_float)]),
+    "ocrs_b200_engine_transfer_bytes": (C.c_int, [C.c_void_p, P(C.c_int64)]),
+    "ocrs_b200_kernel_launch_count": (C.c_int64, []),
 }
 
 

@@ -290,7 +290,7 @@ int ocrs_b200_input_read(ocrs_b200_engine* e, const ocrs_b200_input* in, float* 
   return guard([&] {
     OCRS_CHECK(e && in && out, kInvalidArg, "null argument");
     e->engine->synchronize();
-    OCRS_CUDA_CHECK(cudaMemcpy(out, in->input->grey.ptr, (size_t)in->input->H * in->input->W * 4, cudaMemcpyDeviceToHost));
+    OCRS_CUDA_CHECK(cudaMemcpy(out, in->input->grey(), (size_t)in->input->H * in->input->W * 4, cudaMemcpyDeviceToHost));
   });
 }
 
@@ -460,5 +460,45 @@ int ocrs_b200_engine_stats(ocrs_b200_engine* e, double out[8], int reset) {
     if (reset) e->engine->reset_stats();
   });
 }
+
+int ocrs_b200_engine_set_profiling(ocrs_b200_engine* e, int enable) {
+  return guard([&] {
+    OCRS_CHECK(e, kInvalidArg, "null argument");
+    e->engine->set_profiling(enable != 0);
+  });
+}
+
+int ocrs_b200_engine_profile_json(ocrs_b200_engine* e, char** json, int reset) {
+  return guard([&] {
+    OCRS_CHECK(e && json, kInvalidArg, "null argument");
+    std::string j = e->engine->profile_json(reset != 0);
+    *json = cmalloc<char>(j.size() + 1);
+    std::memcpy(*json, j.c_str(), j.size() + 1);
+  });
+}
+
+int ocrs_b200_engine_timer_start(ocrs_b200_engine* e) {
+  return guard([&] {
+    OCRS_CHECK(e, kInvalidArg, "null argument");
+    e->engine->timer_start();
+  });
+}
+
+int ocrs_b200_engine_timer_stop(ocrs_b200_engine* e, float* ms) {
+  return guard([&] {
+    OCRS_CHECK(e && ms, kInvalidArg, "null argument");
+    *ms = e->engine->timer_stop();
+  });
+}
+
+int ocrs_b200_engine_transfer_bytes(ocrs_b200_engine* e, int64_t out[2]) {
+  return guard([&] {
+    OCRS_CHECK(e && out, kInvalidArg, "null argument");
+    out[0] = e->engine->h2d_bytes();
+    out[1] = e->engine->d2h_bytes();
+  });
+}
+
+int64_t ocrs_b200_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 }  // extern "C"

@@ -2,8 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -44,6 +46,34 @@ struct Error : public std::runtime_error {
   do {                                               \
     if (!(cond)) throw ::ocrs::Error((code), (msg)); \
   } while (0)
+
+// Number of kernels launched by this library (all engines) since process start.
+extern std::atomic<int64_t> g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Optional CUDA-event profiler: brackets named regions on a stream, resolved after a sync.
+struct OpProfile {
+  double ms = 0, flops = 0, bytes = 0;
+  int64_t calls = 0, launches = 0;
+};
+class Profiler {
+ public:
+  ~Profiler();
+  bool enabled = false;
+  // returns a token (index) or -1 when disabled
+  int begin(const std::string& name, cudaStream_t st);
+  void end(int token, cudaStream_t st, double flops = 0, double bytes = 0);
+  void collect();  // call after the stream is synchronized
+  void reset() { acc_.clear(); }
+  const std::map<std::string, OpProfile>& results() const { return acc_; }
+
+ private:
+  struct Pending { std::string name; cudaEvent_t a, b; double flops, bytes; int64_t launches0, launches; };
+  std::vector<Pending> pending_;
+  std::vector<cudaEvent_t> free_events_;
+  std::map<std::string, OpProfile> acc_;
+  cudaEvent_t get_event();
+};
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

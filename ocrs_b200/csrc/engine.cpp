@@ -133,12 +133,61 @@ Engine::~Engine() {
   }
   det_.reset();
   rec_.reset();
+  if (ev_a_) cudaEventDestroy(ev_a_);
+  if (ev_copy_) cudaEventDestroy(ev_copy_);
+  if (ev_b_) cudaEventDestroy(ev_b_);
   if (st_) cudaStreamDestroy(st_);
 }
 
 void Engine::synchronize() {
   OCRS_CUDA_CHECK(cudaSetDevice(device_));
   OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+}
+
+void Engine::set_profiling(bool on) {
+  std::lock_guard<std::mutex> lk(mu_);
+  prof_.enabled = on;
+}
+
+std::string Engine::profile_json(bool reset) {
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  prof_.collect();
+  std::string j = "{";
+  bool first = true;
+  for (const auto& kv : prof_.results()) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"calls\": %lld, \"launches\": %lld, \"flops\": %.6e, \"bytes\": %.6e}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.ms, (long long)kv.second.calls,
+             (long long)kv.second.launches, kv.second.flops, kv.second.bytes);
+    j += buf;
+    first = false;
+  }
+  j += "}";
+  if (reset) prof_.reset();
+  return j;
+}
+
+void Engine::timer_start() {
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  if (!ev_a_) {
+    OCRS_CUDA_CHECK(cudaEventCreate(&ev_a_));
+    OCRS_CUDA_CHECK(cudaEventCreate(&ev_b_));
+  }
+  OCRS_CUDA_CHECK(cudaEventRecord(ev_a_, st_));
+}
+
+float Engine::timer_stop() {
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  OCRS_CHECK(ev_a_ != nullptr, kInvalidArg, "timer_stop without timer_start");
+  OCRS_CUDA_CHECK(cudaEventRecord(ev_b_, st_));
+  OCRS_CUDA_CHECK(cudaEventSynchronize(ev_b_));
+  float ms = 0;
+  OCRS_CUDA_CHECK(cudaEventElapsedTime(&ms, ev_a_, ev_b_));
+  return ms;
 }
 
 uint32_t Engine::rec_input_height() const {  // recognition.rs:332-337
@@ -163,19 +212,25 @@ std::unique_ptr<OcrInput> Engine::prepare_input(const void* pixels, int dtype, i
   in->W = W;
   in->device = device_;
   size_t hw = (size_t)H * W;
-  in->grey.reserve(std::max<size_t>(hw, 1) * sizeof(float));
+  in->store = std::make_shared<Storage>(std::max<size_t>(hw, 1) * sizeof(float), st_);
   if (hw == 0) return in;
   size_t bytes = hw * C * (dtype == 0 ? 1 : 4);
   const void* dpx = pixels;
+  std::shared_ptr<Storage> staging;  // freed (stream-ordered) after the conversion kernel
   if (!on_device) {
-    staging_.reserve(bytes);
-    OCRS_CUDA_CHECK(cudaMemcpyAsync(staging_.ptr, pixels, bytes, cudaMemcpyHostToDevice, st_));
-    dpx = staging_.ptr;
+    staging = std::make_shared<Storage>(bytes, st_);
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(staging->ptr, pixels, bytes, cudaMemcpyHostToDevice, st_));
+    dpx = staging->ptr;
+    h2d_bytes_ += (int64_t)bytes;
+    // the caller's buffer is only borrowed for this call (ImageSource<'a>): wait for the copy,
+    // not for the kernel
+    if (!ev_copy_) OCRS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
+    OCRS_CUDA_CHECK(cudaEventRecord(ev_copy_, st_));
   }
-  img::prepare_image(dpx, dtype, order, H, W, C, in->grey.as<float>(), st_);
-  stats_.kernel_launches += 1;
-  // the staging buffer is reused by the next call: order it behind this kernel
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  int tk = prof_.begin("stage/prepare_image", st_);
+  img::prepare_image(dpx, dtype, order, H, W, C, in->grey(), st_);
+  prof_.end(tk, st_, 0, (double)bytes + (double)hw * 4);
+  if (!on_device) OCRS_CUDA_CHECK(cudaEventSynchronize(ev_copy_));
   return in;
 }
 
@@ -201,7 +256,7 @@ std::vector<float> Engine::detect_text_pixels(const OcrInput& in) {
   int H = in.H, W = in.W;
   int pad_bottom = std::max(in_h - H, 0), pad_right = std::max(in_w - W, 0);
   det_in_.reserve((size_t)in_h * in_w * 4);
-  img::resize_padded(in.grey.as<float>(), H, W, H + pad_bottom, W + pad_right, img::kBlackValue, det_in_.as<float>(),
+  img::resize_padded(in.grey(), H, W, H + pad_bottom, W + pad_right, img::kBlackValue, det_in_.as<float>(),
                      in_h, in_w, 1, 0, 0, st_);
   DTensor out = det_->run(wrap_tensor(det_in_.as<float>(), {1, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_);
   OCRS_CHECK(out.shape.size() == 4 && out.numel() == (int64_t)in_h * in_w, kWrongOutput,
@@ -228,15 +283,22 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words(const std::vector<con
   const int in_h = (int)shp[2], in_w = (int)shp[3];
   const int64_t plane = (int64_t)in_h * in_w;
   det_in_.reserve((size_t)N * plane * 4);
+  int tk = prof_.begin("stage/resize_in", st_);
+  double rs_bytes = 0;
   for (int i = 0; i < N; ++i) {
     const OcrInput& in = *pages[i];
+    rs_bytes += 4.0 * ((double)in.H * in.W + (double)plane);
     OCRS_CHECK(in.device == device_, kInvalidArg, "input lives on another device");
     int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
-    img::resize_padded(in.grey.as<float>(), in.H, in.W, in.H + pb, in.W + pr, img::kBlackValue,
+    img::resize_padded(in.grey(), in.H, in.W, in.H + pb, in.W + pr, img::kBlackValue,
                        det_in_.as<float>() + i * plane, in_h, in_w, 1, 0, 0, st_);
   }
+  prof_.end(tk, st_, 0, rs_bytes);
   ModelCost cost;
-  DTensor out = det_->run(wrap_tensor(det_in_.as<float>(), {N, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_, &cost);
+  tk = prof_.begin("stage/det_net", st_);
+  DTensor out = det_->run(wrap_tensor(det_in_.as<float>(), {N, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_, &cost,
+                          &prof_, "det/");
+  prof_.end(tk, st_, cost.flops, cost.min_bytes);
   stats_.det_flops += cost.flops;
   OCRS_CHECK(out.shape.size() == 4 && out.numel() == (int64_t)N * plane, kWrongOutput,
              "detection output must be [N,1,H,W]");
@@ -246,11 +308,16 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words(const std::vector<con
     const OcrInput& in = *pages[i];
     PageScratch& s = scratch_for(i, in.H, in.W);
     int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
+    int t1 = prof_.begin("stage/resize_threshold", st_);
     img::resize_threshold(out.data + i * plane, in_h, in_w, in_h - pb, in_w - pr, nullptr, s.mask.as<uint8_t>(),
                           in.H, in.W, text_threshold_, st_);
+    prof_.end(t1, st_, 0, 4.0 * (in_h - pb) * (in_w - pr) + (double)in.H * in.W);
+    int t2 = prof_.begin("stage/components_to_rects", st_);
     img::find_component_rects(s.mask.as<uint8_t>(), in.H, in.W, 2.0f /* detection.rs:50 */,
                               3.0f /* detection.rs:116 */, min_area_, s.bufs, st_);
+    prof_.end(t2, st_, 0, 5.0 * in.H * in.W);  // read mask + write/read labels
     OCRS_CUDA_CHECK(cudaMemcpyAsync(h_counters + 8 * i, s.bufs.counters, 8 * 4, cudaMemcpyDeviceToHost, st_));
+    d2h_bytes_ += 32;
   }
   OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
   std::vector<std::vector<int32_t>> roots((size_t)N);
@@ -266,6 +333,7 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words(const std::vector<con
       OCRS_CUDA_CHECK(cudaMemcpyAsync(result[i].data(), s.bufs.rects, (size_t)n * sizeof(RotatedRect),
                                       cudaMemcpyDeviceToHost, st_));
       OCRS_CUDA_CHECK(cudaMemcpyAsync(roots[i].data(), s.bufs.rect_root, (size_t)n * 4, cudaMemcpyDeviceToHost, st_));
+      d2h_bytes_ += (int64_t)n * (sizeof(RotatedRect) + 4);
     }
   }
   OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -372,7 +440,7 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
   std::vector<int> page_hw((size_t)2 * n_pages);
   for (int p = 0; p < n_pages; ++p) {
     OCRS_CHECK(pages[p]->device == device_, kInvalidArg, "input lives on another device");
-    page_ptrs[p] = pages[p]->grey.as<float>();
+    page_ptrs[p] = pages[p]->grey();
     page_hw[p] = pages[p]->H;
     page_hw[n_pages + p] = pages[p]->W;
   }
@@ -387,9 +455,12 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
   OCRS_CUDA_CHECK(cudaMemcpyAsync(d_page_hw, page_hw.data(), 2 * n_pages * sizeof(int), cudaMemcpyHostToDevice, st_));
   OCRS_CUDA_CHECK(cudaMemcpyAsync(line_desc_.ptr, descs.data(), descs.size() * sizeof(img::LineDesc), cudaMemcpyHostToDevice, st_));
   OCRS_CUDA_CHECK(cudaMemcpyAsync(poly_.ptr, poly_xy.data(), poly_xy.size() * 4, cudaMemcpyHostToDevice, st_));
+  h2d_bytes_ += (int64_t)(descs.size() * sizeof(img::LineDesc) + poly_xy.size() * 4 + tab_bytes);
+  int tkc = prof_.begin("stage/crop_lines", st_);
   img::crop_lines(page_tab_.as<const float*>(), d_page_hw, d_page_hw + n_pages, line_desc_.as<img::LineDesc>(),
                   n_lines, poly_.as<int32_t>(), cross_.as<int32_t>(), rec_batch_.as<float>(), rec_h, max_gw, max_rows,
                   st_);
+  prof_.end(tkc, st_, 0, 2.0 * 4.0 * (double)dst_total);
   // host vectors must outlive the async copies
   OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
 
@@ -418,7 +489,9 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
   for (auto& c : chunks) {
     float* in_ptr = rec_batch_.as<float>() + descs[c.first].dst_off;
     ModelCost cost;
-    DTensor logits = rec_->run(wrap_tensor(in_ptr, {c.count, 1, rec_h, c.gw}), st_, &cost);
+    int tkr = prof_.begin("stage/rec_net", st_);
+    DTensor logits = rec_->run(wrap_tensor(in_ptr, {c.count, 1, rec_h, c.gw}), st_, &cost, &prof_, "rec/");
+    prof_.end(tkr, st_, cost.flops, cost.min_bytes);
     stats_.rec_flops += cost.flops;
     stats_.rec_batches += 1;
     OCRS_CHECK(logits.shape.size() == 3, kWrongOutput,
@@ -432,11 +505,14 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
     stats_.n_timesteps += (int64_t)c.T * c.count;
     ctc_scratch_.reserve((size_t)c.count * c.T * 4 + 4);
     int32_t* o = ctc_out_.as<int32_t>() + c.out_off;
+    int tkt = prof_.begin("stage/ctc_greedy", st_);
     img::ctc_greedy(logits.data, c.T, c.count, (int)n_classes, has_excluded_ ? d_excluded_.as<uint8_t>() : nullptr,
                     ctc_scratch_.as<int32_t>(), o, o + (int64_t)c.count * c.gw, o + (int64_t)c.count * c.gw * 2, st_);
+    prof_.end(tkt, st_, 0, 4.0 * (double)c.T * c.count * (double)n_classes);
     // ctc_scratch_ is reused by the next chunk on the same stream: ordering is preserved.
   }
   OCRS_CUDA_CHECK(cudaMemcpyAsync(h_pin_.ptr, ctc_out_.ptr, (size_t)out_total * 4, cudaMemcpyDeviceToHost, st_));
+  d2h_bytes_ += out_total * 4;
   OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
 
   // ---- host: CTC steps -> characters with boxes (recognition.rs:241-311) ----
@@ -498,7 +574,7 @@ std::vector<float> Engine::prepare_recognition_input(const OcrInput& in, const s
   d.lh = std::max(geom::rheight(pr), 0); d.lw = std::max(geom::rwidth(pr), 0);
   d.resized_width = (int32_t)rw; d.group_width = (int32_t)rw;
   d.dst_off = 0; d.cross_off = 0; d.max_cross = non_horizontal; d.page = 0;
-  const float* page_ptr = in.grey.as<float>();
+  const float* page_ptr = in.grey();
   int hw[2] = {in.H, in.W};
   page_tab_.reserve(sizeof(float*) + 2 * sizeof(int));
   line_desc_.reserve(sizeof(d));

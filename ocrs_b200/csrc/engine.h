@@ -34,9 +34,10 @@ struct EngineParams {  // lib.rs:37-71
 
 // `OcrInput` (lib.rs:125-128): greyscale page in [-0.5, 0.5], resident in HBM.
 struct OcrInput {
-  DeviceBuffer grey;  // f32 [H*W]
+  std::shared_ptr<Storage> store;  // f32 [H*W], stream-ordered allocation on the engine's stream
   int H = 0, W = 0;
   int device = 0;
+  float* grey() const { return reinterpret_cast<float*>(store->ptr); }
 };
 
 struct TextChar {  // text_items.rs:47-53
@@ -99,6 +100,15 @@ class Engine {
   void reset_stats() { stats_ = Stats(); }
   void synchronize();
 
+  // CUDA-event profiling of stages and of every operator of the two networks
+  void set_profiling(bool on);
+  std::string profile_json(bool reset);
+  // Event timer on the engine's stream (bench: device-side timing of the timed region)
+  void timer_start();
+  float timer_stop();
+  int64_t d2h_bytes() const { return d2h_bytes_; }
+  int64_t h2d_bytes() const { return h2d_bytes_; }
+
  private:
   struct PageScratch;  // per concurrent page: mask, labels, pools
   PageScratch& scratch_for(int slot, int H, int W);
@@ -120,6 +130,9 @@ class Engine {
   PinnedBuffer h_pin_;
   std::mutex mu_;
   Stats stats_;
+  Profiler prof_;
+  cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_copy_ = nullptr;
+  int64_t d2h_bytes_ = 0, h2d_bytes_ = 0;
 };
 
 std::vector<uint32_t> utf8_to_codepoints(const std::string& s);

@@ -9,6 +9,50 @@
 
 namespace ocrs {
 
+std::atomic<int64_t> g_kernel_launches{0};
+
+Profiler::~Profiler() {
+  for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : free_events_) cudaEventDestroy(e);
+}
+cudaEvent_t Profiler::get_event() {
+  if (!free_events_.empty()) { cudaEvent_t e = free_events_.back(); free_events_.pop_back(); return e; }
+  cudaEvent_t e;
+  OCRS_CUDA_CHECK(cudaEventCreate(&e));
+  return e;
+}
+int Profiler::begin(const std::string& name, cudaStream_t st) {
+  if (!enabled) return -1;
+  Pending p{name, get_event(), get_event(), 0, 0, g_kernel_launches.load(), 0};
+  OCRS_CUDA_CHECK(cudaEventRecord(p.a, st));
+  pending_.push_back(std::move(p));
+  return (int)pending_.size() - 1;
+}
+void Profiler::end(int token, cudaStream_t st, double flops, double bytes) {
+  if (token < 0) return;
+  Pending& p = pending_[(size_t)token];
+  OCRS_CUDA_CHECK(cudaEventRecord(p.b, st));
+  p.flops = flops;
+  p.bytes = bytes;
+  p.launches = g_kernel_launches.load() - p.launches0;
+}
+void Profiler::collect() {
+  for (auto& p : pending_) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      OpProfile& o = acc_[p.name];
+      o.ms += ms;
+      o.flops += p.flops;
+      o.bytes += p.bytes;
+      o.calls += 1;
+      o.launches += p.launches;
+    }
+    free_events_.push_back(p.a);
+    free_events_.push_back(p.b);
+  }
+  pending_.clear();
+}
+
 using onnx::Attr;
 using onnx::Node;
 using onnx::TensorData;
@@ -202,7 +246,8 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
   return m;
 }
 
-DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost) const {
+DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profiler* prof,
+                   const std::string& prof_prefix) const {
   const Impl* impl = impl_.get();
   const auto& g = graph_;
   OCRS_CHECK(input.shape.size() == input_shape_.size(), kRunFailed,
@@ -248,6 +293,8 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost) const
     auto has = [&](size_t i) { return i < in.size() && present[i]; };
     std::vector<Value> out;
     const std::string& op = n.op;
+    const double flops_before = flops;
+    int ptok = prof ? prof->begin(prof_prefix + op, st) : -1;
 
     if (op == "Conv") {
       const Value& X = in[0];
@@ -654,6 +701,7 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost) const
       throw Error(kRunFailed, "unsupported operator at run time: " + op);
     }
 
+    if (prof) prof->end(ptok, st, flops - flops_before);
     // publish outputs
     for (size_t k = 0; k < out.size() && k < n.outputs.size(); ++k) {
       std::string name = n.outputs[k];

@@ -58,7 +58,8 @@ class Model {
 
   // Runs the graph.  `input` lives on the device; the result is stream-ordered on `st`.
   // Re-entrant: any number of threads may call run() on one Model with distinct streams.
-  DTensor run(const DTensor& input, cudaStream_t st, ModelCost* cost = nullptr) const;
+  DTensor run(const DTensor& input, cudaStream_t st, ModelCost* cost = nullptr, Profiler* prof = nullptr,
+              const std::string& prof_prefix = "") const;
 
   size_t weight_bytes() const { return weight_bytes_; }
   const onnx::Graph& graph() const { return graph_; }

@@ -435,15 +435,22 @@ void prepare_image(const void* pixels, int dtype, int order, int H, int W, int C
         (reinterpret_cast<uintptr_t>(out) % 16 == 0)) {
       prepare_image_rgb8_x4_kernel<<<grid1d(hw / 4), kThreads, 0, st>>>(reinterpret_cast<const uint32_t*>(p),
                                                                          reinterpret_cast<float4*>(out), hw / 4, pw);
+  count_launch();
     } else if (order == 0) {
       prepare_image_kernel<uint8_t, true><<<grid1d(hw), kThreads, 0, st>>>(p, out, hw, C, pw);
+  count_launch();
     } else {
       prepare_image_kernel<uint8_t, false><<<grid1d(hw), kThreads, 0, st>>>(p, out, hw, C, pw);
+  count_launch();
     }
   } else {
     const float* p = static_cast<const float*>(pixels);
-    if (order == 0) prepare_image_kernel<float, true><<<grid1d(hw), kThreads, 0, st>>>(p, out, hw, C, pw);
-    else prepare_image_kernel<float, false><<<grid1d(hw), kThreads, 0, st>>>(p, out, hw, C, pw);
+    if (order == 0) {
+      prepare_image_kernel<float, true><<<grid1d(hw), kThreads, 0, st>>>(p, out, hw, C, pw);
+    } else {
+      prepare_image_kernel<float, false><<<grid1d(hw), kThreads, 0, st>>>(p, out, hw, C, pw);
+    }
+    count_launch();
   }
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -453,6 +460,7 @@ void resize_padded(const float* src, int H, int W, int padH, int padW, float pad
   if (OH == 0 || OW == 0 || n == 0) return;
   dim3 grid(grid1d(OW, 128), OH, n);
   resize_padded_kernel<<<grid, 128, 0, st>>>(src, H, W, padH, padW, pad_value, dst, OH, OW, src_stride, dst_stride);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -462,12 +470,14 @@ void resize_threshold(const float* net_out, int inH, int inW, int sliceH, int sl
   if (H == 0 || W == 0) return;
   dim3 grid(grid1d(W, 128), H);
   resize_threshold_kernel<<<grid, 128, 0, st>>>(net_out, inW, sliceH, sliceW, prob, mask, H, W, thr);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
 void threshold(const float* prob, uint8_t* mask, int64_t n, float thr, cudaStream_t st) {
   if (!n) return;
   threshold_kernel<<<grid1d(n), kThreads, 0, st>>>(prob, mask, n, thr);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -478,13 +488,17 @@ void find_component_rects(const uint8_t* mask, int H, int W, float eps, float ex
   if (n == 0) return;
   OCRS_CHECK(H < 32768 && W < 32768, kInvalidArg, "image dimensions exceed 32767");
   ccl_init_kernel<<<grid1d(n + 1), kThreads, 0, st>>>(b.labels, n);
+  count_launch();
   dim3 grid(grid1d(W, 128), H);
   ccl_merge_kernel<<<grid, 128, 0, st>>>(mask, b.labels, H, W);
+  count_launch();
   ccl_flatten_kernel<<<grid1d(n + 1), kThreads, 0, st>>>(mask, b.labels, n, b.comp_roots, b.counters, b.max_comps);
+  count_launch();
   // one thread per component; the count is only known on the device, so launch for the
   // theoretical maximum in chunks guarded by counters[0] (cheap: threads beyond n_comps exit).
   int max_c = b.max_comps;
   component_rects_kernel<<<grid1d(max_c, 64), 64, 0, st>>>(mask, H, W, eps, expand_dist, min_area, b);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -495,9 +509,11 @@ void crop_lines(const float* const* pages, const int* page_h, const int* page_w,
   if (max_rows > 0) {
     dim3 g1(grid1d(max_rows, 64), n_lines);
     line_crossings_kernel<<<g1, 64, 0, st>>>(lines, n_lines, poly_xy, cross_scratch);
+  count_launch();
   }
   dim3 g2(grid1d(max_group_width, 128), out_h, n_lines);
   crop_resize_kernel<<<g2, 128, 0, st>>>(pages, page_h, page_w, lines, n_lines, cross_scratch, dst, out_h);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -505,7 +521,9 @@ void ctc_greedy(const float* logits, int T, int B, int C, const uint8_t* exclude
                 int32_t* labels_out, int32_t* pos_out, int32_t* counts_out, cudaStream_t st) {
   if (B == 0) return;
   if (T > 0) ctc_argmax_kernel<<<grid1d((int64_t)T * B * 32), kThreads, 0, st>>>(logits, T, B, C, excluded, scratch_labels);
+  count_launch();
   ctc_collapse_kernel<<<grid1d(B, 64), 64, 0, st>>>(scratch_labels, T, B, labels_out, pos_out, counts_out);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 

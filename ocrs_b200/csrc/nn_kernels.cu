@@ -439,8 +439,10 @@ void conv2d(const float* x, const float* w, const float* b, float* y, const Conv
     int64_t npix = (int64_t)p.N * p.OH * p.OW;
     dim3 grid((unsigned)ceil_div(npix, BN), (unsigned)ceil_div(p.K, BM));
     conv_igemm_kernel<<<grid, 256, 0, st>>>(x, w, b, y, p);
+  count_launch();
   } else {
     conv_direct_kernel<<<grid1d(total), kThreads, 0, st>>>(x, w, b, y, p);
+  count_launch();
   }
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -450,6 +452,7 @@ void conv_transpose2d(const float* x, const float* w, const float* b, float* y, 
   int64_t total = (int64_t)p.N * p.K * p.OH * p.OW;
   if (total == 0) return;
   conv_transpose_kernel<<<grid1d(total), kThreads, 0, st>>>(x, w, b, y, p);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -457,38 +460,45 @@ void max_pool2d(const float* x, float* y, const PoolParams& p, cudaStream_t st) 
   int64_t total = (int64_t)p.NC * p.OH * p.OW;
   if (total == 0) return;
   pool_kernel<true><<<grid1d(total), kThreads, 0, st>>>(x, y, p);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 void avg_pool2d(const float* x, float* y, const PoolParams& p, cudaStream_t st) {
   int64_t total = (int64_t)p.NC * p.OH * p.OW;
   if (total == 0) return;
   pool_kernel<false><<<grid1d(total), kThreads, 0, st>>>(x, y, p);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
 void relu(const float* x, float* y, int64_t n, cudaStream_t st) {
   if (!n) return;
   unary_kernel<Unary::kRelu><<<grid1d(n), kThreads, 0, st>>>(x, y, n);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 void sigmoid(const float* x, float* y, int64_t n, cudaStream_t st) {
   if (!n) return;
   unary_kernel<Unary::kSigmoid><<<grid1d(n), kThreads, 0, st>>>(x, y, n);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 void tanh_op(const float* x, float* y, int64_t n, cudaStream_t st) {
   if (!n) return;
   unary_kernel<Unary::kTanh><<<grid1d(n), kThreads, 0, st>>>(x, y, n);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 void add_bcast_suffix(const float* a, const float* b, float* y, int64_t n, int64_t nb, cudaStream_t st) {
   if (!n) return;
   add_bcast_kernel<<<grid1d(n), kThreads, 0, st>>>(a, b, y, n, nb);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 void fill(float* y, float v, int64_t n, cudaStream_t st) {
   if (!n) return;
   fill_kernel<<<grid1d(n), kThreads, 0, st>>>(y, v, n);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -497,6 +507,7 @@ void sgemm_nt(const float* A, const float* B, const float* bias, float* C, int M
   if (M == 0 || N == 0) return;
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM));
   sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, B, bias, C, M, N, K, relu);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -516,6 +527,7 @@ void permute(const float* x, float* y, const int64_t* shape, const int* perm, in
     a.in_stride[d] = in_stride[perm[d]];
   }
   permute_kernel<<<grid1d(s), kThreads, 0, st>>>(x, y, a, s);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -524,6 +536,7 @@ void concat_copy(const float* x, float* y, int64_t outer, int64_t len_src, int64
   int64_t total = outer * len_src * inner;
   if (!total) return;
   concat_copy_kernel<<<grid1d(total), kThreads, 0, st>>>(x, y, outer, len_src, len_dst, dst_off, inner);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -539,12 +552,14 @@ void pad4d(const float* x, float* y, const int64_t in_shape[4], const int64_t be
   }
   if (!total) return;
   pad4d_kernel<<<grid1d(total), kThreads, 0, st>>>(x, y, a, value, total);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
 void log_softmax_lastdim(const float* x, float* y, int64_t rows, int cols, cudaStream_t st) {
   if (!rows) return;
   log_softmax_kernel<<<grid1d(rows * 32), kThreads, 0, st>>>(x, y, rows, cols);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -555,6 +570,7 @@ void gru_step(const float* xw, const float* R, const float* Rb, const float* h_i
   int t1 = (D > 1) ? (dir_reverse_host[1] ? T - 1 - step : step) : 0;
   dim3 grid((unsigned)ceil_div(N, GL), (unsigned)ceil_div(H, GJ), (unsigned)D);
   gru_step_kernel<<<grid, 256, 0, st>>>(xw, R, Rb, h_in, h_out, Y, D, T, N, H, t0, t1, lbr);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 

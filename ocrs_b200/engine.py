@@ -376,6 +376,36 @@ class OcrEngine:
                 "timesteps": int(buf[4]), "rec_batches": int(buf[5])}
 
 
+    # -- measurement hooks
+    def set_profiling(self, on: bool) -> None:
+        check(lib.ocrs_b200_engine_set_profiling(self._h, int(on)))
+
+    def profile(self, reset: bool = True) -> dict:
+        import json
+        s = C.c_char_p()
+        check(lib.ocrs_b200_engine_profile_json(self._h, C.byref(s), int(reset)))
+        out = json.loads(s.value.decode())
+        lib.ocrs_b200_free(s)
+        return out
+
+    def timer_start(self) -> None:
+        check(lib.ocrs_b200_engine_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        check(lib.ocrs_b200_engine_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def transfer_bytes(self) -> Tuple[int, int]:
+        buf = (C.c_int64 * 2)()
+        check(lib.ocrs_b200_engine_transfer_bytes(self._h, buf))
+        return int(buf[0]), int(buf[1])
+
+
+def kernel_launch_count() -> int:
+    return int(lib.ocrs_b200_kernel_launch_count())
+
+
 def find_text_lines(words: Sequence[RotatedRect]) -> List[List[RotatedRect]]:
     """layout_analysis.rs:158 through the C ABI (host code; needs no GPU)."""
     arr = _rects_to_c(words)

@@ -21,6 +21,8 @@ from tools.synth import make_page
 
 pytestmark = pytest.mark.gpu
 
+PROB_TOL = 1e-3  # north_star: "within 1e-3 fp32 of the reference"
+
 
 @pytest.fixture(scope="module")
 def engines():
@@ -37,9 +39,9 @@ def _staged_check(eng, ora, page):
 
     prob = eng.detect_text_pixels(inp)
     oprob = ora.detect_text_pixels(oimg)
-    assert np.abs(prob - oprob).max() < 1e-4
+    assert np.abs(prob - oprob).max() < PROB_TOL
     diff = threshold_mask(prob) != threshold_mask(oprob)
-    assert np.all(np.abs(oprob[diff] - np.float32(0.2)) <= 1e-4)
+    assert np.all(np.abs(oprob[diff] - np.float32(0.2)) <= PROB_TOL)
 
     words = eng.detect_words(inp)
     owords = find_connected_component_rects(threshold_mask(prob), 3.0, 100.0)

@@ -11,7 +11,7 @@ from tests.gpu_util import model_paths
 pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 1e-3
-PROB_TOL = 1e-4
+PROB_TOL = 1e-3
 
 
 @pytest.fixture(scope="module")

@@ -19,15 +19,17 @@ VOCAB = ("the of and to in is that it was for on are as with his they at be this
 
 
 def make_page(seed: int, height: int = 768, width: int = 1024, n_rows: int | None = None,
-              two_col: bool | None = None) -> Tuple[np.ndarray, List[str]]:
+              two_col: bool | None = None, with_boxes: bool = False):
     """White (250 +/- 5) page with rows of dark words rendered by cv2.putText.
-    Returns (HWC u8 RGB image, list of row strings)."""
+    Returns (HWC u8 RGB image, list of row strings); with_boxes adds a third item: per row, the
+    list of word boxes (top, left, bottom, right)."""
     rng = np.random.default_rng(seed)
     img = np.clip(250 + rng.normal(0, 2.0, (height, width, 1)), 0, 255).repeat(3, axis=2).astype(np.uint8)
     if two_col is None:
         two_col = bool(seed % 2)
     cols = [(24, width // 2 - 24), (width // 2 + 24, width - 24)] if two_col else [(24, width - 24)]
     texts: List[str] = []
+    all_boxes = []
     y = 30
     rows = 0
     while y < height - 20 and (n_rows is None or rows < n_rows):
@@ -37,22 +39,27 @@ def make_page(seed: int, height: int = 768, width: int = 1024, n_rows: int | Non
         for (x0, x1) in cols:
             x = x0 + int(rng.integers(0, 12))
             words = []
+            boxes = []
             while True:
                 w = VOCAB[int(rng.integers(0, len(VOCAB)))]
-                (tw, th), _ = cv2.getTextSize(w, cv2.FONT_HERSHEY_SIMPLEX, scale, thick)
+                (tw, th), base = cv2.getTextSize(w, cv2.FONT_HERSHEY_SIMPLEX, scale, thick)
                 if x + tw > x1:
                     break
                 shade = int(rng.integers(10, 60))
                 cv2.putText(img, w, (x, y + th), cv2.FONT_HERSHEY_SIMPLEX, scale, (shade, shade, shade), thick,
                             cv2.LINE_AA)
                 words.append(w)
+                boxes.append((y - 1, x - 1, y + th + base // 2 + 2, x + tw + 1))
                 x += tw + int(rng.integers(12, 20))
                 if rng.random() < 0.04:
                     break
             if words:
                 texts.append(" ".join(words))
+                all_boxes.append(boxes)
         y += line_h + int(rng.integers(4, 14))
         rows += 1
+    if with_boxes:
+        return img, texts, all_boxes
     return img, texts
 
 
