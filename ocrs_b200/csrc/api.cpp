@@ -89,10 +89,13 @@ struct ocrs_b200_model {
   std::mutex mu;
 };
 struct ocrs_b200_engine {
-  std::unique_ptr<Engine> engine;
+  std::shared_ptr<Engine> engine;
 };
+// An input keeps its engine (stream, memory pool) alive: handles may be destroyed in any order.
 struct ocrs_b200_input {
   std::unique_ptr<OcrInput> input;
+  std::shared_ptr<Engine> owner;
+  ~ocrs_b200_input() { input.reset(); }
 };
 
 extern "C" {
@@ -225,7 +228,7 @@ int ocrs_b200_engine_create(const ocrs_b200_engine_params* p, ocrs_b200_engine**
     ep.device = p->device;
     auto* e = new ocrs_b200_engine();
     try {
-      e->engine = std::make_unique<Engine>(ep);
+      e->engine = std::make_shared<Engine>(ep);
     } catch (...) {
       delete e;
       throw;
@@ -253,6 +256,7 @@ int ocrs_b200_engine_prepare_input_bytes(ocrs_b200_engine* e, const uint8_t* byt
     auto in = e->engine->prepare_input(bytes, 0, 0, (int)height, (int)width, (int)channels);
     auto* h = new ocrs_b200_input();
     h->input = std::move(in);
+    h->owner = e->engine;
     *out = h;
   });
 }
@@ -265,6 +269,7 @@ static int prepare_input_common(ocrs_b200_engine* e, const void* pixels, int dty
     auto in = e->engine->prepare_input(pixels, dtype, order, height, width, channels, on_device);
     auto* h = new ocrs_b200_input();
     h->input = std::move(in);
+    h->owner = e->engine;
     *out = h;
   });
 }

@@ -1,0 +1,500 @@
+// tcgen05 / TMEM / TMA implicit-GEMM 3x3 convolution (sm_100a).  See conv_tc.h.
+//
+// Tile: 128 output pixels (TH rows x TW columns of one image) x COUT channels per CTA.
+// K loop: 9 taps x (Cin / KC) channel chunks; per k-block TMA loads
+//   A_hi, A_lo : [128 pixels][KC] bf16, box {KC, TW, TH, 1} of the NHWC activation at
+//                (c0, w0 + kw - 1, h0 + kh - 1, n) -- the halo / zero padding is TMA out-of-bounds fill
+//   B_hi, B_lo : [COUT][KC] bf16 from the [COUT][9*Cin] weight matrix
+// into 128B- (KC = 64) or 64B- (KC = 32) swizzled shared memory; one elected thread issues
+//   D += A_hi*B_hi ; D += A_hi*B_lo ; D += A_lo*B_hi        (tcgen05.mma kind::f16, fp32 accumulate in TMEM)
+// and the four warps drain TMEM (tcgen05.ld 32x32b), add bias, ReLU, split to bf16 hi/lo, store NHWC.
+#include "conv_tc.h"
+
+#include <cuda.h>
+
+#include <mutex>
+#include <vector>
+
+namespace ocrs {
+namespace tc {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor layout)
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  constexpr uint64_t kLayout = (KC == 64) ? 2 : 4;          // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint64_t kSbo = ((KC == 64) ? 1024 : 512) >> 4;  // 8 rows of one swizzle atom
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major) = 1
+  d |= kSbo << 32;                          // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                   // descriptor version 1 (Blackwell)
+  d |= kLayout << 61;                       // layout type, bits [61,64)
+  return d;
+}
+
+template <int KC, int COUT>
+struct Cfg {
+  static constexpr int kABytes = 128 * KC * 2;
+  static constexpr int kBBytes = COUT * KC * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = (kStageBytes * 4 + 2048 <= 200 * 1024) ? 4 : 3;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int KC, int COUT>
+__global__ void __launch_bounds__(128, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi,
+                  __nv_bfloat16* __restrict__ out_lo, int N, int H, int W, int Cin, int TW, int TH, int relu) {
+  using C = Cfg<KC, COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+  int t = blockIdx.x;
+  const int tw_i = t % tiles_w;
+  t /= tiles_w;
+  const int th_i = t % tiles_h;
+  const int n = t / tiles_h;
+  const int w0 = tw_i * TW, h0 = th_i * TH;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, COUT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int chunks = Cin / KC;
+  const int nkb = 9 * chunks;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- TMA producer ----------------
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % C::kStages;
+      const uint32_t ph = (kb / C::kStages) & 1;
+      mbar_wait(empty_bar(s), ph ^ 1);
+      const uint32_t st = base + s * C::kStageBytes;
+      mbar_expect_tx(full_bar(s), C::kStageBytes);
+      const int tap = kb / chunks, c0 = (kb - tap * chunks) * KC;
+      const int kh = tap / 3, kw = tap - kh * 3;
+      tma_load_4d(st, &tm_x_hi, c0, w0 + kw - 1, h0 + kh - 1, n, full_bar(s));
+      tma_load_4d(st + C::kABytes, &tm_x_lo, c0, w0 + kw - 1, h0 + kh - 1, n, full_bar(s));
+      tma_load_2d(st + 2 * C::kABytes, &tm_w_hi, tap * Cin + c0, 0, full_bar(s));
+      tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tm_w_lo, tap * Cin + c0, 0, full_bar(s));
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % C::kStages;
+      const uint32_t ph = (kb / C::kStages) & 1;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t st = base + s * C::kStageBytes;
+      const uint32_t a_hi = st, a_lo = st + C::kABytes, b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
+#pragma unroll
+      for (int k = 0; k < KC / 16; ++k) {
+        const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle atom
+        const uint64_t da_hi = make_desc<KC>(a_hi + koff), da_lo = make_desc<KC>(a_lo + koff);
+        const uint64_t db_hi = make_desc<KC>(b_hi + koff), db_lo = make_desc<KC>(b_lo + koff);
+        umma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
+        umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
+        umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+      }
+      umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+    }
+    umma_commit(tmem_full_bar);
+  }
+  __syncwarp();
+
+  // ---------------- epilogue: all four warps ----------------
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  const int p = warp * 32 + lane;  // TMEM lane == pixel index inside the tile
+  const int th = p / TW, tw = p - th * TW;
+  const int h = h0 + th, w = w0 + tw;
+  const bool valid = (th < TH) && (h < H) && (w < W);
+  const size_t pix = ((size_t)n * H + h) * W + w;
+#pragma unroll 1
+  for (int c0 = 0; c0 < COUT; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    uint32_t hi_pack[16], lo_pack[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float v0 = __uint_as_float(r[j]) + bias[c0 + j];
+      float v1 = __uint_as_float(r[j + 1]) + bias[c0 + j + 1];
+      if (relu) {
+        v0 = fmaxf(v0, 0.f);
+        v1 = fmaxf(v1, 0.f);
+      }
+      __nv_bfloat16 h0b = __float2bfloat16_rn(v0), h1b = __float2bfloat16_rn(v1);
+      __nv_bfloat16 l0b = __float2bfloat16_rn(v0 - __bfloat162float(h0b));
+      __nv_bfloat16 l1b = __float2bfloat16_rn(v1 - __bfloat162float(h1b));
+      hi_pack[j / 2] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+      lo_pack[j / 2] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+    }
+    if (valid) {
+      uint4* dh = reinterpret_cast<uint4*>(out_hi + pix * COUT + c0);
+      uint4* dl = reinterpret_cast<uint4*>(out_lo + pix * COUT + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dh[q] = make_uint4(hi_pack[4 * q], hi_pack[4 * q + 1], hi_pack[4 * q + 2], hi_pack[4 * q + 3]);
+        dl[q] = make_uint4(lo_pack[4 * q], lo_pack[4 * q + 1], lo_pack[4 * q + 2], lo_pack[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, COUT);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout converters / pooling (bandwidth-bound helpers)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                          __nv_bfloat16* __restrict__ lo, int C, int64_t HW, int64_t total_pix) {
+  // one thread per (pixel, 8-channel group): coalesced reads along pixels, 16-byte writes
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int groups = C / 8;
+  int64_t pix = idx % total_pix;
+  int g = (int)(idx / total_pix);
+  if (g >= groups) return;
+  int64_t n = pix / HW, rem = pix - n * HW;
+  const float* src = x + (n * C + (int64_t)g * 8) * HW + rem;
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(src[(int64_t)j * HW], h0, l0);
+    split_bf16(src[(int64_t)(j + 1) * HW], h1, l1);
+    ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4*>(hi + pix * C + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  *reinterpret_cast<uint4*>(lo + pix * C + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+__global__ void nhwc_split_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                          float* __restrict__ y, int C, int64_t HW, int64_t total_pix) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int groups = C / 8;
+  int64_t pix = idx % total_pix;
+  int g = (int)(idx / total_pix);
+  if (g >= groups) return;
+  int64_t n = pix / HW, rem = pix - n * HW;
+  uint4 vh = *reinterpret_cast<const uint4*>(hi + pix * C + g * 8);
+  uint4 vl = *reinterpret_cast<const uint4*>(lo + pix * C + g * 8);
+  const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
+  float* dst = y + (n * C + (int64_t)g * 8) * HW + rem;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+    float b = __uint_as_float(hh[j] & 0xFFFF0000u) + __uint_as_float(ll[j] & 0xFFFF0000u);
+    dst[(int64_t)(2 * j) * HW] = a;
+    dst[(int64_t)(2 * j + 1) * HW] = b;
+  }
+}
+
+__global__ void maxpool_nhwc_split_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
+                                          __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int N,
+                                          int H, int W, int C, int ph, int pw) {
+  const int OH = H / ph, OW = W / pw, groups = C / 8;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)N * OH * OW * groups;
+  if (idx >= total) return;
+  int g = (int)(idx % groups);
+  int64_t opix = idx / groups;
+  int ow = (int)(opix % OW);
+  int oh = (int)((opix / OW) % OH);
+  int n = (int)(opix / ((int64_t)OW * OH));
+  float best[8];
+  uint32_t bh[4] = {0, 0, 0, 0}, bl[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+  for (int r = 0; r < ph; ++r)
+    for (int s = 0; s < pw; ++s) {
+      int64_t ipix = ((int64_t)n * H + oh * ph + r) * W + ow * pw + s;
+      uint4 vh = *reinterpret_cast<const uint4*>(x_hi + ipix * C + g * 8);
+      uint4 vl = *reinterpret_cast<const uint4*>(x_lo + ipix * C + g * 8);
+      const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+        float b = __uint_as_float(hh[j] & 0xFFFF0000u) + __uint_as_float(ll[j] & 0xFFFF0000u);
+        if (a > best[2 * j]) {
+          best[2 * j] = a;
+          bh[j] = (bh[j] & 0xFFFF0000u) | (hh[j] & 0xFFFFu);
+          bl[j] = (bl[j] & 0xFFFF0000u) | (ll[j] & 0xFFFFu);
+        }
+        if (b > best[2 * j + 1]) {
+          best[2 * j + 1] = b;
+          bh[j] = (bh[j] & 0xFFFFu) | (hh[j] & 0xFFFF0000u);
+          bl[j] = (bl[j] & 0xFFFFu) | (ll[j] & 0xFFFF0000u);
+        }
+      }
+    }
+  *reinterpret_cast<uint4*>(y_hi + opix * C + g * 8) = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+  *reinterpret_cast<uint4*>(y_lo + opix * C + g * 8) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+CUtensorMap make_map(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, CUtensorMapSwizzle swz) {
+  CUtensorMap m;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr),
+                            reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                            reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OCRS_CHECK(r == CUDA_SUCCESS, kCuda, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+template <int KC, int COUT>
+void launch_conv(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvWeightsTC& w, __nv_bfloat16* y_hi,
+                 __nv_bfloat16* y_lo, int N, int H, int W, int relu, cudaStream_t st) {
+  using C = Cfg<KC, COUT>;
+  const int Cin = w.Cin;
+  int TW = W > 64 ? 128 : (W > 32 ? 64 : (W > 16 ? 32 : 16));
+  int TH = 128 / TW;
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  uint32_t xb[4] = {(uint32_t)KC, (uint32_t)TW, (uint32_t)TH, 1};
+  CUtensorMap tm_x_hi = make_map(x_hi, 4, xd, xs, xb, swz);
+  CUtensorMap tm_x_lo = make_map(x_lo, 4, xd, xs, xb, swz);
+  uint64_t wd[2] = {(uint64_t)9 * Cin, (uint64_t)COUT};
+  uint64_t ws[1] = {(uint64_t)9 * Cin * 2};
+  uint32_t wb[2] = {(uint32_t)KC, (uint32_t)COUT};
+  CUtensorMap tm_w_hi = make_map(w.w_hi.ptr, 2, wd, ws, wb, swz);
+  CUtensorMap tm_w_lo = make_map(w.w_lo.ptr, 2, wd, ws, wb, swz);
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+  conv3x3_tc_kernel<KC, COUT><<<tiles, 128, C::kSmemBytes, st>>>(tm_x_hi, tm_x_lo, tm_w_hi, tm_w_lo,
+                                                                   w.bias.as<float>(), y_hi, y_lo, N, H, W, Cin, TW, TH,
+                                                                   relu);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+bool available() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0;
+    cudaDeviceProp prop{};
+    bool ok = cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess &&
+              prop.major == 10 && get_encode() != nullptr;
+    if (!ok) cudaGetLastError();
+    cached = ok ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+bool conv_supported(int Cin, int Cout, int R, int S, int stride_h, int stride_w, int pad_t, int pad_l, int pad_b,
+                    int pad_r, int dil_h, int dil_w, int groups) {
+  return R == 3 && S == 3 && stride_h == 1 && stride_w == 1 && pad_t == 1 && pad_l == 1 && pad_b == 1 && pad_r == 1 &&
+         dil_h == 1 && dil_w == 1 && groups == 1 && (Cin == 32 || Cin % 64 == 0) && (Cout == 64 || Cout == 128);
+}
+
+std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, int Cin, int Cout) {
+  auto out = std::make_unique<ConvWeightsTC>();
+  out->Cin = Cin;
+  out->Cout = Cout;
+  const size_t K = (size_t)9 * Cin;
+  std::vector<__nv_bfloat16> hi(K * Cout), lo(K * Cout);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          float v = w[(((size_t)co * Cin + ci) * 3 + kh) * 3 + kw];
+          __nv_bfloat16 h = __float2bfloat16_rn(v);
+          __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+          size_t k = (size_t)(kh * 3 + kw) * Cin + ci;
+          hi[(size_t)co * K + k] = h;
+          lo[(size_t)co * K + k] = l;
+        }
+  std::vector<float> bias((size_t)Cout, 0.f);
+  if (b) bias.assign(b, b + Cout);
+  out->w_hi.reserve(hi.size() * 2);
+  out->w_lo.reserve(lo.size() * 2);
+  out->bias.reserve(bias.size() * 4);
+  OCRS_CUDA_CHECK(cudaMemcpy(out->w_hi.ptr, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+  OCRS_CUDA_CHECK(cudaMemcpy(out->w_lo.ptr, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+  OCRS_CUDA_CHECK(cudaMemcpy(out->bias.ptr, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  return out;
+}
+
+void conv3x3(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvWeightsTC& w, __nv_bfloat16* y_hi,
+             __nv_bfloat16* y_lo, int N, int H, int W, int relu, cudaStream_t st) {
+  if (N == 0 || H == 0 || W == 0) return;
+  const bool k64 = (w.Cin % 64 == 0);
+  if (k64 && w.Cout == 128) launch_conv<64, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, st);
+  else if (k64 && w.Cout == 64) launch_conv<64, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, st);
+  else if (!k64 && w.Cout == 128) launch_conv<32, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, st);
+  else if (!k64 && w.Cout == 64) launch_conv<32, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, st);
+  else throw Error(kInternal, "conv3x3 (tensor core): unsupported channel configuration");
+}
+
+void nchw_to_nhwc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int C, int H, int W,
+                        cudaStream_t st) {
+  OCRS_CHECK(C % 8 == 0, kInternal, "nchw_to_nhwc_split: C must be a multiple of 8");
+  int64_t HW = (int64_t)H * W, total_pix = (int64_t)N * HW, total = total_pix * (C / 8);
+  if (!total) return;
+  nchw_to_nhwc_split_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(x, hi, lo, C, HW, total_pix);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void nhwc_split_to_nchw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* y, int N, int C, int H, int W,
+                        cudaStream_t st) {
+  OCRS_CHECK(C % 8 == 0, kInternal, "nhwc_split_to_nchw: C must be a multiple of 8");
+  int64_t HW = (int64_t)H * W, total_pix = (int64_t)N * HW, total = total_pix * (C / 8);
+  if (!total) return;
+  nhwc_split_to_nchw_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(hi, lo, y, C, HW, total_pix);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void maxpool_nhwc_split(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, __nv_bfloat16* y_hi,
+                        __nv_bfloat16* y_lo, int N, int H, int W, int C, int ph, int pw, cudaStream_t st) {
+  OCRS_CHECK(C % 8 == 0, kInternal, "maxpool_nhwc_split: C must be a multiple of 8");
+  int64_t total = (int64_t)N * (H / ph) * (W / pw) * (C / 8);
+  if (!total) return;
+  maxpool_nhwc_split_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(x_hi, x_lo, y_hi, y_lo, N, H, W, C, ph, pw);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace tc
+}  // namespace ocrs

@@ -1,0 +1,53 @@
+// Dense 3x3 convolutions of the recognition CRNN on the 5th-generation tensor cores:
+// implicit GEMM, TMA-fed, tcgen05.mma with the accumulator in TMEM (sm_100a only).
+//
+// Precision: the reference computes in fp32 and BASELINE.json asks for log-probs within 1e-3 of
+// it, so operands are carried as split bf16 (x = hi + lo, 16 mantissa bits) in NHWC and every
+// k-block issues three MMAs (hi*hi + hi*lo + lo*hi) into one fp32 accumulator.
+//
+// Replaces rten's Conv operator kernels (reached through `Model::run`, ocrs/src/model.rs:33-40)
+// for the layers where `group == 1`, kernel 3x3, stride 1, pad 1 and C_in is a multiple of 32.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+
+#include "common.h"
+
+namespace ocrs {
+namespace tc {
+
+// True when the tcgen05 path can be used on this device / build (sm_100 family, driver entry
+// point for cuTensorMapEncodeTiled resolvable).
+bool available();
+
+struct ConvWeightsTC {
+  int Cin = 0, Cout = 0;
+  DeviceBuffer w_hi, w_lo;  // bf16 [Cout][9*Cin], k = (kh*3 + kw)*Cin + ci
+  DeviceBuffer bias;        // f32 [Cout]
+};
+
+// Eligibility of one Conv node (shapes only).
+bool conv_supported(int Cin, int Cout, int R, int S, int stride_h, int stride_w, int pad_t, int pad_l, int pad_b,
+                    int pad_r, int dil_h, int dil_w, int groups);
+
+// Re-lays out ONNX weights [Cout][Cin][3][3] (+ bias, may be null) for the kernel.
+std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, int Cin, int Cout);
+
+// y = relu?(conv3x3(x) + bias); x, y: NHWC split bf16.  x: [N,H,W,Cin], y: [N,H,W,Cout].
+void conv3x3(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvWeightsTC& w, __nv_bfloat16* y_hi,
+             __nv_bfloat16* y_lo, int N, int H, int W, int relu, cudaStream_t st);
+
+// Layout / precision converters and the pooling used between tensor-core layers.
+void nchw_to_nhwc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int C, int H, int W,
+                        cudaStream_t st);
+void nhwc_split_to_nchw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* y, int N, int C, int H, int W,
+                        cudaStream_t st);
+// max-pool with kernel == stride == (ph, pw), no padding; NHWC split in and out.
+void maxpool_nhwc_split(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, __nv_bfloat16* y_hi,
+                        __nv_bfloat16* y_lo, int N, int H, int W, int C, int ph, int pw, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace ocrs

@@ -2,9 +2,11 @@
 #include "executor.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
+#include "conv_tc.h"
 #include "nn_kernels.h"
 
 namespace ocrs {
@@ -62,7 +64,13 @@ Storage::Storage(size_t n, cudaStream_t st) : bytes(n), stream(st) {
   OCRS_CUDA_CHECK(cudaMallocAsync(&ptr, n, st));
 }
 Storage::~Storage() {
-  if (ptr && owned) cudaFreeAsync(ptr, stream);
+  if (ptr && owned) {
+    if (cudaFreeAsync(ptr, stream) != cudaSuccess) {
+      cudaGetLastError();  // do not leave a sticky error behind for unrelated launches
+      cudaFree(ptr);
+      cudaGetLastError();
+    }
+  }
 }
 
 void configure_device_pool(int device) {
@@ -123,10 +131,24 @@ std::shared_ptr<Storage> upload(const void* host, size_t bytes) {
 
 }  // namespace
 
+struct TcUnit {
+  int conv_node = -1, pool_node = -1;
+  int ph = 1, pw = 1, relu = 0;
+  std::unique_ptr<tc::ConvWeightsTC> w;
+};
+struct TcChain {
+  std::vector<TcUnit> units;
+  std::string out_name;  // published name of the chain's result
+};
+
 struct Model::Impl {
   // per GRU node: Wb [D][3H], Rb [D][3H]
   std::map<int, std::pair<std::shared_ptr<Storage>, std::shared_ptr<Storage>>> gru_bias;
   std::vector<std::string> out_rename;  // per node: published name of output 0 ("" = own name)
+  // tensor-core conv chains (Conv3x3 [+Relu] [+MaxPool]) keyed by their first node
+  std::map<int, TcChain> tc_chains;
+  std::vector<int> tc_member;  // node is executed as part of a chain started earlier
+  bool tc_enabled = false;
 };
 
 Model::Model() = default;
@@ -200,6 +222,82 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
       if (!in.empty()) m->use_count_[in]++;
   }
   for (const auto& o : g.outputs) m->use_count_[o.name] += 1 << 20;
+
+  // ---- tensor-core chains: Conv(3x3,s1,p1,g1) [+Relu fused] [+MaxPool k==s] ... ----
+  impl->tc_member.assign(nn_, 0);
+  impl->tc_enabled = tc::available() && std::getenv("OCRS_B200_DISABLE_TC") == nullptr;
+  if (impl->tc_enabled) {
+    auto published = [&](int i) { return impl->out_rename[i].empty() ? g.nodes[i].outputs[0] : impl->out_rename[i]; };
+    auto conv_ok = [&](const Node& n) {
+      if (n.op != "Conv" || n.inputs.size() < 2) return false;
+      auto wit = g.initializers.find(n.inputs[1]);
+      if (wit == g.initializers.end() || wit->second.dims.size() != 4) return false;
+      if (n.inputs.size() > 2 && !n.inputs[2].empty() && !g.initializers.count(n.inputs[2])) return false;
+      auto pads = n.attr_ints("pads", {0, 0, 0, 0});
+      auto st = n.attr_ints("strides", {1, 1});
+      auto dl = n.attr_ints("dilations", {1, 1});
+      int grp = (int)n.attr_i("group", 1);
+      const auto& d = wit->second.dims;
+      return n.attr_s("auto_pad", "NOTSET") == "NOTSET" &&
+             tc::conv_supported((int)d[1] * grp, (int)d[0], (int)d[2], (int)d[3], (int)st[0], (int)st[1], (int)pads[0],
+                                (int)pads[1], (int)pads[2], (int)pads[3], (int)dl[0], (int)dl[1], grp);
+    };
+    auto sole_consumer = [&](const std::string& name) -> int {
+      if (graph_outs.count(name)) return -1;
+      int found = -1, cnt = 0;
+      for (int j = 0; j < nn_; ++j) {
+        if (m->skip_[j]) continue;
+        for (const auto& in : g.nodes[j].inputs)
+          if (in == name) { ++cnt; found = j; }
+      }
+      return cnt == 1 ? found : -1;
+    };
+    for (int i = 0; i < nn_; ++i) {
+      if (m->skip_[i] || impl->tc_member[i] || !conv_ok(g.nodes[i])) continue;
+      TcChain chain;
+      int cur = i;
+      while (true) {
+        const Node& cn = g.nodes[cur];
+        TcUnit u;
+        u.conv_node = cur;
+        u.relu = m->fuse_relu_[cur];
+        const auto& wt = g.initializers.at(cn.inputs[1]);
+        const float* bptr = (cn.inputs.size() > 2 && !cn.inputs[2].empty()) ? g.initializers.at(cn.inputs[2]).f32() : nullptr;
+        u.w = tc::prepare_weights(wt.f32(), bptr, (int)wt.dims[1], (int)wt.dims[0]);
+        std::string out = published(cur);
+        int nxt = sole_consumer(out);
+        if (nxt >= 0 && g.nodes[nxt].op == "MaxPool" && g.nodes[nxt].inputs[0] == out) {
+          const Node& pn = g.nodes[nxt];
+          auto ks = pn.attr_ints("kernel_shape", {});
+          auto ps = pn.attr_ints("pads", {0, 0, 0, 0});
+          auto ss = pn.attr_ints("strides", {1, 1});
+          bool ok = ks.size() == 2 && ss.size() == 2 && ks[0] == ss[0] && ks[1] == ss[1] && pn.attr_i("ceil_mode", 0) == 0 &&
+                    ps[0] == 0 && ps[1] == 0 && ps[2] == 0 && ps[3] == 0 && pn.outputs.size() == 1;
+          if (ok) {
+            u.pool_node = nxt;
+            u.ph = (int)ks[0];
+            u.pw = (int)ks[1];
+            out = pn.outputs[0];
+            nxt = sole_consumer(out);
+          }
+        }
+        chain.units.push_back(std::move(u));
+        chain.out_name = out;
+        if (nxt >= 0 && !m->skip_[nxt] && conv_ok(g.nodes[nxt]) && g.nodes[nxt].inputs[0] == out &&
+            g.initializers.at(g.nodes[nxt].inputs[1]).dims[1] == g.initializers.at(g.nodes[chain.units.back().conv_node].inputs[1]).dims[0]) {
+          cur = nxt;
+          continue;
+        }
+        break;
+      }
+      for (size_t k = 0; k < chain.units.size(); ++k) {
+        if (k > 0) impl->tc_member[chain.units[k].conv_node] = 1;
+        if (chain.units[k].pool_node >= 0) impl->tc_member[chain.units[k].pool_node] = 1;
+      }
+      impl->tc_chains[i] = std::move(chain);
+    }
+    // chain-internal values are never published: drop their use counts
+  }
 
   // upload float initializers
   for (const auto& kv : g.initializers) {
@@ -282,8 +380,47 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
   };
 
   for (int ni = 0; ni < (int)g.nodes.size(); ++ni) {
-    if (skip_[ni]) continue;
+    if (skip_[ni] || impl->tc_member[ni]) continue;
     const Node& n = g.nodes[ni];
+    auto chain_it = impl->tc_chains.find(ni);
+    if (chain_it != impl->tc_chains.end()) {
+      // ---- Conv3x3(+ReLU)(+MaxPool) chain on the tensor cores (NHWC split-bf16) ----
+      const TcChain& ch = chain_it->second;
+      Value X = get(n.inputs[0]);
+      OCRS_CHECK(!X.is_int && X.shape.size() == 4, kRunFailed, "Conv: expected 4-D input");
+      int N_ = (int)X.shape[0], C_ = (int)X.shape[1], H_ = (int)X.shape[2], W_ = (int)X.shape[3];
+      OCRS_CHECK(C_ == ch.units[0].w->Cin, kRunFailed, "Conv: channel mismatch");
+      int ptok = prof ? prof->begin(prof_prefix + "ConvTC", st) : -1;
+      const double flops_before = flops;
+      auto alloc_bf16 = [&](int64_t elems) { return std::make_shared<Storage>((size_t)elems * 2, st); };
+      int64_t elems = (int64_t)N_ * H_ * W_ * C_;
+      auto cur_hi = alloc_bf16(elems), cur_lo = alloc_bf16(elems);
+      tc::nchw_to_nhwc_split(X.t.data, (__nv_bfloat16*)cur_hi->ptr, (__nv_bfloat16*)cur_lo->ptr, N_, C_, H_, W_, st);
+      for (const TcUnit& u : ch.units) {
+        int Co = u.w->Cout;
+        int64_t oe = (int64_t)N_ * H_ * W_ * Co;
+        auto o_hi = alloc_bf16(oe), o_lo = alloc_bf16(oe);
+        tc::conv3x3((const __nv_bfloat16*)cur_hi->ptr, (const __nv_bfloat16*)cur_lo->ptr, *u.w, (__nv_bfloat16*)o_hi->ptr,
+                    (__nv_bfloat16*)o_lo->ptr, N_, H_, W_, u.relu, st);
+        flops += 2.0 * N_ * H_ * W_ * (double)Co * C_ * 9.0;
+        cur_hi = o_hi; cur_lo = o_lo; C_ = Co;
+        if (u.pool_node >= 0) {
+          int OH = H_ / u.ph, OW = W_ / u.pw;
+          int64_t pe = (int64_t)N_ * OH * OW * C_;
+          auto p_hi = alloc_bf16(pe), p_lo = alloc_bf16(pe);
+          tc::maxpool_nhwc_split((const __nv_bfloat16*)cur_hi->ptr, (const __nv_bfloat16*)cur_lo->ptr,
+                                 (__nv_bfloat16*)p_hi->ptr, (__nv_bfloat16*)p_lo->ptr, N_, H_, W_, C_, u.ph, u.pw, st);
+          cur_hi = p_hi; cur_lo = p_lo; H_ = OH; W_ = OW;
+        }
+      }
+      DTensor Y = alloc_tensor({N_, C_, H_, W_}, st);
+      tc::nhwc_split_to_nchw((const __nv_bfloat16*)cur_hi->ptr, (const __nv_bfloat16*)cur_lo->ptr, Y.data, N_, C_, H_, W_, st);
+      if (prof) prof->end(ptok, st, flops - flops_before);
+      env[ch.out_name] = dev_value(Y);
+      auto it0 = remaining.find(n.inputs[0]);
+      if (it0 != remaining.end() && --it0->second <= 0) env.erase(n.inputs[0]);
+      continue;
+    }
     std::vector<Value> in;
     std::vector<bool> present;
     for (const auto& name : n.inputs) {
