@@ -7,6 +7,7 @@
 #include <set>
 
 #include "conv_tc.h"
+#include "gru_tc.h"
 #include "nn_kernels.h"
 
 namespace ocrs {
@@ -147,6 +148,7 @@ struct Model::Impl {
   std::vector<std::string> out_rename;  // per node: published name of output 0 ("" = own name)
   // tensor-core conv chains (Conv3x3 [+Relu] [+MaxPool]) keyed by their first node
   std::map<int, TcChain> tc_chains;
+  std::map<int, std::unique_ptr<tc::GruWeightsTC>> tc_gru;  // per GRU node
   std::vector<int> tc_member;  // node is executed as part of a chain started earlier
   bool tc_enabled = false;
 };
@@ -336,6 +338,14 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
         }
       }
       impl->gru_bias[i] = {upload(wb.data(), wb.size() * 4), upload(rb.data(), rb.size() * 4)};
+      {
+        int64_t Hh = H3 / 3, Ii = wit->second.dims[2];
+        if (impl->tc_enabled && std::getenv("OCRS_B200_DISABLE_TC_GRU") == nullptr &&
+            tc::gru_supported((int)D, (int)Hh, (int)Ii)) {
+          const float* bptr = (n.inputs.size() > 3 && !n.inputs[3].empty()) ? g.initializers.at(n.inputs[3]).f32() : nullptr;
+          impl->tc_gru[i] = tc::prepare_gru(wit->second.f32(), rit->second.f32(), bptr, (int)D, (int)Hh, (int)Ii);
+        }
+      }
       OCRS_CHECK(n.attr_i("linear_before_reset", 0) != 0, kModelLoad,
                  "GRU with linear_before_reset=0 is not supported (PyTorch exports use 1)");
     }
@@ -809,6 +819,21 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
       const auto& gb = impl->gru_bias.at(ni);
       const float* Wb = reinterpret_cast<const float*>(gb.first->ptr);
       const float* Rb = reinterpret_cast<const float*>(gb.second->ptr);
+      auto tcg = impl->tc_gru.find(ni);
+      if (tcg != impl->tc_gru.end()) {
+        OCRS_CHECK(!has(5) || in[5].numel() == (int64_t)D * N * H, kRunFailed, "GRU: initial_h shape mismatch");
+        DTensor Y = alloc_tensor({T, D, N, H}, st);
+        bool want_yh = n.outputs.size() > 1 && !n.outputs[1].empty() && remaining.count(n.outputs[1]);
+        DTensor Yh;
+        if (want_yh) Yh = alloc_tensor({D, N, H}, st);
+        std::vector<std::shared_ptr<Storage>> scratch;
+        tc::gru_forward(X.t.data, *tcg->second, has(5) ? in[5].t.data : nullptr, Y.data, want_yh ? Yh.data : nullptr, T, N,
+                        rev, [&](size_t bytes) { scratch.push_back(std::make_shared<Storage>(bytes, st)); return scratch.back()->ptr; },
+                        st);
+        flops += 2.0 * D * T * N * 3.0 * H * (I + H);
+        out.push_back(dev_value(Y));
+        if (want_yh) out.push_back(dev_value(Yh));
+      } else {
       DTensor xw = alloc_tensor({D, (int64_t)T * N, 3 * H}, st);
       for (int d = 0; d < D; ++d)
         nn::sgemm_nt(X.t.data, W.t.data + (int64_t)d * 3 * H * I, Wb + (int64_t)d * 3 * H,
@@ -833,6 +858,7 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
         DTensor Yh = alloc_tensor({D, N, H}, st);
         OCRS_CUDA_CHECK(cudaMemcpyAsync(Yh.data, hin, sizeof(float) * D * N * H, cudaMemcpyDeviceToDevice, st));
         out.push_back(dev_value(Yh));
+      }
       }
     } else {
       throw Error(kRunFailed, "unsupported operator at run time: " + op);

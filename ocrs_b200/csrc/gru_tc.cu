@@ -1,0 +1,675 @@
+// Tensor-core GRU: input-projection GEMM + persistent recurrent kernel (sm_100a).  See gru_tc.h.
+#include "gru_tc.h"
+
+#include "conv_tc.h"
+
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <vector>
+
+#include "tc_host.h"
+#include "tc_ptx.cuh"
+
+namespace ocrs {
+namespace tc {
+
+namespace {
+
+using namespace ptx;
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// f32 -> split bf16 planes, 8 elements per thread
+__global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                             int64_t n8) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[j], h0, l0);
+    split_bf16(v[j + 1], h1, l1);
+    ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  reinterpret_cast<uint4*>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  reinterpret_cast<uint4*>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// C[M, Ntot] (f32) = A[M, K] * B[Ntot, K]^T + bias[Ntot]; A, B split bf16, K-major.
+// Tile 128 x 128, K chunks of 64, 3 stages (64 KB each).
+// ------------------------------------------------------------------------------------------
+constexpr int kGemmStages = 3;
+constexpr int kGemmTile = 128 * 64 * 2;                 // one operand plane of one stage
+constexpr int kGemmStageBytes = 4 * kGemmTile;          // A_hi, A_lo, B_hi, B_lo
+constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(128, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+               const float* __restrict__ bias, float* __restrict__ Cout, int M, int Ntot, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kGemmStages * kGemmStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kGemmStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kGemmStages);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const int nkb = K / 64;
+
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kGemmStages;
+      const uint32_t ph = (kb / kGemmStages) & 1;
+      mbar_wait(empty_bar(s), ph ^ 1);
+      const uint32_t st = base + s * kGemmStageBytes;
+      mbar_expect_tx(full_bar(s), kGemmStageBytes);
+      tma_load_2d(st, &tm_a_hi, kb * 64, m0, full_bar(s));
+      tma_load_2d(st + kGemmTile, &tm_a_lo, kb * 64, m0, full_bar(s));
+      tma_load_2d(st + 2 * kGemmTile, &tm_b_hi, kb * 64, n0, full_bar(s));
+      tma_load_2d(st + 3 * kGemmTile, &tm_b_lo, kb * 64, n0, full_bar(s));
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kGemmStages;
+      const uint32_t ph = (kb / kGemmStages) & 1;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t st = base + s * kGemmStageBytes;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t koff = k * 32;
+        const uint64_t da_hi = make_desc<64>(st + koff), da_lo = make_desc<64>(st + kGemmTile + koff);
+        const uint64_t db_hi = make_desc<64>(st + 2 * kGemmTile + koff), db_lo = make_desc<64>(st + 3 * kGemmTile + koff);
+        umma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
+        umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
+        umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+      }
+      umma_commit(empty_bar(s));
+    }
+    umma_commit(tmem_full_bar);
+  }
+  __syncwarp();
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    if (row < M) {
+      float4* dst = reinterpret_cast<float4*>(Cout + (size_t)row * Ntot + n0 + c0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 v;
+        v.x = __uint_as_float(r[4 * q]) + bias[n0 + c0 + 4 * q];
+        v.y = __uint_as_float(r[4 * q + 1]) + bias[n0 + c0 + 4 * q + 1];
+        v.z = __uint_as_float(r[4 * q + 2]) + bias[n0 + c0 + 4 * q + 2];
+        v.w = __uint_as_float(r[4 * q + 3]) + bias[n0 + c0 + 4 * q + 3];
+        dst[q] = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent recurrent kernel.  H = 256.  CTA = (tile of NL lines, direction).
+//   D[gate row (6 tiles x 128 lanes)][line] = R[768 x 256] * h_{t-1}^T[256 x NL]
+// TMEM column of (tile, line) = tile * NL + line, tile = gate * 2 + unit / 128, lane = unit % 128,
+// so one thread finds z, r, n of its unit in the same lane of three column blocks.
+// ------------------------------------------------------------------------------------------
+constexpr int NL = 32;
+constexpr int kRecStages = 4;
+constexpr int kRTile = 128 * 64 * 2;                 // one plane of one R stage (16 KB)
+constexpr int kRecStageBytes = 2 * kRTile;
+constexpr int kHSub = NL * 128;                      // one 64-wide K sub-tile of h (bytes)
+constexpr int kHPlane = 4 * kHSub;                   // h plane (hi or lo): [NL][256] bf16
+constexpr int kRecSmem = kRecStages * kRecStageBytes + 2 * kHPlane + 1024 + 256;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(192, 1)
+gru_rec_tc_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
+                  const float* __restrict__ xw, const float* __restrict__ rb, const float* __restrict__ h0,
+                  float* __restrict__ Y, float* __restrict__ Yh, int T, int N, int D, int rev0, int rev1) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t h_hi = base + kRecStages * kRecStageBytes;
+  const uint32_t h_lo = h_hi + kHPlane;
+  const uint32_t bar_base = h_lo + kHPlane;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kRecStages + s); };
+  const uint32_t d_full_bar = bar_base + 8u * (2 * kRecStages);
+  const uint32_t h_ready_bar = d_full_bar + 8u;
+  const uint32_t tmem_slot = h_ready_bar + 8u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = blockIdx.y;
+  const int line0 = blockIdx.x * NL;
+  const int rev = d == 0 ? rev0 : rev1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRecStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(d_full_bar, 1);
+    mbar_init(h_ready_bar, 128);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    // ---------------- TMA producer: streams R (24 stages per step) ----------------
+    if (lane == 0) {
+      int it = 0;
+      for (int step = 0; step < T; ++step) {
+        for (int tile = 0; tile < 6; ++tile) {
+          for (int kk = 0; kk < 4; ++kk, ++it) {
+            const int s = it % kRecStages;
+            const uint32_t ph = (it / kRecStages) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            const uint32_t st = base + s * kRecStageBytes;
+            mbar_expect_tx(full_bar(s), kRecStageBytes);
+            tma_load_2d(st, &tm_r_hi, kk * 64, d * 768 + tile * 128, full_bar(s));
+            tma_load_2d(st + kRTile, &tm_r_lo, kk * 64, d * 768 + tile * 128, full_bar(s));
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NL >> 3) << 17) | ((128u >> 4) << 24);
+      int it = 0;
+      for (int step = 0; step < T; ++step) {
+        mbar_wait(h_ready_bar, step & 1);
+        tc_fence_after();
+        for (int tile = 0; tile < 6; ++tile) {
+          const uint32_t dcol = tmem_base + (uint32_t)(tile * NL);
+          for (int kk = 0; kk < 4; ++kk, ++it) {
+            const int s = it % kRecStages;
+            const uint32_t ph = (it / kRecStages) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t st = base + s * kRecStageBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t koff = k * 32;
+              const uint64_t da_hi = make_desc<64>(st + koff), da_lo = make_desc<64>(st + kRTile + koff);
+              const uint64_t db_hi = make_desc<64>(h_hi + kk * kHSub + koff), db_lo = make_desc<64>(h_lo + kk * kHSub + koff);
+              umma_bf16(dcol, da_hi, db_hi, idesc, (kk | k) ? 1u : 0u);
+              umma_bf16(dcol, da_hi, db_lo, idesc, 1u);
+              umma_bf16(dcol, da_lo, db_hi, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));
+          }
+        }
+        umma_commit(d_full_bar);
+      }
+    }
+  } else {
+    // ---------------- gate math: warps 0..3, thread = TMEM lane L -> units L and 128 + L ----------------
+    const int L = warp * 32 + lane;
+    float h[2][NL];
+    // h_{-1}
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const int line = line0 + l;
+        h[j][l] = (h0 != nullptr && line < N) ? h0[((size_t)d * N + line) * 256 + j * 128 + L] : 0.f;
+      }
+    auto store_h_smem = [&](int j, int l, float v) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      const int u = j * 128 + L, kk = u >> 6, col = u & 63;
+      const uint32_t off = (uint32_t)(kk * kHSub + (l >> 3) * 1024 + (l & 7) * 128 + ((((col >> 3) ^ (l & 7))) << 4) +
+                                      (col & 7) * 2);
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(h_hi + off), "h"(__bfloat16_as_ushort(hi)) : "memory");
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(h_lo + off), "h"(__bfloat16_as_ushort(lo)) : "memory");
+    };
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int l = 0; l < NL; ++l) store_h_smem(j, l, h[j][l]);
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(h_ready_bar);
+
+    float rbz[2], rbr[2], rbn[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float* b = rb + (size_t)d * 768 + j * 128 + L;
+      rbz[j] = b[0];
+      rbr[j] = b[256];
+      rbn[j] = b[512];
+    }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int step = 0; step < T; ++step) {
+      const int t = rev ? (T - 1 - step) : step;
+      mbar_wait(d_full_bar, step & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int half = 0; half < NL / 16; ++half) {
+          uint32_t az[16], ar[16], an[16];
+          tmem_ld16(lane_base + (uint32_t)((0 * 2 + j) * NL + half * 16), az);
+          tmem_ld16(lane_base + (uint32_t)((1 * 2 + j) * NL + half * 16), ar);
+          tmem_ld16(lane_base + (uint32_t)((2 * 2 + j) * NL + half * 16), an);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int l = half * 16 + q;
+            const int line = line0 + l;
+            if (line < N) {
+              const float* xg = xw + (((size_t)t * N + line) * D + d) * 768 + j * 128 + L;
+              const float xz = xg[0], xr = xg[256], xn = xg[512];
+              const float z = sigmoidf_(xz + __uint_as_float(az[q]) + rbz[j]);
+              const float r = sigmoidf_(xr + __uint_as_float(ar[q]) + rbr[j]);
+              const float nn_ = tanhf(xn + r * (__uint_as_float(an[q]) + rbn[j]));
+              const float hn = (1.f - z) * nn_ + z * h[j][l];
+              h[j][l] = hn;
+              Y[(((size_t)t * D + d) * N + line) * 256 + j * 128 + L] = hn;
+              store_h_smem(j, l, hn);
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(h_ready_bar);
+    }
+    if (Yh != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+          if (line0 + l < N) Yh[((size_t)d * N + line0 + l) * 256 + j * 128 + L] = h[j][l];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Cluster-resident recurrent kernel.  A cluster of 8 CTAs owns one tile of <= 32 lines of one
+// direction for all timesteps.  CTA rank r keeps the R rows of hidden units [32r, 32r+32) (3 gates
+// x 32 rows, split bf16) resident in shared memory as the MMA A operand, so nothing is streamed per
+// step; after each step every CTA writes its 32-unit slice of h_t (split bf16, MMA B-operand layout)
+// into the shared memory of all 8 CTAs (DSMEM) and signals their mbarriers.
+// Lines are described individually (ragged): own length, own row strides for xw and Y.
+// ------------------------------------------------------------------------------------------
+struct SeqLine {
+  int32_t T;            // timesteps of this line
+  int32_t valid;        // 0 for padding slots of the tile
+  int64_t xw_base, xw_tstride;  // xw element offset of (t = 0), per-timestep stride (elements); + d*768 + gate*256 + unit
+  int64_t y_base, y_tstride;    // Y element offset of (t = 0), per-timestep stride; + d*y_dstride + unit
+};
+
+constexpr int kCl = 8;                                 // CTAs per cluster
+constexpr int kAPlane = 4 * 128 * 128;                 // R slice plane: 4 K-subtiles x [128 rows x 128 B] = 64 KB
+constexpr int kHBuf = 2 * kHPlane;                     // one h buffer (hi + lo) = 32 KB
+constexpr int kExBytes = 3 * NL * 32 * 4;              // gate pre-activation exchange [3][NL][32] f32
+constexpr int kStageBf = 4 * 1024;                     // per-warp bf16 staging [8 lines][32 units] x (hi, lo)
+constexpr int kClSmem = 2 * kAPlane + 2 * kHBuf + kExBytes + kStageBf + 1024 + 256;
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(192, 1)
+gru_cluster_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
+                   const float* __restrict__ xw, const float* __restrict__ rb, const float* __restrict__ h0,
+                   float* __restrict__ Y, float* __restrict__ Yh, const SeqLine* __restrict__ lines, int n_lines,
+                   int D, int64_t y_dstride, int rev0, int rev1) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_hi = base, a_lo = base + kAPlane;
+  const uint32_t hbuf0 = base + 2 * kAPlane;           // buffer b at hbuf0 + b*kHBuf: [hi plane | lo plane]
+  const uint32_t ex = hbuf0 + 2 * kHBuf;
+  const uint32_t stage = ex + kExBytes;
+  const uint32_t bar_base = stage + kStageBf;
+  const uint32_t r_full_bar = bar_base;
+  const uint32_t d_full_bar = bar_base + 8;
+  const uint32_t h_ready_bar0 = bar_base + 16;         // [2]
+  const uint32_t tmem_slot = bar_base + 32;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int tile = blockIdx.x / kCl;
+  const int d = blockIdx.y;
+  const int rev = d == 0 ? rev0 : rev1;
+  const SeqLine* tl = lines + (size_t)tile * NL;
+  const int n_in_tile = min(NL, n_lines - tile * NL);
+  const int steps = tl[0].T;                           // lines are sorted by T descending inside a tile
+
+  if (threadIdx.x == 0) {
+    mbar_init(r_full_bar, 1);
+    mbar_init(d_full_bar, 1);
+    mbar_init(h_ready_bar0, kCl);
+    mbar_init(h_ready_bar0 + 8, kCl);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    // ---- one-time load of this CTA's R slice: rows [g*32, g*32+32) <- R[d][g*256 + rank*32 ...] ----
+    if (lane == 0) {
+      mbar_expect_tx(r_full_bar, 2 * 12 * 32 * 128);
+      for (int g = 0; g < 3; ++g)
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t off = (uint32_t)(kk * 16384 + g * 4096);
+          const int row = d * 768 + g * 256 + (int)rank * 32;
+          tma_load_2d(a_hi + off, &tm_r_hi, kk * 64, row, r_full_bar);
+          tma_load_2d(a_lo + off, &tm_r_lo, kk * 64, row, r_full_bar);
+        }
+    }
+  } else if (warp < 4) {
+    // ---- h_{-1}: every CTA fills its own copy of buffer 0 (all 256 units) ----
+    for (int e = threadIdx.x; e < NL * 256; e += 128) {
+      const int l = e >> 8, u = e & 255;
+      float v = 0.f;
+      if (h0 != nullptr && l < n_in_tile && tl[l].valid) v = h0[((size_t)d * n_lines + tile * NL + l) * 256 + u];
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      const int kk = u >> 6, col = u & 63;
+      const uint32_t off = (uint32_t)(kk * kHSub + (l >> 3) * 1024 + (l & 7) * 128 + (((col >> 3) ^ (l & 7)) << 4) + (col & 7) * 2);
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(hbuf0 + off), "h"(__bfloat16_as_ushort(hi)) : "memory");
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(hbuf0 + kHPlane + off), "h"(__bfloat16_as_ushort(lo)) : "memory");
+    }
+    fence_proxy_async_all();
+  }
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before anyone arrives remotely
+
+  if (warp == 5) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NL >> 3) << 17) | ((128u >> 4) << 24);
+      mbar_wait(r_full_bar, 0);
+      for (int step = 0; step < steps; ++step) {
+        const int b = step & 1;
+        if (step > 0) mbar_wait_cluster(h_ready_bar0 + 8 * b, ((step - 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t hb = hbuf0 + b * kHBuf;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t koff = k * 32;
+            const uint64_t da_hi = make_desc<64>(a_hi + kk * 16384 + koff), da_lo = make_desc<64>(a_lo + kk * 16384 + koff);
+            const uint64_t db_hi = make_desc<64>(hb + kk * kHSub + koff), db_lo = make_desc<64>(hb + kHPlane + kk * kHSub + koff);
+            umma_bf16(tmem_base, da_hi, db_hi, idesc, (kk | k) ? 1u : 0u);
+            umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
+            umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+          }
+        }
+        umma_commit(d_full_bar);
+      }
+    }
+  } else if (warp < 4) {
+    // ---------------- gate math ----------------
+    // phase A: warp g < 3 drains gate g (TMEM lanes 32g..32g+31 = units, columns = lines) into `ex`
+    // phase B: thread (warp w, lane) owns unit = lane of this CTA's slice and lines w*8 .. w*8+7
+    const int unit = (int)rank * 32 + lane;
+    float h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = warp * 8 + i;
+      h[i] = (h0 != nullptr && l < n_in_tile && tl[l].valid) ? h0[((size_t)d * n_lines + tile * NL + l) * 256 + unit] : 0.f;
+    }
+    const float rbz = rb[(size_t)d * 768 + unit], rbr = rb[(size_t)d * 768 + 256 + unit], rbn = rb[(size_t)d * 768 + 512 + unit];
+    // per-line descriptors of my 8 lines
+    int lT[8];
+    int64_t lx[8], lxs[8], ly[8], lys[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = warp * 8 + i;
+      const bool ok = l < n_in_tile && tl[l].valid;
+      lT[i] = ok ? tl[l].T : 0;
+      lx[i] = ok ? tl[l].xw_base : 0;
+      lxs[i] = ok ? tl[l].xw_tstride : 0;
+      ly[i] = ok ? tl[l].y_base : 0;
+      lys[i] = ok ? tl[l].y_tstride : 0;
+    }
+    const uint32_t my_stage = stage + warp * (8 * 32 * 2 * 2);  // [hi: 8 lines x 32 units][lo: ...] bf16
+    for (int step = 0; step < steps; ++step) {
+      const int b = step & 1, nb = b ^ 1;
+      // prefetch the input projections of this step (overlaps the MMAs)
+      float xz[8], xr[8], xn[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xz[i] = xr[i] = xn[i] = 0.f;
+        if (step < lT[i]) {
+          const int t = rev ? (lT[i] - 1 - step) : step;
+          const float* xg = xw + lx[i] + (int64_t)t * lxs[i] + (int64_t)d * 768 + unit;
+          xz[i] = __ldg(xg);
+          xr[i] = __ldg(xg + 256);
+          xn[i] = __ldg(xg + 512);
+        }
+      }
+      mbar_wait(d_full_bar, step & 1);
+      tc_fence_after();
+      if (warp < 3) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), acc);
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(ex + (uint32_t)(((warp * NL + l) * 32 + lane) * 4)), "r"(acc[l]) : "memory");
+      }
+      tc_fence_before();
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int l = warp * 8 + i;
+        float hn = h[i];
+        if (step < lT[i]) {
+          float pz, pr, pn;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pz) : "r"(ex + (uint32_t)(((0 * NL + l) * 32 + lane) * 4)));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pr) : "r"(ex + (uint32_t)(((1 * NL + l) * 32 + lane) * 4)));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pn) : "r"(ex + (uint32_t)(((2 * NL + l) * 32 + lane) * 4)));
+          const float z = sigmoidf_(xz[i] + pz + rbz);
+          const float r = sigmoidf_(xr[i] + pr + rbr);
+          const float nn_ = tanhf(xn[i] + r * (pn + rbn));
+          hn = (1.f - z) * nn_ + z * h[i];
+          h[i] = hn;
+          const int t = rev ? (lT[i] - 1 - step) : step;
+          Y[ly[i] + (int64_t)t * lys[i] + (int64_t)d * y_dstride + unit] = hn;
+        }
+        __nv_bfloat16 hi, lo;
+        split_bf16(hn, hi, lo);
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(my_stage + (uint32_t)((i * 32 + lane) * 2)), "h"(__bfloat16_as_ushort(hi)) : "memory");
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(my_stage + 512u + (uint32_t)((i * 32 + lane) * 2)), "h"(__bfloat16_as_ushort(lo)) : "memory");
+      }
+      __syncwarp();
+      if (step + 1 < steps) {
+        // lane -> (line i = lane / 4, 16-byte chunk c = lane % 4 = units 8c..8c+7 of my slice)
+        const int i = lane >> 2, c = lane & 3;
+        const int l = warp * 8 + i;
+        uint4 vhi, vlo;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vhi.x), "=r"(vhi.y), "=r"(vhi.z), "=r"(vhi.w) : "r"(my_stage + (uint32_t)(i * 64 + c * 16)));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vlo.x), "=r"(vlo.y), "=r"(vlo.z), "=r"(vlo.w) : "r"(my_stage + 512u + (uint32_t)(i * 64 + c * 16)));
+        const int kk = (int)rank >> 1;
+        const int chunk = (((int)rank & 1) * 4 + c) ^ (l & 7);
+        const uint32_t off = (uint32_t)(kk * kHSub + (l >> 3) * 1024 + (l & 7) * 128 + chunk * 16);
+        const uint32_t dst_hi = hbuf0 + nb * kHBuf + off, dst_lo = dst_hi + kHPlane;
+#pragma unroll
+        for (int p = 0; p < kCl; ++p) {
+          st_cluster_v4(mapa(dst_hi, (uint32_t)p), vhi);
+          st_cluster_v4(mapa(dst_lo, (uint32_t)p), vlo);
+        }
+        fence_proxy_async_all();
+      }
+      named_bar_sync(1, 128);
+      if (step + 1 < steps && threadIdx.x == 0) {
+#pragma unroll
+        for (int p = 0; p < kCl; ++p) mbar_arrive_remote(mapa(h_ready_bar0 + 8 * nb, (uint32_t)p));
+      }
+    }
+    if (Yh != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int l = warp * 8 + i;
+        if (l < n_in_tile && tl[l].valid) Yh[((size_t)d * n_lines + tile * NL + l) * 256 + unit] = h[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits while peers may still write into its shared memory
+  if (warp == 0) tmem_dealloc(tmem_base, 32);
+}
+
+}  // namespace
+
+bool gru_supported(int D, int H, int I) { return available() && H == 256 && (D == 1 || D == 2) && I % 64 == 0 && I >= 64; }
+
+std::unique_ptr<GruWeightsTC> prepare_gru(const float* W, const float* R, const float* B, int D, int H, int I) {
+  auto g = std::make_unique<GruWeightsTC>();
+  g->D = D; g->H = H; g->I = I;
+  auto split_upload = [](const float* src, size_t n, DeviceBuffer& hi, DeviceBuffer& lo) {
+    std::vector<__nv_bfloat16> h(n), l(n);
+    for (size_t i = 0; i < n; ++i) {
+      h[i] = __float2bfloat16_rn(src[i]);
+      l[i] = __float2bfloat16_rn(src[i] - __bfloat162float(h[i]));
+    }
+    hi.reserve(n * 2);
+    lo.reserve(n * 2);
+    OCRS_CUDA_CHECK(cudaMemcpy(hi.ptr, h.data(), n * 2, cudaMemcpyHostToDevice));
+    OCRS_CUDA_CHECK(cudaMemcpy(lo.ptr, l.data(), n * 2, cudaMemcpyHostToDevice));
+  };
+  split_upload(W, (size_t)D * 3 * H * I, g->w_hi, g->w_lo);
+  split_upload(R, (size_t)D * 3 * H * H, g->r_hi, g->r_lo);
+  std::vector<float> wb((size_t)D * 3 * H, 0.f), rb((size_t)D * 3 * H, 0.f);
+  if (B) {
+    for (int d = 0; d < D; ++d) {
+      std::copy(B + (size_t)d * 6 * H, B + (size_t)d * 6 * H + 3 * H, wb.begin() + (size_t)d * 3 * H);
+      std::copy(B + (size_t)d * 6 * H + 3 * H, B + (size_t)(d + 1) * 6 * H, rb.begin() + (size_t)d * 3 * H);
+    }
+  }
+  g->wb.reserve(wb.size() * 4);
+  g->rb.reserve(rb.size() * 4);
+  OCRS_CUDA_CHECK(cudaMemcpy(g->wb.ptr, wb.data(), wb.size() * 4, cudaMemcpyHostToDevice));
+  OCRS_CUDA_CHECK(cudaMemcpy(g->rb.ptr, rb.data(), rb.size() * 4, cudaMemcpyHostToDevice));
+  return g;
+}
+
+void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* Y, float* Yh, int T, int N,
+                 const int* reverse, const ScratchAlloc& alloc, cudaStream_t st) {
+  if (T == 0 || N == 0) return;
+  const int D = w.D, H = w.H, I = w.I;
+  const int64_t M = (int64_t)T * N;
+  const int Ntot = D * 3 * H;
+  // (1) split X
+  auto* x_hi = static_cast<__nv_bfloat16*>(alloc((size_t)M * I * 2));
+  auto* x_lo = static_cast<__nv_bfloat16*>(alloc((size_t)M * I * 2));
+  const int64_t n8 = M * I / 8;
+  split_kernel<<<(unsigned)ceil_div(n8, 256), 256, 0, st>>>(X, x_hi, x_lo, n8);
+  count_launch();
+  // (2) xw[M][D*3H] = X W^T + Wb
+  float* xw = static_cast<float*>(alloc((size_t)M * Ntot * 4));
+  {
+    uint64_t ad[2] = {(uint64_t)I, (uint64_t)M};
+    uint64_t as[1] = {(uint64_t)I * 2};
+    uint32_t box[2] = {64, 128};
+    CUtensorMap ta_hi = make_map(x_hi, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap ta_lo = make_map(x_lo, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint64_t bd[2] = {(uint64_t)I, (uint64_t)Ntot};
+    CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    static bool attr = false;
+    if (!attr) {
+      OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+      attr = true;
+    }
+    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)(Ntot / 128));
+    gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)M, Ntot, I);
+    count_launch();
+  }
+  // (3) recurrence
+  static const bool use_stream_kernel = std::getenv("OCRS_B200_GRU_STREAM") != nullptr;
+  uint64_t rd[2] = {(uint64_t)H, (uint64_t)D * 3 * H};
+  uint64_t rs[1] = {(uint64_t)H * 2};
+  if (use_stream_kernel) {
+    uint32_t box[2] = {64, 128};
+    CUtensorMap tr_hi = make_map(w.r_hi.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tr_lo = make_map(w.r_lo.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    static bool attr = false;
+    if (!attr) {
+      OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecSmem));
+      attr = true;
+    }
+    dim3 grid((unsigned)ceil_div(N, NL), (unsigned)D);
+    gru_rec_tc_kernel<<<grid, 192, kRecSmem, st>>>(tr_hi, tr_lo, xw, w.rb.as<float>(), h0, Y, Yh, T, N, D, reverse[0],
+                                                   D > 1 ? reverse[1] : 0);
+    count_launch();
+  } else {
+    uint32_t box[2] = {64, 32};
+    CUtensorMap tr_hi = make_map(w.r_hi.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tr_lo = make_map(w.r_lo.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const int n_tiles = (int)ceil_div(N, NL);
+    std::vector<SeqLine> desc((size_t)n_tiles * NL);
+    for (int i = 0; i < n_tiles * NL; ++i) {
+      SeqLine& L = desc[(size_t)i];
+      L.valid = i < N ? 1 : 0;
+      L.T = i < N ? T : 0;
+      L.xw_base = (int64_t)i * Ntot;
+      L.xw_tstride = (int64_t)N * Ntot;
+      L.y_base = (int64_t)i * H;
+      L.y_tstride = (int64_t)D * N * H;
+    }
+    auto* d_desc = static_cast<SeqLine*>(alloc(desc.size() * sizeof(SeqLine)));
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(SeqLine), cudaMemcpyHostToDevice, st));
+    static bool attr = false;
+    if (!attr) {
+      OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
+      attr = true;
+    }
+    dim3 grid((unsigned)(n_tiles * kCl), (unsigned)D);
+    gru_cluster_kernel<<<grid, 192, kClSmem, st>>>(tr_hi, tr_lo, xw, w.rb.as<float>(), h0, Y, Yh, d_desc, N, D,
+                                                   (int64_t)N * H, reverse[0], D > 1 ? reverse[1] : 0);
+    count_launch();
+  }
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace tc
+}  // namespace ocrs
