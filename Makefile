@@ -31,7 +31,7 @@ $(BUILD)/%.cpp.o: $(CSRC)/%.cpp $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -x cu -fmad=false -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lpthread
 
 clean:
 	rm -rf $(BUILD) $(LIB)

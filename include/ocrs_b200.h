@@ -160,6 +160,10 @@ int ocrs_b200_engine_get_text(ocrs_b200_engine* e, const ocrs_b200_input* in, ch
  * results[i] is a malloc'ed ocrs_b200_text_result for page i (ocrs_b200_text_result_free). */
 int ocrs_b200_engine_ocr_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
                                ocrs_b200_text_result** results);
+/* Same pipeline, results as text only: texts[i] is a malloc'ed NUL-terminated UTF-8 string, the
+ * recognised lines of page i joined with '\n' (== OcrEngine::get_text, lib.rs:290-300). */
+int ocrs_b200_engine_ocr_batch_text(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
+                                    char** texts);
 /* Batched detect_words: rects of page i are (*rects)[offsets[i] .. offsets[i+1]). */
 int ocrs_b200_engine_detect_words_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
                                         ocrs_b200_rotated_rect** rects, size_t** offsets);

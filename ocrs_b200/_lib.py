@@ -95,6 +95,7 @@ SIGNATURES = {
     "ocrs_b200_engine_detection_threshold": (C.c_float, [C.c_void_p]),
     "ocrs_b200_engine_get_text": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_char_p)]),
     "ocrs_b200_engine_ocr_batch": (C.c_int, [C.c_void_p, P(C.c_void_p), C.c_size_t, P(P(TextResultC))]),
+    "ocrs_b200_engine_ocr_batch_text": (C.c_int, [C.c_void_p, P(C.c_void_p), C.c_size_t, P(C.c_void_p)]),
     "ocrs_b200_engine_detect_words_batch": (C.c_int, [C.c_void_p, P(C.c_void_p), C.c_size_t, P(P(RotatedRectC)),
                                                       P(P(C.c_size_t))]),
     "ocrs_b200_engine_stats": (C.c_int, [C.c_void_p, P(C.c_double), C.c_int]),

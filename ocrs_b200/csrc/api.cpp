@@ -450,6 +450,35 @@ int ocrs_b200_engine_ocr_batch(ocrs_b200_engine* e, const ocrs_b200_input* const
   });
 }
 
+int ocrs_b200_engine_ocr_batch_text(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
+                                    char** texts) {
+  return guard([&] {
+    OCRS_CHECK(e && (inputs || n_pages == 0) && texts, kInvalidArg, "null argument");
+    std::vector<const OcrInput*> pages(n_pages);
+    for (size_t i = 0; i < n_pages; ++i) {
+      OCRS_CHECK(inputs[i] != nullptr, kInvalidArg, "null input");
+      pages[i] = inputs[i]->input.get();
+      texts[i] = nullptr;
+    }
+    auto r = e->engine->ocr_pages(pages);
+    for (size_t i = 0; i < n_pages; ++i) {
+      std::string text;
+      bool first = true;
+      for (const auto& l : r[i]) {
+        if (!l.present) continue;
+        if (!first) text.push_back('\n');
+        first = false;
+        std::vector<uint32_t> cps;
+        cps.reserve(l.chars.size());
+        for (const auto& c : l.chars) cps.push_back(c.ch);
+        text += codepoints_to_utf8(cps);
+      }
+      texts[i] = cmalloc<char>(text.size() + 1);
+      std::memcpy(texts[i], text.c_str(), text.size() + 1);
+    }
+  });
+}
+
 int ocrs_b200_engine_stats(ocrs_b200_engine* e, double out[8], int reset) {
   return guard([&] {
     OCRS_CHECK(e && out, kInvalidArg, "null argument");

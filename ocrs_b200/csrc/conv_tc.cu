@@ -252,6 +252,65 @@ __global__ void maxpool_nhwc_split_kernel(const __nv_bfloat16* __restrict__ x_hi
   *reinterpret_cast<uint4*>(y_lo + opix * C + g * 8) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
 }
 
+// one thread = one pooled output pixel, all Cout channels (weights broadcast from shared memory)
+template <int COUT>
+__global__ void __launch_bounds__(128)
+stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int N, int H, int W) {
+  __shared__ float sw[COUT * 9 + COUT];
+  for (int i = threadIdx.x; i < COUT * 10; i += blockDim.x) sw[i] = i < COUT * 9 ? wgt[i] : bias[i - COUT * 9];
+  __syncthreads();
+  const int OH = H / 2, OW = W / 2;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * OH * OW) return;
+  const int ow = (int)(idx % OW), oh = (int)((idx / OW) % OH), n = (int)(idx / ((int64_t)OW * OH));
+  const float* xi = x + (int64_t)n * H * W;
+  float p[4][4];  // input patch rows 2oh-1 .. 2oh+2, cols 2ow-1 .. 2ow+2 (zero padded)
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ih = 2 * oh - 1 + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int iw = 2 * ow - 1 + c;
+      p[r][c] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xi + (int64_t)ih * W + iw) : 0.f;
+    }
+  }
+  __nv_bfloat16* oh_ptr = out_hi + idx * COUT;
+  __nv_bfloat16* ol_ptr = out_lo + idx * COUT;
+#pragma unroll 1
+  for (int c8 = 0; c8 < COUT; c8 += 8) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* k = sw + (c8 + j) * 9;
+      float best = -INFINITY;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float a = 0.f;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) a = fmaf(p[dy + r][dx + s], k[r * 3 + s], a);
+          best = fmaxf(best, a);
+        }
+      const float v = fmaxf(best + sw[COUT * 9 + c8 + j], 0.f);
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      if (j & 1) {
+        ph[j / 2] |= (uint32_t)__bfloat16_as_ushort(hi) << 16;
+        pl[j / 2] |= (uint32_t)__bfloat16_as_ushort(lo) << 16;
+      } else {
+        ph[j / 2] = (uint32_t)__bfloat16_as_ushort(hi);
+        pl[j / 2] = (uint32_t)__bfloat16_as_ushort(lo);
+      }
+    }
+    *reinterpret_cast<uint4*>(oh_ptr + c8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(ol_ptr + c8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -306,6 +365,35 @@ bool conv_supported(int Cin, int Cout, int R, int S, int stride_h, int stride_w,
                     int pad_r, int dil_h, int dil_w, int groups) {
   return R == 3 && S == 3 && stride_h == 1 && stride_w == 1 && pad_t == 1 && pad_l == 1 && pad_b == 1 && pad_r == 1 &&
          dil_h == 1 && dil_w == 1 && groups == 1 && (Cin == 32 || Cin % 64 == 0) && (Cout == 64 || Cout == 128);
+}
+
+bool stem_supported(int Cin, int Cout, int R, int S, int stride_h, int stride_w, int pad_t, int pad_l, int pad_b,
+                    int pad_r, int dil_h, int dil_w, int groups) {
+  return Cin == 1 && R == 3 && S == 3 && stride_h == 1 && stride_w == 1 && pad_t == 1 && pad_l == 1 && pad_b == 1 &&
+         pad_r == 1 && dil_h == 1 && dil_w == 1 && groups == 1 && (Cout == 32 || Cout == 64);
+}
+
+std::unique_ptr<StemWeights> prepare_stem(const float* w, const float* b, int Cout) {
+  auto s = std::make_unique<StemWeights>();
+  s->Cout = Cout;
+  std::vector<float> bias((size_t)Cout, 0.f);
+  if (b) bias.assign(b, b + Cout);
+  s->w.reserve((size_t)Cout * 9 * 4);
+  s->bias.reserve((size_t)Cout * 4);
+  OCRS_CUDA_CHECK(cudaMemcpy(s->w.ptr, w, (size_t)Cout * 9 * 4, cudaMemcpyHostToDevice));
+  OCRS_CUDA_CHECK(cudaMemcpy(s->bias.ptr, bias.data(), (size_t)Cout * 4, cudaMemcpyHostToDevice));
+  return s;
+}
+
+void stem_conv_relu_pool2(const float* x, const StemWeights& w, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int N, int H,
+                          int W, cudaStream_t st) {
+  int64_t total = (int64_t)N * (H / 2) * (W / 2);
+  if (!total) return;
+  unsigned grid = (unsigned)ceil_div(total, 128);
+  if (w.Cout == 32) stem_kernel<32><<<grid, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, N, H, W);
+  else stem_kernel<64><<<grid, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, N, H, W);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
 std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, int Cin, int Cout) {

@@ -40,6 +40,19 @@ std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, i
 void conv3x3(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvWeightsTC& w, __nv_bfloat16* y_hi,
              __nv_bfloat16* y_lo, int N, int H, int W, int relu, cudaStream_t st);
 
+// First layer of the CRNN: conv3x3(1 -> Cout, stride 1, pad 1) + bias + ReLU + MaxPool(2,2), fused,
+// CUDA cores (K = 9 is not tensor-core work).  x: [N,1,H,W] f32; out: NHWC split bf16 [N,H/2,W/2,Cout].
+// w: ONNX layout [Cout][1][3][3].  Cout must be a multiple of 8 and <= 64.
+struct StemWeights {
+  int Cout = 0;
+  DeviceBuffer w, bias;  // f32 [Cout*9], [Cout]
+};
+bool stem_supported(int Cin, int Cout, int R, int S, int stride_h, int stride_w, int pad_t, int pad_l, int pad_b,
+                    int pad_r, int dil_h, int dil_w, int groups);
+std::unique_ptr<StemWeights> prepare_stem(const float* w, const float* b, int Cout);
+void stem_conv_relu_pool2(const float* x, const StemWeights& w, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int N, int H,
+                          int W, cudaStream_t st);
+
 // Layout / precision converters and the pooling used between tensor-core layers.
 void nchw_to_nhwc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int C, int H, int W,
                         cudaStream_t st);

@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <exception>
 #include <map>
+#include <thread>
 
 #include "layout.h"
 
@@ -54,6 +56,21 @@ std::string codepoints_to_utf8(const std::vector<uint32_t>& cps) {
   }
   return s;
 }
+
+// RAII host-section timer feeding profile_json ("host/<name>")
+struct Engine::HostTimer {
+  Engine* e;
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  HostTimer(Engine* eng, const char* n) : e(eng), name(n), t0(std::chrono::steady_clock::now()) {}
+  ~HostTimer() {
+    if (!e->prof_.enabled) return;
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    auto& slot = e->host_ms_[name];
+    slot.first += ms;
+    slot.second += 1;
+  }
+};
 
 struct Engine::PageScratch {
   int cap_hw = 0;
@@ -164,8 +181,18 @@ std::string Engine::profile_json(bool reset) {
     j += buf;
     first = false;
   }
+  for (const auto& kv : host_ms_) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"host/%s\": {\"ms\": %.6f, \"calls\": %lld, \"launches\": 0, \"flops\": 0, \"bytes\": 0}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.first, (long long)kv.second.second);
+    j += buf;
+    first = false;
+  }
   j += "}";
-  if (reset) prof_.reset();
+  if (reset) {
+    prof_.reset();
+    host_ms_.clear();
+  }
   return j;
 }
 
@@ -278,6 +305,7 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words(const std::vector<con
   const int N = (int)pages.size();
   std::vector<std::vector<RotatedRect>> result((size_t)N);
   if (N == 0) return result;
+  HostTimer ht_all(this, "detect_words_total");
   const auto& shp = det_->input_shape();
   OCRS_CHECK(shp.size() == 4 && shp[2] >= 0 && shp[3] >= 0, kRunFailed, "failed to get model dims");
   const int in_h = (int)shp[2], in_w = (int)shp[3];
@@ -375,6 +403,8 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
   const int n_pages = (int)pages.size();
   const int rec_h = (int)rec_input_height();
   std::vector<std::vector<TextLine>> result((size_t)n_pages);
+  HostTimer ht_all(this, "recognize_text_total");
+  auto ht_prep = std::make_unique<HostTimer>(this, "rec_line_geometry");
 
   // ---- host: per-line geometry (recognition.rs:429-446) ----
   std::vector<RecLine> lines;
@@ -461,8 +491,13 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
                   n_lines, poly_.as<int32_t>(), cross_.as<int32_t>(), rec_batch_.as<float>(), rec_h, max_gw, max_rows,
                   st_);
   prof_.end(tkc, st_, 0, 2.0 * 4.0 * (double)dst_total);
+  ht_prep.reset();
   // host vectors must outlive the async copies
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  {
+    HostTimer ht(this, "rec_sync_after_crop");
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  }
+  auto ht_launch = std::make_unique<HostTimer>(this, "rec_enqueue_networks");
 
   // ---- recognition network + CTC per (group, chunk) ----
   struct Chunk { int first, count, gw, T; int64_t out_off; };
@@ -486,34 +521,82 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
   }
   ctc_out_.reserve((size_t)out_total * 4);
   h_pin_.reserve((size_t)out_total * 4);
-  for (auto& c : chunks) {
-    float* in_ptr = rec_batch_.as<float>() + descs[c.first].dst_off;
-    ModelCost cost;
-    int tkr = prof_.begin("stage/rec_net", st_);
-    DTensor logits = rec_->run(wrap_tensor(in_ptr, {c.count, 1, rec_h, c.gw}), st_, &cost, &prof_, "rec/");
-    prof_.end(tkr, st_, cost.flops, cost.min_bytes);
-    stats_.rec_flops += cost.flops;
-    stats_.rec_batches += 1;
-    OCRS_CHECK(logits.shape.size() == 3, kWrongOutput,
-               "expected recognition output to have 3 dims but it has " + std::to_string(logits.shape.size()));  // :350
-    OCRS_CHECK(logits.shape[1] == c.count, kWrongOutput, "recognition output batch dim mismatch");
-    OCRS_CHECK((size_t)logits.shape[2] == n_classes, kWrongOutput,
-               "output column count (" + std::to_string(logits.shape[2]) + ") does not match alphabet size (" +
+  auto check_logits = [&](const std::vector<int64_t>& shape, int count) {
+    OCRS_CHECK(shape.size() == 3, kWrongOutput,
+               "expected recognition output to have 3 dims but it has " + std::to_string(shape.size()));  // :350
+    OCRS_CHECK(shape[1] == count, kWrongOutput, "recognition output batch dim mismatch");
+    OCRS_CHECK((size_t)shape[2] == n_classes, kWrongOutput,
+               "output column count (" + std::to_string(shape[2]) + ") does not match alphabet size (" +
                    std::to_string(n_classes) + ")");  // recognition.rs:487-493
-    c.T = (int)logits.shape[0];
+  };
+  auto run_ctc = [&](Chunk& c, const float* logits_ptr) {
     OCRS_CHECK(c.T <= c.gw, kWrongOutput, "recognition output longer than its input");
     stats_.n_timesteps += (int64_t)c.T * c.count;
     ctc_scratch_.reserve((size_t)c.count * c.T * 4 + 4);
     int32_t* o = ctc_out_.as<int32_t>() + c.out_off;
     int tkt = prof_.begin("stage/ctc_greedy", st_);
-    img::ctc_greedy(logits.data, c.T, c.count, (int)n_classes, has_excluded_ ? d_excluded_.as<uint8_t>() : nullptr,
+    img::ctc_greedy(logits_ptr, c.T, c.count, (int)n_classes, has_excluded_ ? d_excluded_.as<uint8_t>() : nullptr,
                     ctc_scratch_.as<int32_t>(), o, o + (int64_t)c.count * c.gw, o + (int64_t)c.count * c.gw * 2, st_);
     prof_.end(tkt, st_, 0, 4.0 * (double)c.T * c.count * (double)n_classes);
     // ctc_scratch_ is reused by the next chunk on the same stream: ordering is preserved.
+  };
+  if (rec_->has_seq_head()) {
+    // ---- packed path: conv prefix per width group, then ONE ragged GRU/Linear pass over all lines ----
+    OCRS_CHECK((size_t)rec_->seq_head_classes() == n_classes, kWrongOutput,
+               "output column count (" + std::to_string(rec_->seq_head_classes()) + ") does not match alphabet size (" +
+                   std::to_string(n_classes) + ")");
+    std::vector<DTensor> feats;
+    std::vector<Model::PackedGroup> groups;
+    int64_t rows = 0;
+    const int Cf = rec_->seq_head_channels();
+    for (auto& c : chunks) {
+      float* in_ptr = rec_batch_.as<float>() + descs[c.first].dst_off;
+      ModelCost cost;
+      int tkr = prof_.begin("stage/rec_prefix", st_);
+      DTensor x = rec_->run_prefix(wrap_tensor(in_ptr, {c.count, 1, rec_h, c.gw}), st_, &cost, &prof_, "rec/");
+      prof_.end(tkr, st_, cost.flops, 0);
+      stats_.rec_flops += cost.flops;
+      stats_.rec_batches += 1;
+      OCRS_CHECK(x.shape.size() == 3 && x.shape[1] == c.count && x.shape[2] == Cf, kWrongOutput,
+                 "recognition feature sequence must be [T, N, C]");
+      c.T = (int)x.shape[0];
+      groups.push_back(Model::PackedGroup{c.T, c.count, rows});
+      rows += (int64_t)c.T * c.count;
+      feats.push_back(std::move(x));
+    }
+    auto packed = std::make_shared<Storage>((size_t)rows * Cf * 4, st_);
+    for (size_t g = 0; g < feats.size(); ++g)
+      OCRS_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<float*>(packed->ptr) + groups[g].row_off * Cf, feats[g].data,
+                                      (size_t)feats[g].numel() * 4, cudaMemcpyDeviceToDevice, st_));
+    feats.clear();
+    ModelCost cost;
+    int tkh = prof_.begin("stage/rec_seq_head", st_);
+    DTensor logits = rec_->run_seq_head(reinterpret_cast<const float*>(packed->ptr), rows, groups, st_, &cost, &prof_, "rec/");
+    prof_.end(tkh, st_, cost.flops, 0);
+    stats_.rec_flops += cost.flops;
+    for (size_t g = 0; g < chunks.size(); ++g) run_ctc(chunks[g], logits.data + groups[g].row_off * (int64_t)n_classes);
+  } else {
+    for (auto& c : chunks) {
+      float* in_ptr = rec_batch_.as<float>() + descs[c.first].dst_off;
+      ModelCost cost;
+      int tkr = prof_.begin("stage/rec_net", st_);
+      DTensor logits = rec_->run(wrap_tensor(in_ptr, {c.count, 1, rec_h, c.gw}), st_, &cost, &prof_, "rec/");
+      prof_.end(tkr, st_, cost.flops, cost.min_bytes);
+      stats_.rec_flops += cost.flops;
+      stats_.rec_batches += 1;
+      check_logits(logits.shape, c.count);
+      c.T = (int)logits.shape[0];
+      run_ctc(c, logits.data);
+    }
   }
   OCRS_CUDA_CHECK(cudaMemcpyAsync(h_pin_.ptr, ctc_out_.ptr, (size_t)out_total * 4, cudaMemcpyDeviceToHost, st_));
   d2h_bytes_ += out_total * 4;
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  ht_launch.reset();
+  {
+    HostTimer ht(this, "rec_sync_wait_gpu");
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  }
+  HostTimer ht_asm(this, "rec_assemble_text");
 
   // ---- host: CTC steps -> characters with boxes (recognition.rs:241-311) ----
   const int32_t* h = h_pin_.as<int32_t>();
@@ -599,7 +682,27 @@ std::vector<float> Engine::prepare_recognition_input(const OcrInput& in, const s
 std::vector<std::vector<TextLine>> Engine::ocr_pages(const std::vector<const OcrInput*>& pages) {
   auto words = detect_words(pages);
   std::vector<std::vector<std::vector<RotatedRect>>> lines(pages.size());
-  for (size_t p = 0; p < pages.size(); ++p) lines[p] = layout::find_text_lines(words[p]);
+  {
+    // layout analysis is pure host code and independent per page: one thread per page
+    HostTimer ht(this, "find_text_lines");
+    if (pages.size() <= 1) {
+      for (size_t p = 0; p < pages.size(); ++p) lines[p] = layout::find_text_lines(words[p]);
+    } else {
+      std::vector<std::thread> pool;
+      std::vector<std::exception_ptr> errs(pages.size());
+      for (size_t p = 0; p < pages.size(); ++p)
+        pool.emplace_back([&, p] {
+          try {
+            lines[p] = layout::find_text_lines(words[p]);
+          } catch (...) {
+            errs[p] = std::current_exception();
+          }
+        });
+      for (auto& t : pool) t.join();
+      for (auto& e : errs)
+        if (e) std::rethrow_exception(e);
+    }
+  }
   return recognize_text(pages, lines);
 }
 

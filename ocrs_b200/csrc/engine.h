@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -133,6 +135,8 @@ class Engine {
   Profiler prof_;
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_copy_ = nullptr;
   int64_t d2h_bytes_ = 0, h2d_bytes_ = 0;
+  std::map<std::string, std::pair<double, int64_t>> host_ms_;  // host-side section timers (ms, calls)
+  struct HostTimer;
 };
 
 std::vector<uint32_t> utf8_to_codepoints(const std::string& s);

@@ -138,6 +138,7 @@ struct TcUnit {
   std::unique_ptr<tc::ConvWeightsTC> w;
 };
 struct TcChain {
+  std::unique_ptr<tc::StemWeights> stem;  // optional fused first layer: Conv(1->C)+ReLU+MaxPool(2,2)
   std::vector<TcUnit> units;
   std::string out_name;  // published name of the chain's result
 };
@@ -149,6 +150,14 @@ struct Model::Impl {
   // tensor-core conv chains (Conv3x3 [+Relu] [+MaxPool]) keyed by their first node
   std::map<int, TcChain> tc_chains;
   std::map<int, std::unique_ptr<tc::GruWeightsTC>> tc_gru;  // per GRU node
+  // packed sequence head
+  struct SeqHead {
+    bool present = false;
+    std::string x_name;          // X_seq value
+    std::vector<int> gru_nodes;  // in execution order
+    int fc_node = -1;            // MatMul node (bias fused)
+    int C = 0, H = 0, classes = 0;
+  } head;
   std::vector<int> tc_member;  // node is executed as part of a chain started earlier
   bool tc_enabled = false;
 };
@@ -254,10 +263,43 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
       }
       return cnt == 1 ? found : -1;
     };
+    auto stem_ok = [&](const Node& n) {
+      if (n.op != "Conv" || n.inputs.size() < 2) return false;
+      auto wit = g.initializers.find(n.inputs[1]);
+      if (wit == g.initializers.end() || wit->second.dims.size() != 4) return false;
+      if (n.inputs.size() > 2 && !n.inputs[2].empty() && !g.initializers.count(n.inputs[2])) return false;
+      auto pads = n.attr_ints("pads", {0, 0, 0, 0});
+      auto st = n.attr_ints("strides", {1, 1});
+      auto dl = n.attr_ints("dilations", {1, 1});
+      int grp = (int)n.attr_i("group", 1);
+      const auto& d = wit->second.dims;
+      return n.attr_s("auto_pad", "NOTSET") == "NOTSET" &&
+             tc::stem_supported((int)d[1] * grp, (int)d[0], (int)d[2], (int)d[3], (int)st[0], (int)st[1], (int)pads[0],
+                                (int)pads[1], (int)pads[2], (int)pads[3], (int)dl[0], (int)dl[1], grp);
+    };
     for (int i = 0; i < nn_; ++i) {
-      if (m->skip_[i] || impl->tc_member[i] || !conv_ok(g.nodes[i])) continue;
+      if (m->skip_[i] || impl->tc_member[i]) continue;
       TcChain chain;
       int cur = i;
+      std::vector<int> stem_nodes;
+      if (stem_ok(g.nodes[i]) && m->fuse_relu_[i]) {
+        // Conv(1->C) + ReLU + MaxPool(2,2) feeding a tensor-core conv
+        int pn = sole_consumer(published(i));
+        if (pn >= 0 && g.nodes[pn].op == "MaxPool" && g.nodes[pn].attr_ints("kernel_shape", {}) == std::vector<int64_t>{2, 2} &&
+            g.nodes[pn].attr_ints("strides", {1, 1}) == std::vector<int64_t>{2, 2} &&
+            g.nodes[pn].attr_ints("pads", {0, 0, 0, 0}) == std::vector<int64_t>{0, 0, 0, 0} && g.nodes[pn].attr_i("ceil_mode", 0) == 0) {
+          int nx = sole_consumer(g.nodes[pn].outputs[0]);
+          if (nx >= 0 && !m->skip_[nx] && conv_ok(g.nodes[nx]) && g.nodes[nx].inputs[0] == g.nodes[pn].outputs[0] &&
+              g.initializers.at(g.nodes[nx].inputs[1]).dims[1] == g.initializers.at(g.nodes[i].inputs[1]).dims[0]) {
+            const auto& wt = g.initializers.at(g.nodes[i].inputs[1]);
+            const float* bptr = (g.nodes[i].inputs.size() > 2 && !g.nodes[i].inputs[2].empty()) ? g.initializers.at(g.nodes[i].inputs[2]).f32() : nullptr;
+            chain.stem = tc::prepare_stem(wt.f32(), bptr, (int)wt.dims[0]);
+            stem_nodes = {pn, nx};
+            cur = nx;
+          }
+        }
+      }
+      if (!chain.stem && !conv_ok(g.nodes[i])) continue;
       while (true) {
         const Node& cn = g.nodes[cur];
         TcUnit u;
@@ -292,6 +334,7 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
         }
         break;
       }
+      for (int sn : stem_nodes) impl->tc_member[sn] = 1;
       for (size_t k = 0; k < chain.units.size(); ++k) {
         if (k > 0) impl->tc_member[chain.units[k].conv_node] = 1;
         if (chain.units[k].pool_node >= 0) impl->tc_member[chain.units[k].pool_node] = 1;
@@ -350,12 +393,79 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
                  "GRU with linear_before_reset=0 is not supported (PyTorch exports use 1)");
     }
   }
+  // ---- packed sequence head detection (walk back from the graph output) ----
+  if (impl->tc_enabled && std::getenv("OCRS_B200_DISABLE_SEQ_HEAD") == nullptr) {
+    auto producer = [&](const std::string& name) -> int {
+      for (int j = 0; j < nn_; ++j)
+        for (const auto& o : g.nodes[j].outputs)
+          if (o == name) return j;
+      return -1;
+    };
+    auto& hd = impl->head;
+    bool ok = true;
+    int cur = producer(g.outputs[0].name);
+    ok = ok && cur >= 0 && g.nodes[cur].op == "LogSoftmax";
+    if (ok) {
+      int64_t ax = g.nodes[cur].attr_i("axis", -1);
+      ok = (ax == 2 || ax == -1);
+    }
+    int addn = ok ? producer(g.nodes[cur].inputs[0]) : -1;
+    ok = ok && addn >= 0 && g.nodes[addn].op == "Add" && m->skip_[addn];  // folded into its MatMul
+    int mm = -1;
+    if (ok) {
+      for (int j = 0; j < nn_; ++j)
+        if (g.nodes[j].op == "MatMul" && impl->out_rename[j] == g.nodes[addn].outputs[0]) mm = j;
+      ok = mm >= 0 && !m->fused_bias_[mm].empty();
+    }
+    std::string v = ok ? g.nodes[mm].inputs[0] : std::string();
+    std::vector<int> grus;
+    while (ok) {
+      int rs = producer(v);
+      if (rs < 0 || g.nodes[rs].op != "Reshape") break;
+      auto sh = g.initializers.find(g.nodes[rs].inputs[1]);
+      if (sh == g.initializers.end()) { ok = false; break; }
+      auto shp = sh->second.as_int64();
+      if (!(shp.size() == 3 && shp[0] == 0 && shp[1] == 0 && shp[2] == -1)) { ok = false; break; }
+      int tp = producer(g.nodes[rs].inputs[0]);
+      if (tp < 0 || g.nodes[tp].op != "Transpose" || g.nodes[tp].attr_ints("perm", {}) != std::vector<int64_t>{0, 2, 1, 3}) { ok = false; break; }
+      int gn = producer(g.nodes[tp].inputs[0]);
+      if (gn < 0 || g.nodes[gn].op != "GRU" || g.nodes[gn].outputs[0] != g.nodes[tp].inputs[0] || !impl->tc_gru.count(gn) ||
+          g.nodes[gn].attr_s("direction", "forward") != "bidirectional") { ok = false; break; }
+      // initial_h must be absent or an all-zero ConstantOfShape
+      if (g.nodes[gn].inputs.size() > 5 && !g.nodes[gn].inputs[5].empty()) {
+        int hp = producer(g.nodes[gn].inputs[5]);
+        if (hp < 0 || g.nodes[hp].op != "ConstantOfShape") { ok = false; break; }
+        const Attr* a = g.nodes[hp].find("value");
+        if (a && a->kind == Attr::kTensor && a->t.dtype == onnx::kFloat && a->t.numel() > 0 && a->t.f32()[0] != 0.f) { ok = false; break; }
+      }
+      if (g.nodes[gn].inputs.size() > 4 && !g.nodes[gn].inputs[4].empty()) { ok = false; break; }
+      // Y_h must be unused
+      if (g.nodes[gn].outputs.size() > 1 && !g.nodes[gn].outputs[1].empty() && consumers.count(g.nodes[gn].outputs[1])) { ok = false; break; }
+      grus.push_back(gn);
+      v = g.nodes[gn].inputs[0];
+    }
+    ok = ok && !grus.empty();
+    if (ok) {
+      std::reverse(grus.begin(), grus.end());
+      hd.present = true;
+      hd.x_name = v;
+      hd.gru_nodes = grus;
+      hd.fc_node = mm;
+      hd.H = impl->tc_gru.at(grus[0])->H;
+      hd.C = impl->tc_gru.at(grus[0])->I;
+      hd.classes = (int)g.initializers.at(g.nodes[mm].inputs[1]).dims[1];
+      for (size_t k = 1; k < grus.size(); ++k)
+        if (impl->tc_gru.at(grus[k])->I != 2 * hd.H) hd.present = false;
+      if ((int)g.initializers.at(g.nodes[mm].inputs[1]).dims[0] != 2 * hd.H) hd.present = false;
+    }
+  }
+
   m->impl_ = std::move(impl);
   return m;
 }
 
 DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profiler* prof,
-                   const std::string& prof_prefix) const {
+                   const std::string& prof_prefix, const std::string* stop_at) const {
   const Impl* impl = impl_.get();
   const auto& g = graph_;
   OCRS_CHECK(input.shape.size() == input_shape_.size(), kRunFailed,
@@ -399,13 +509,26 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
       Value X = get(n.inputs[0]);
       OCRS_CHECK(!X.is_int && X.shape.size() == 4, kRunFailed, "Conv: expected 4-D input");
       int N_ = (int)X.shape[0], C_ = (int)X.shape[1], H_ = (int)X.shape[2], W_ = (int)X.shape[3];
-      OCRS_CHECK(C_ == ch.units[0].w->Cin, kRunFailed, "Conv: channel mismatch");
       int ptok = prof ? prof->begin(prof_prefix + "ConvTC", st) : -1;
       const double flops_before = flops;
       auto alloc_bf16 = [&](int64_t elems) { return std::make_shared<Storage>((size_t)elems * 2, st); };
-      int64_t elems = (int64_t)N_ * H_ * W_ * C_;
-      auto cur_hi = alloc_bf16(elems), cur_lo = alloc_bf16(elems);
-      tc::nchw_to_nhwc_split(X.t.data, (__nv_bfloat16*)cur_hi->ptr, (__nv_bfloat16*)cur_lo->ptr, N_, C_, H_, W_, st);
+      std::shared_ptr<Storage> cur_hi, cur_lo;
+      if (ch.stem) {
+        OCRS_CHECK(C_ == 1, kRunFailed, "Conv: channel mismatch");
+        int Co = ch.stem->Cout;
+        flops += 2.0 * N_ * H_ * W_ * (double)Co * 9.0;
+        int64_t oe = (int64_t)N_ * (H_ / 2) * (W_ / 2) * Co;
+        cur_hi = alloc_bf16(oe);
+        cur_lo = alloc_bf16(oe);
+        tc::stem_conv_relu_pool2(X.t.data, *ch.stem, (__nv_bfloat16*)cur_hi->ptr, (__nv_bfloat16*)cur_lo->ptr, N_, H_, W_, st);
+        H_ /= 2; W_ /= 2; C_ = Co;
+      } else {
+        int64_t elems = (int64_t)N_ * H_ * W_ * C_;
+        cur_hi = alloc_bf16(elems);
+        cur_lo = alloc_bf16(elems);
+        tc::nchw_to_nhwc_split(X.t.data, (__nv_bfloat16*)cur_hi->ptr, (__nv_bfloat16*)cur_lo->ptr, N_, C_, H_, W_, st);
+      }
+      OCRS_CHECK(C_ == ch.units[0].w->Cin, kRunFailed, "Conv: channel mismatch");
       for (const TcUnit& u : ch.units) {
         int Co = u.w->Cout;
         int64_t oe = (int64_t)N_ * H_ * W_ * Co;
@@ -427,6 +550,10 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
       tc::nhwc_split_to_nchw((const __nv_bfloat16*)cur_hi->ptr, (const __nv_bfloat16*)cur_lo->ptr, Y.data, N_, C_, H_, W_, st);
       if (prof) prof->end(ptok, st, flops - flops_before);
       env[ch.out_name] = dev_value(Y);
+      if (stop_at && *stop_at == ch.out_name) {
+        if (cost) { cost->flops = flops; cost->min_bytes = 0; }
+        return Y;
+      }
       auto it0 = remaining.find(n.inputs[0]);
       if (it0 != remaining.end() && --it0->second <= 0) env.erase(n.inputs[0]);
       continue;
@@ -871,6 +998,15 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
       if (k == 0 && !impl->out_rename[ni].empty()) name = impl->out_rename[ni];
       if (!name.empty()) env[name] = std::move(out[k]);
     }
+    if (stop_at) {
+      auto sit = env.find(*stop_at);
+      if (sit != env.end()) {
+        if (cost) { cost->flops = flops; cost->min_bytes = 0; }
+        DTensor r = sit->second.t;
+        r.shape = sit->second.shape;
+        return r;
+      }
+    }
     // release inputs whose last consumer just ran
     for (const auto& name : n.inputs) {
       if (name.empty()) continue;
@@ -887,6 +1023,71 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
   DTensor result = it->second.t;
   result.shape = it->second.shape;
   return result;
+}
+
+bool Model::has_seq_head() const { return impl_->head.present; }
+int Model::seq_head_channels() const { return impl_->head.C; }
+int Model::seq_head_classes() const { return impl_->head.classes; }
+
+DTensor Model::run_prefix(const DTensor& input, cudaStream_t st, ModelCost* cost, Profiler* prof,
+                          const std::string& prof_prefix) const {
+  OCRS_CHECK(impl_->head.present, kInternal, "run_prefix: model has no packed sequence head");
+  return run(input, st, cost, prof, prof_prefix, &impl_->head.x_name);
+}
+
+DTensor Model::run_seq_head(const float* X, int64_t rows, const std::vector<PackedGroup>& groups, cudaStream_t st,
+                            ModelCost* cost, Profiler* prof, const std::string& prof_prefix) const {
+  const auto& hd = impl_->head;
+  OCRS_CHECK(hd.present, kInternal, "run_seq_head: model has no packed sequence head");
+  const int H = hd.H;
+  double flops = 0;
+  // ragged line list, longest first (stable): tiles of 32 lines run max-T steps
+  struct L { int T, N; int64_t row0; };
+  std::vector<L> ls;
+  for (const auto& gph : groups)
+    for (int n = 0; n < gph.N; ++n) ls.push_back(L{gph.T, gph.N, gph.row_off + n});
+  std::stable_sort(ls.begin(), ls.end(), [](const L& a, const L& b) { return a.T > b.T; });
+  std::vector<std::shared_ptr<Storage>> scratch;
+  auto alloc = [&](size_t bytes) { scratch.push_back(std::make_shared<Storage>(bytes, st)); return scratch.back()->ptr; };
+  const float* cur = X;
+  std::shared_ptr<Storage> cur_store;
+  int rev[2] = {0, 1};
+  for (size_t li = 0; li < hd.gru_nodes.size(); ++li) {
+    const tc::GruWeightsTC& w = *impl_->tc_gru.at(hd.gru_nodes[li]);
+    const int64_t Ntot = (int64_t)w.D * 3 * H;
+    std::vector<tc::SeqLine> lines(ls.size());
+    for (size_t i = 0; i < ls.size(); ++i) {
+      lines[i].T = ls[i].T;
+      lines[i].valid = 1;
+      lines[i].xw_base = ls[i].row0 * Ntot;
+      lines[i].xw_tstride = (int64_t)ls[i].N * Ntot;
+      lines[i].y_base = ls[i].row0 * 2 * H;
+      lines[i].y_tstride = (int64_t)ls[i].N * 2 * H;
+    }
+    auto y_store = std::make_shared<Storage>((size_t)rows * 2 * H * 4, st);
+    int tk = prof ? prof->begin(prof_prefix + "GRU(packed)", st) : -1;
+    tc::gru_forward_lines(cur, rows, w, lines.data(), (int)lines.size(), reinterpret_cast<float*>(y_store->ptr), H, rev,
+                          alloc, st);
+    double f = 2.0 * w.D * (double)rows * 3.0 * H * (w.I + H);
+    flops += f;
+    if (prof) prof->end(tk, st, f);
+    cur_store = y_store;
+    cur = reinterpret_cast<const float*>(y_store->ptr);
+  }
+  // Linear + LogSoftmax over all rows
+  const Node& fc = graph_.nodes[hd.fc_node];
+  const float* Wt = reinterpret_cast<const float*>(dev_weights_t_.at(fc.inputs[1])->ptr);
+  const float* bias = reinterpret_cast<const float*>(dev_weights_.at(fused_bias_[hd.fc_node])->ptr);
+  DTensor logits = alloc_tensor({rows, hd.classes}, st);
+  int tk = prof ? prof->begin(prof_prefix + "Linear+LogSoftmax(packed)", st) : -1;
+  DTensor tmp = alloc_tensor({rows, hd.classes}, st);
+  nn::sgemm_nt(cur, Wt, bias, tmp.data, (int)rows, hd.classes, 2 * H, 0, st);
+  nn::log_softmax_lastdim(tmp.data, logits.data, rows, hd.classes, st);
+  double f = 2.0 * (double)rows * hd.classes * 2 * H;
+  flops += f;
+  if (prof) prof->end(tk, st, f);
+  if (cost) { cost->flops = flops; cost->min_bytes = 0; }
+  return logits;
 }
 
 }  // namespace ocrs

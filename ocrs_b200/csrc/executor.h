@@ -59,7 +59,26 @@ class Model {
   // Runs the graph.  `input` lives on the device; the result is stream-ordered on `st`.
   // Re-entrant: any number of threads may call run() on one Model with distinct streams.
   DTensor run(const DTensor& input, cudaStream_t st, ModelCost* cost = nullptr, Profiler* prof = nullptr,
-              const std::string& prof_prefix = "") const;
+              const std::string& prof_prefix = "", const std::string* stop_at = nullptr) const;
+
+  // ---- packed sequence head (graph-level fusion, optional) ----------------------------------
+  // When the graph ends in  X_seq[T,N,C] -> {bidirectional GRU (h0 = 0) -> Transpose(0,2,1,3) ->
+  // Reshape(0,0,-1)} x L -> MatMul(const) + Add(const) -> LogSoftmax(last axis), the suffix is
+  // row-wise except for the recurrence, so several runs with different (T, N) can share one ragged
+  // execution: run_prefix() stops at X_seq, run_seq_head() finishes all groups at once.
+  struct PackedGroup {
+    int T = 0, N = 0;
+    int64_t row_off = 0;  // first row of this group's [T, N, C] block in the packed buffer
+  };
+  bool has_seq_head() const;
+  int seq_head_channels() const;  // C of X_seq
+  int seq_head_classes() const;
+  DTensor run_prefix(const DTensor& input, cudaStream_t st, ModelCost* cost = nullptr, Profiler* prof = nullptr,
+                     const std::string& prof_prefix = "") const;
+  // X: packed [rows, C] f32.  Returns log-probs [rows, classes]; group g occupies rows
+  // [row_off, row_off + T*N) in [T, N, classes] order.
+  DTensor run_seq_head(const float* X, int64_t rows, const std::vector<PackedGroup>& groups, cudaStream_t st,
+                       ModelCost* cost = nullptr, Profiler* prof = nullptr, const std::string& prof_prefix = "") const;
 
   size_t weight_bytes() const { return weight_bytes_; }
   const onnx::Graph& graph() const { return graph_; }

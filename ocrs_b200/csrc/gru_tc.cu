@@ -336,12 +336,6 @@ gru_rec_tc_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_cons
 // into the shared memory of all 8 CTAs (DSMEM) and signals their mbarriers.
 // Lines are described individually (ragged): own length, own row strides for xw and Y.
 // ------------------------------------------------------------------------------------------
-struct SeqLine {
-  int32_t T;            // timesteps of this line
-  int32_t valid;        // 0 for padding slots of the tile
-  int64_t xw_base, xw_tstride;  // xw element offset of (t = 0), per-timestep stride (elements); + d*768 + gate*256 + unit
-  int64_t y_base, y_tstride;    // Y element offset of (t = 0), per-timestep stride; + d*y_dstride + unit
-};
 
 constexpr int kCl = 8;                                 // CTAs per cluster
 constexpr int kAPlane = 4 * 128 * 128;                 // R slice plane: 4 K-subtiles x [128 rows x 128 B] = 64 KB
@@ -668,6 +662,60 @@ void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* 
                                                    (int64_t)N * H, reverse[0], D > 1 ? reverse[1] : 0);
     count_launch();
   }
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, const SeqLine* lines_host, int n_lines,
+                       float* Y, int64_t y_dstride, const int* reverse, const ScratchAlloc& alloc, cudaStream_t st) {
+  if (rows == 0 || n_lines == 0) return;
+  const int D = w.D, H = w.H, I = w.I;
+  const int Ntot = D * 3 * H;
+  auto* x_hi = static_cast<__nv_bfloat16*>(alloc((size_t)rows * I * 2));
+  auto* x_lo = static_cast<__nv_bfloat16*>(alloc((size_t)rows * I * 2));
+  const int64_t n8 = rows * I / 8;
+  split_kernel<<<(unsigned)ceil_div(n8, 256), 256, 0, st>>>(X, x_hi, x_lo, n8);
+  count_launch();
+  float* xw = static_cast<float*>(alloc((size_t)rows * Ntot * 4));
+  {
+    uint64_t ad[2] = {(uint64_t)I, (uint64_t)rows};
+    uint64_t as[1] = {(uint64_t)I * 2};
+    uint32_t box[2] = {64, 128};
+    CUtensorMap ta_hi = make_map(x_hi, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap ta_lo = make_map(x_lo, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint64_t bd[2] = {(uint64_t)I, (uint64_t)Ntot};
+    CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    static bool attr = false;
+    if (!attr) {
+      OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+      attr = true;
+    }
+    dim3 grid((unsigned)ceil_div(rows, 128), (unsigned)(Ntot / 128));
+    gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)rows, Ntot, I);
+    count_launch();
+  }
+  uint64_t rd[2] = {(uint64_t)H, (uint64_t)D * 3 * H};
+  uint64_t rs[1] = {(uint64_t)H * 2};
+  uint32_t box[2] = {64, 32};
+  CUtensorMap tr_hi = make_map(w.r_hi.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tr_lo = make_map(w.r_lo.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  const int n_tiles = (int)ceil_div(n_lines, NL);
+  std::vector<SeqLine> desc((size_t)n_tiles * NL);
+  for (int i = 0; i < n_tiles * NL; ++i) {
+    if (i < n_lines) desc[(size_t)i] = lines_host[i];
+    else desc[(size_t)i] = SeqLine{0, 0, 0, 0, 0, 0};
+  }
+  auto* d_desc = static_cast<SeqLine*>(alloc(desc.size() * sizeof(SeqLine)));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(SeqLine), cudaMemcpyHostToDevice, st));
+  static bool attr2 = false;
+  if (!attr2) {
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
+    attr2 = true;
+  }
+  dim3 grid((unsigned)(n_tiles * kCl), (unsigned)D);
+  gru_cluster_kernel<<<grid, 192, kClSmem, st>>>(tr_hi, tr_lo, xw, w.rb.as<float>(), nullptr, Y, nullptr, d_desc, n_lines, D,
+                                                 y_dstride, reverse[0], D > 1 ? reverse[1] : 0);
+  count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -38,5 +38,18 @@ using ScratchAlloc = std::function<void*(size_t bytes)>;
 void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* Y, float* Yh, int T, int N,
                  const int* reverse, const ScratchAlloc& alloc, cudaStream_t st);
 
+// One sequence of a ragged batch: own length and own element strides into xw / Y.
+struct SeqLine {
+  int32_t T;                    // timesteps
+  int32_t valid;                // 0 = padding slot
+  int64_t xw_base, xw_tstride;  // xw element offset at t = 0 and per-timestep stride (+ d*3H + gate*H + unit)
+  int64_t y_base, y_tstride;    // Y  element offset at t = 0 and per-timestep stride (+ d*y_dstride + unit)
+};
+
+// Ragged GRU layer over `rows` packed input rows X [rows, I]: writes Y with the strides given per line.
+// `lines` must be ordered by T descending (tiles of 32 lines run max-T steps).
+void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, const SeqLine* lines_host, int n_lines,
+                       float* Y, int64_t y_dstride, const int* reverse, const ScratchAlloc& alloc, cudaStream_t st);
+
 }  // namespace tc
 }  // namespace ocrs

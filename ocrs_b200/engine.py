@@ -369,6 +369,17 @@ class OcrEngine:
             lib.ocrs_b200_text_result_free(res[i])
         return out
 
+    def ocr_batch_text(self, inputs: Sequence[OcrInput]) -> List[str]:
+        """`get_text` (lib.rs:290-300) for a batch of pages."""
+        hs = (C.c_void_p * max(len(inputs), 1))(*[i._h for i in inputs])
+        res = (C.c_void_p * max(len(inputs), 1))()
+        check(lib.ocrs_b200_engine_ocr_batch_text(self._h, hs, len(inputs), res))
+        out = []
+        for i in range(len(inputs)):
+            out.append(C.string_at(res[i]).decode("utf-8"))
+            lib.ocrs_b200_free(res[i])
+        return out
+
     def stats(self, reset: bool = False) -> dict:
         buf = (C.c_double * 8)()
         check(lib.ocrs_b200_engine_stats(self._h, buf, int(reset)))

@@ -62,12 +62,46 @@ def _gru(X, W, R, B, initial_h, hidden_size: int, direction: str, linear_before_
     return torch.stack(ys, 1), torch.stack(yh, 0)
 
 
+def _torch_gru_module(W, R, B, hidden_size: int, direction: str):
+    """ONNX GRU (gate order z, r, h; linear_before_reset = 1) as a torch.nn.GRU (gate order r, z, n):
+    the same recurrence evaluated by ATen's fused CPU kernel -- only used to make the oracle fast."""
+    D, H = W.shape[0], hidden_size
+    gru = torch.nn.GRU(W.shape[2], H, num_layers=1, bidirectional=(D == 2))
+
+    def reorder(t):
+        z, r, n = t[:H], t[H:2 * H], t[2 * H:]
+        return torch.cat([r, z, n], 0)
+
+    with torch.no_grad():
+        for d in range(D):
+            sfx = "_reverse" if d == 1 else ""
+            getattr(gru, "weight_ih_l0" + sfx).copy_(reorder(W[d]))
+            getattr(gru, "weight_hh_l0" + sfx).copy_(reorder(R[d]))
+            if B is not None:
+                getattr(gru, "bias_ih_l0" + sfx).copy_(reorder(B[d, :3 * H]))
+                getattr(gru, "bias_hh_l0" + sfx).copy_(reorder(B[d, 3 * H:]))
+            else:
+                getattr(gru, "bias_ih_l0" + sfx).zero_()
+                getattr(gru, "bias_hh_l0" + sfx).zero_()
+    return gru.eval()
+
+
 class OnnxModel:
     """`impl Model for rten::Model` stand-in: `input_shape()` + `run()` (model.rs:19-41)."""
 
-    def __init__(self, graph_or_path):
+    def __init__(self, graph_or_path, fused_gru: bool = True):
         self.graph: Graph = load_model(graph_or_path) if isinstance(graph_or_path, str) else graph_or_path
         self.consts = {k: torch.from_numpy(_c(v)) for k, v in self.graph.initializers.items()}
+        self._gru_modules = {}
+        if fused_gru:
+            for i, n in enumerate(self.graph.nodes):
+                if (n.op_type == "GRU" and n.attrs.get("linear_before_reset", 0) and len(n.inputs) >= 3
+                        and n.inputs[1] in self.consts and n.inputs[2] in self.consts
+                        and n.attrs.get("direction", "forward") in ("forward", "bidirectional")
+                        and (len(n.inputs) < 4 or not n.inputs[3] or n.inputs[3] in self.consts)):
+                    B = self.consts[n.inputs[3]] if len(n.inputs) > 3 and n.inputs[3] else None
+                    self._gru_modules[id(n)] = _torch_gru_module(self.consts[n.inputs[1]], self.consts[n.inputs[2]], B,
+                                                                 n.attrs["hidden_size"], n.attrs.get("direction", "forward"))
 
     def input_shape(self) -> List[Any]:
         """Fixed dims as int, symbolic dims as str (rten::Dimension)."""
@@ -218,6 +252,14 @@ class OnnxModel:
             if any(tp):
                 out = Fnn.pad(out, tp, value=value)
             return out
+        if op == "GRU" and id(n) in self._gru_modules:
+            assert a[4] is None if len(a) > 4 else True, "sequence_lens unsupported"
+            mod = self._gru_modules[id(n)]
+            h0 = a[5] if len(a) > 5 and a[5] is not None else None
+            y, hn = mod(a[0], h0)
+            T, N = a[0].shape[0], a[0].shape[1]
+            D = 2 if mod.bidirectional else 1
+            return y.reshape(T, N, D, mod.hidden_size).permute(0, 2, 1, 3).contiguous(), hn
         if op == "GRU":
             assert a[4] is None if len(a) > 4 else True, "sequence_lens unsupported"
             return _gru(a[0], a[1], a[2], a[3] if len(a) > 3 else None, a[5] if len(a) > 5 else None,

@@ -62,3 +62,12 @@ def test_recognition_graph_matches_torch(tmp_models):
     ops = {n.op_type for n in m.graph.nodes}
     assert {"Conv", "MaxPool", "AveragePool", "Reshape", "Transpose", "GRU", "Shape", "Gather", "Unsqueeze",
             "Concat", "ConstantOfShape", "MatMul", "Add", "LogSoftmax"} <= ops
+
+
+def test_fused_gru_equals_spec_loop(tmp_models):
+    """The ATen-backed GRU used for speed matches the explicit ONNX-spec recurrence."""
+    _, _, _, rec_p = tmp_models
+    x = np.random.default_rng(2).uniform(-0.5, 0.5, (2, 1, 64, 200)).astype(np.float32)
+    a = OnnxModel(rec_p, fused_gru=True).run(x)
+    b = OnnxModel(rec_p, fused_gru=False).run(x)
+    assert np.abs(a - b).max() < 1e-4

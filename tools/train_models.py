@@ -127,6 +127,48 @@ def rec_lines(seed, max_width=1300):
     return out
 
 
+_PIPE = {}
+
+
+def rec_lines_pipeline(seed, max_width=1300):
+    """Like rec_lines, but the crops come from the oracle pipeline itself (trained detection net ->
+    word rects -> find_text_lines -> line polygon crop), so the recogniser sees exactly what the
+    engine feeds it.  Lines are labelled with the ground-truth row they cover word for word."""
+    from oracle.engine import OcrEngine, OcrEngineParams
+    from oracle.onnx_eval import OnnxModel
+    if "eng" not in _PIPE:
+        det = os.path.join(default_model_dir(), "text-detection.onnx")
+        _PIPE["eng"] = OcrEngine(OcrEngineParams(detection_model=OnnxModel(det)))
+        from oracle.engine import TextRecognizer
+
+        class _Shape:
+            def input_shape(self):
+                return ["batch", 1, 64, "seq"]
+        _PIPE["rec"] = TextRecognizer(_Shape())
+    eng, recog = _PIPE["eng"], _PIPE["rec"]
+    rng = np.random.default_rng(seed)
+    page, texts, boxes = make_page(seed, 768, 1024, two_col=bool(rng.random() < 0.8), with_boxes=True)
+    img = eng.prepare_input(page, "hwc")
+    lines = eng.find_text_lines(img, eng.detect_words(img))
+    out = []
+    for line in lines:
+        centers = [(float(w.cy), float(w.cx)) for w in line]
+        label = None
+        for text, row in zip(texts, boxes):
+            if len(row) != len(line):
+                continue
+            if all(b[0] - 2 <= cy <= b[2] + 2 and b[1] - 2 <= cx <= b[3] + 2 for (cy, cx), b in zip(centers, row)):
+                label = text
+                break
+        if label is None:
+            continue
+        crop = recog.prepare_input(img, line)
+        if crop.shape[1] > max_width:
+            continue
+        out.append((crop.astype(np.float32), [DEFAULT_ALPHABET.index(c) + 1 for c in label]))
+    return out
+
+
 def collate(items):
     wmax = max(i[0].shape[1] for i in items)
     wg = ((wmax + 49) // 50) * 50
@@ -151,7 +193,8 @@ def greedy(logp):
     return outs
 
 
-def train_rec(minutes: float, out_path: str, threads: int, resume: str | None = None):
+def train_rec(minutes: float, out_path: str, threads: int, resume: str | None = None, pipeline: bool = False,
+              lr0: float = 1e-3):
     torch.set_num_threads(threads)
     torch.manual_seed(1)
     net = RecognitionNet().train()
@@ -163,11 +206,12 @@ def train_rec(minutes: float, out_path: str, threads: int, resume: str | None = 
     t0 = time.time()
     step, seed = 0, 50_000
     pool = []
-    val = [it for s in range(900_000, 900_003) for it in rec_lines(s)][:48]
+    gen = rec_lines_pipeline if pipeline else rec_lines
+    val = [it for s in range(900_000, 900_003) for it in gen(s)][:48]
     best = -1.0
     while time.time() - t0 < minutes * 60:
         while len(pool) < 64:
-            pool.extend(rec_lines(seed))
+            pool.extend(gen(seed))
             seed += 1
         pool.sort(key=lambda it: it[0].shape[1] + 40 * np.random.rand())
         k = int(np.random.randint(0, max(1, len(pool) - 8)))
@@ -176,7 +220,7 @@ def train_rec(minutes: float, out_path: str, threads: int, resume: str | None = 
         x, targets, lens = collate(items)
         frac = min(1.0, (time.time() - t0) / (minutes * 60))
         for g in opt.param_groups:
-            g["lr"] = 1e-3 * (0.5 * (1 + np.cos(np.pi * frac))) + 2e-5
+            g["lr"] = lr0 * (0.5 * (1 + np.cos(np.pi * frac))) + 2e-5
         logp = net(x)  # [T, N, C]
         T = logp.shape[0]
         loss = ctc(logp, targets, torch.full((len(items),), T, dtype=torch.long), lens)
@@ -212,10 +256,12 @@ if __name__ == "__main__":
     ap.add_argument("--threads", type=int, default=4)
     ap.add_argument("--out", default=None)
     ap.add_argument("--resume", default=None)
+    ap.add_argument("--pipeline", action="store_true")
+    ap.add_argument("--lr", type=float, default=1e-3)
     a = ap.parse_args()
     d = default_model_dir()
     os.makedirs(d, exist_ok=True)
     if a.which == "det":
         train_det(a.minutes, a.out or os.path.join(d, "text-detection.trained.onnx"), a.threads)
     else:
-        train_rec(a.minutes, a.out or os.path.join(d, "text-recognition.trained.onnx"), a.threads, a.resume)
+        train_rec(a.minutes, a.out or os.path.join(d, "text-recognition.trained.onnx"), a.threads, a.resume, a.pipeline, a.lr)
