@@ -152,8 +152,23 @@ Engine::~Engine() {
   rec_.reset();
   if (ev_a_) cudaEventDestroy(ev_a_);
   if (ev_copy_) cudaEventDestroy(ev_copy_);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  for (auto e : aux_done_) cudaEventDestroy(e);
+  for (auto s2 : aux_) cudaStreamDestroy(s2);
   if (ev_b_) cudaEventDestroy(ev_b_);
   if (st_) cudaStreamDestroy(st_);
+}
+
+void Engine::ensure_aux(int n) {
+  if (!ev_fork_) OCRS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  while ((int)aux_.size() < n) {
+    cudaStream_t s;
+    cudaEvent_t e;
+    OCRS_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    OCRS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    aux_.push_back(s);
+    aux_done_.push_back(e);
+  }
 }
 
 void Engine::synchronize() {
@@ -332,20 +347,31 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words(const std::vector<con
              "detection output must be [N,1,H,W]");
   h_pin_.reserve((size_t)N * 8 * 4);
   int32_t* h_counters = h_pin_.as<int32_t>();
+  // post-processing of the N pages is independent: fork onto per-page side streams so the small,
+  // latency-bound kernels (labelling, per-component border following) overlap
+  const int n_aux = prof_.enabled ? 1 : std::min(N, 8);  // profiling brackets need serial kernels
+  ensure_aux(n_aux);
+  OCRS_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
+  for (int a = 0; a < n_aux; ++a) OCRS_CUDA_CHECK(cudaStreamWaitEvent(aux_[a], ev_fork_, 0));
   for (int i = 0; i < N; ++i) {
     const OcrInput& in = *pages[i];
+    cudaStream_t sa = aux_[i % n_aux];
     PageScratch& s = scratch_for(i, in.H, in.W);
     int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
-    int t1 = prof_.begin("stage/resize_threshold", st_);
+    int t1 = prof_.begin("stage/resize_threshold", sa);
     img::resize_threshold(out.data + i * plane, in_h, in_w, in_h - pb, in_w - pr, nullptr, s.mask.as<uint8_t>(),
-                          in.H, in.W, text_threshold_, st_);
-    prof_.end(t1, st_, 0, 4.0 * (in_h - pb) * (in_w - pr) + (double)in.H * in.W);
-    int t2 = prof_.begin("stage/components_to_rects", st_);
+                          in.H, in.W, text_threshold_, sa);
+    prof_.end(t1, sa, 0, 4.0 * (in_h - pb) * (in_w - pr) + (double)in.H * in.W);
+    int t2 = prof_.begin("stage/components_to_rects", sa);
     img::find_component_rects(s.mask.as<uint8_t>(), in.H, in.W, 2.0f /* detection.rs:50 */,
-                              3.0f /* detection.rs:116 */, min_area_, s.bufs, st_);
-    prof_.end(t2, st_, 0, 5.0 * in.H * in.W);  // read mask + write/read labels
-    OCRS_CUDA_CHECK(cudaMemcpyAsync(h_counters + 8 * i, s.bufs.counters, 8 * 4, cudaMemcpyDeviceToHost, st_));
+                              3.0f /* detection.rs:116 */, min_area_, s.bufs, sa);
+    prof_.end(t2, sa, 0, 5.0 * in.H * in.W);  // read mask + write/read labels
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(h_counters + 8 * i, s.bufs.counters, 8 * 4, cudaMemcpyDeviceToHost, sa));
     d2h_bytes_ += 32;
+  }
+  for (int a = 0; a < n_aux; ++a) {
+    OCRS_CUDA_CHECK(cudaEventRecord(aux_done_[a], aux_[a]));
+    OCRS_CUDA_CHECK(cudaStreamWaitEvent(st_, aux_done_[a], 0));
   }
   OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
   std::vector<std::vector<int32_t>> roots((size_t)N);
@@ -540,21 +566,29 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
     prof_.end(tkt, st_, 0, 4.0 * (double)c.T * c.count * (double)n_classes);
     // ctc_scratch_ is reused by the next chunk on the same stream: ordering is preserved.
   };
+  std::vector<DTensor> feats;  // per-group feature sequences (packed path)
   if (rec_->has_seq_head()) {
     // ---- packed path: conv prefix per width group, then ONE ragged GRU/Linear pass over all lines ----
     OCRS_CHECK((size_t)rec_->seq_head_classes() == n_classes, kWrongOutput,
                "output column count (" + std::to_string(rec_->seq_head_classes()) + ") does not match alphabet size (" +
                    std::to_string(n_classes) + ")");
-    std::vector<DTensor> feats;
     std::vector<Model::PackedGroup> groups;
     int64_t rows = 0;
     const int Cf = rec_->seq_head_channels();
+    // the per-group conv prefixes are independent and individually too small to fill 148 SMs:
+    // spread them over side streams, join before the packed head
+    const int n_aux = prof_.enabled ? 1 : (int)std::min<size_t>(chunks.size(), 6);
+    ensure_aux(n_aux);
+    OCRS_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
+    for (int a = 0; a < n_aux; ++a) OCRS_CUDA_CHECK(cudaStreamWaitEvent(aux_[a], ev_fork_, 0));
+    int ci = 0;
     for (auto& c : chunks) {
+      cudaStream_t sa = aux_[ci++ % n_aux];
       float* in_ptr = rec_batch_.as<float>() + descs[c.first].dst_off;
       ModelCost cost;
-      int tkr = prof_.begin("stage/rec_prefix", st_);
-      DTensor x = rec_->run_prefix(wrap_tensor(in_ptr, {c.count, 1, rec_h, c.gw}), st_, &cost, &prof_, "rec/");
-      prof_.end(tkr, st_, cost.flops, 0);
+      int tkr = prof_.begin("stage/rec_prefix", sa);
+      DTensor x = rec_->run_prefix(wrap_tensor(in_ptr, {c.count, 1, rec_h, c.gw}), sa, &cost, &prof_, "rec/");
+      prof_.end(tkr, sa, cost.flops, 0);
       stats_.rec_flops += cost.flops;
       stats_.rec_batches += 1;
       OCRS_CHECK(x.shape.size() == 3 && x.shape[1] == c.count && x.shape[2] == Cf, kWrongOutput,
@@ -564,11 +598,15 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
       rows += (int64_t)c.T * c.count;
       feats.push_back(std::move(x));
     }
+    for (int a = 0; a < n_aux; ++a) {
+      OCRS_CUDA_CHECK(cudaEventRecord(aux_done_[a], aux_[a]));
+      OCRS_CUDA_CHECK(cudaStreamWaitEvent(st_, aux_done_[a], 0));
+    }
     auto packed = std::make_shared<Storage>((size_t)rows * Cf * 4, st_);
     for (size_t g = 0; g < feats.size(); ++g)
       OCRS_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<float*>(packed->ptr) + groups[g].row_off * Cf, feats[g].data,
                                       (size_t)feats[g].numel() * 4, cudaMemcpyDeviceToDevice, st_));
-    feats.clear();
+    // `feats` (allocated on the side streams) stay alive until the final synchronisation below
     ModelCost cost;
     int tkh = prof_.begin("stage/rec_seq_head", st_);
     DTensor logits = rec_->run_seq_head(reinterpret_cast<const float*>(packed->ptr), rows, groups, st_, &cost, &prof_, "rec/");

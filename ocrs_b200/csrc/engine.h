@@ -134,6 +134,10 @@ class Engine {
   Stats stats_;
   Profiler prof_;
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_copy_ = nullptr;
+  std::vector<cudaStream_t> aux_;       // per-page side streams for detection post-processing
+  std::vector<cudaEvent_t> aux_done_;
+  cudaEvent_t ev_fork_ = nullptr;
+  void ensure_aux(int n);
   int64_t d2h_bytes_ = 0, h2d_bytes_ = 0;
   std::map<std::string, std::pair<double, int64_t>> host_ms_;  // host-side section timers (ms, calls)
   struct HostTimer;

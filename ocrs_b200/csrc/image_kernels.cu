@@ -147,6 +147,8 @@ __device__ void uf_union(int32_t* L, int a, int b) {
   }
 }
 
+__global__ void ccl_frame_init_kernel(int32_t* L, int64_t n) { L[n] = (int32_t)n; }
+
 __global__ void ccl_init_kernel(int32_t* L, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= n) L[i] = (int32_t)i;  // includes the virtual frame node n
@@ -169,6 +171,98 @@ __global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int32_t* L, i
     if (x > 0 && !mask[p - 1]) uf_union(L, p, p - 1);
     if (y > 0 && !mask[p - W]) uf_union(L, p, p - W);
     if (x == 0 || y == 0 || x == W - 1 || y == H - 1) uf_union(L, p, H * W);
+  }
+}
+
+// ---- two-level labelling: tile-local union-find in shared memory, then unions across tile borders ----
+constexpr int kTile = 32;
+
+__device__ __forceinline__ int suf_find(const int* L, int i) {
+  int p = L[i];
+  while (p != i) {
+    i = p;
+    p = L[i];
+  }
+  return i;
+}
+__device__ __forceinline__ void suf_union(int* L, int a, int b) {
+  bool done = false;
+  while (!done) {
+    a = suf_find(L, a);
+    b = suf_find(L, b);
+    if (a < b) {
+      int old = atomicMin(&L[b], a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      int old = atomicMin(&L[a], b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ccl_tile_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ L, int H,
+                                                       int W) {
+  __shared__ int sl[kTile * kTile];
+  __shared__ uint8_t sm[kTile * kTile];
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;  // 8 rows per pass
+  for (int ty = ty0; ty < kTile; ty += 8) {
+    int x = x0 + tx, y = y0 + ty, li = ty * kTile + tx;
+    sl[li] = li;
+    sm[li] = (x < W && y < H) ? (mask[(int64_t)y * W + x] ? 1 : 0) : 2;  // 2 = outside the image
+  }
+  __syncthreads();
+  for (int ty = ty0; ty < kTile; ty += 8) {
+    int li = ty * kTile + tx;
+    uint8_t v = sm[li];
+    if (v == 2) continue;
+    if (v) {
+      if (tx > 0 && sm[li - 1] == 1) suf_union(sl, li, li - 1);
+      if (ty > 0) {
+        if (sm[li - kTile] == 1) suf_union(sl, li, li - kTile);
+        if (tx > 0 && sm[li - kTile - 1] == 1) suf_union(sl, li, li - kTile - 1);
+        if (tx + 1 < kTile && sm[li - kTile + 1] == 1) suf_union(sl, li, li - kTile + 1);
+      }
+    } else {
+      if (tx > 0 && sm[li - 1] == 0) suf_union(sl, li, li - 1);
+      if (ty > 0 && sm[li - kTile] == 0) suf_union(sl, li, li - kTile);
+    }
+  }
+  __syncthreads();
+  for (int ty = ty0; ty < kTile; ty += 8) {
+    int x = x0 + tx, y = y0 + ty, li = ty * kTile + tx;
+    if (x >= W || y >= H) continue;
+    int r = suf_find(sl, li);
+    L[(int64_t)y * W + x] = (y0 + r / kTile) * W + x0 + (r % kTile);  // global index of the tile-local root
+  }
+}
+
+// unions across tile borders + the virtual frame node (index H*W) for background on the image border
+__global__ void ccl_border_kernel(const uint8_t* __restrict__ mask, int32_t* L, int H, int W) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= W) return;
+  const bool on_v = (x % kTile) == 0, on_h = (y % kTile) == 0;
+  const bool img_border = (x == 0 || y == 0 || x == W - 1 || y == H - 1);
+  const bool right_edge = (x % kTile) == kTile - 1;  // NE neighbour lies in the next tile column
+  if (!on_v && !on_h && !img_border && !right_edge) return;
+  int p = y * W + x;
+  uint8_t v = mask[p];
+  if (v) {
+    if (on_v && x > 0 && mask[p - 1]) uf_union(L, p, p - 1);
+    if (y > 0) {
+      if (on_h && mask[p - W]) uf_union(L, p, p - W);
+      if ((on_h || on_v) && x > 0 && mask[p - W - 1]) uf_union(L, p, p - W - 1);
+      if ((on_h || right_edge) && x + 1 < W && mask[p - W + 1]) uf_union(L, p, p - W + 1);
+    }
+  } else {
+    if (on_v && x > 0 && !mask[p - 1]) uf_union(L, p, p - 1);
+    if (on_h && y > 0 && !mask[p - W]) uf_union(L, p, p - W);
+    if (img_border) uf_union(L, p, H * W);
   }
 }
 
@@ -487,11 +581,16 @@ void find_component_rects(const uint8_t* mask, int H, int W, float eps, float ex
   OCRS_CUDA_CHECK(cudaMemsetAsync(b.counters, 0, 8 * sizeof(int32_t), st));
   if (n == 0) return;
   OCRS_CHECK(H < 32768 && W < 32768, kInvalidArg, "image dimensions exceed 32767");
-  ccl_init_kernel<<<grid1d(n + 1), kThreads, 0, st>>>(b.labels, n);
-  count_launch();
-  dim3 grid(grid1d(W, 128), H);
-  ccl_merge_kernel<<<grid, 128, 0, st>>>(mask, b.labels, H, W);
-  count_launch();
+  {
+    dim3 tg((unsigned)ceil_div(W, kTile), (unsigned)ceil_div(H, kTile));
+    ccl_tile_kernel<<<tg, 256, 0, st>>>(mask, b.labels, H, W);
+    count_launch();
+    ccl_frame_init_kernel<<<1, 1, 0, st>>>(b.labels, n);
+    count_launch();
+    dim3 grid(grid1d(W, 128), H);
+    ccl_border_kernel<<<grid, 128, 0, st>>>(mask, b.labels, H, W);
+    count_launch();
+  }
   ccl_flatten_kernel<<<grid1d(n + 1), kThreads, 0, st>>>(mask, b.labels, n, b.comp_roots, b.counters, b.max_comps);
   count_launch();
   // one thread per component; the count is only known on the device, so launch for the

@@ -151,37 +151,55 @@ RectF bounding_rect_of(const std::vector<RotatedRect>& rects, bool* ok) {
 
 std::vector<std::vector<RotatedRect>> group_into_lines(const std::vector<RotatedRect>& rects,
                                                        const std::vector<LineF>& separators) {
-  std::vector<RotatedRect> sorted = rects;
-  std::stable_sort(sorted.begin(), sorted.end(), [](const RotatedRect& a, const RotatedRect& b) {  // :21
-    return f2i(rr_bounding_rect(a).left) < f2i(rr_bounding_rect(b).left);
-  });
+  // Per-rect quantities the reference recomputes inside its O(n^2) loop (layout_analysis.rs:46-59)
+  // are pure functions of the rect: cache them once.  Semantics (stable sort, filter order,
+  // first-minimum tie break) are unchanged.
+  struct Item {
+    RotatedRect r;
+    LineF left_edge, right_edge;
+    float left_cx;  // leftmost_edge(r).center().x
+    int key;        // r.center().x as i32
+    int sort_key;   // bounding_rect().left() as i32
+  };
+  std::vector<Item> sorted;
+  sorted.reserve(rects.size());
+  for (const RotatedRect& r : rects) {
+    Item it;
+    it.r = r;
+    it.left_edge = leftmost_edge(r);
+    it.right_edge = rightmost_edge(r);
+    it.left_cx = line_center(it.left_edge).x;
+    it.key = f2i(r.cx);
+    it.sort_key = f2i(rr_bounding_rect(r).left);
+    sorted.push_back(it);
+  }
+  std::stable_sort(sorted.begin(), sorted.end(), [](const Item& a, const Item& b) { return a.sort_key < b.sort_key; });  // :21
   std::vector<std::vector<RotatedRect>> lines;
   const float overlap_threshold = 5.0f;  // :27
   const float max_h_overlap = 5.0f;      // :35
   while (!sorted.empty()) {
     std::vector<RotatedRect> line;
-    line.push_back(sorted.front());
+    Item last = sorted.front();
+    line.push_back(last.r);
     sorted.erase(sorted.begin());
     while (true) {
-      const RotatedRect last = line.back();
-      LineF last_edge = rightmost_edge(last);
-      float last_edge_cx = line_center(last_edge).x;
+      const LineF last_edge = last.right_edge;
+      const float last_edge_cx = line_center(last_edge).x;
       int best_i = -1, best_key = 0;
       for (size_t i = 0; i < sorted.size(); ++i) {
-        const RotatedRect& r = sorted[i];
-        LineF edge = leftmost_edge(r);
-        if (!(r.cx > last.cx)) continue;
-        if (!(line_center(edge).x - last_edge_cx >= -max_h_overlap)) continue;
-        if (!(line_vertical_overlap(last_edge, edge) >= overlap_threshold)) continue;
+        const Item& c = sorted[i];
+        if (!(c.r.cx > last.r.cx)) continue;
+        if (!(c.left_cx - last_edge_cx >= -max_h_overlap)) continue;
+        if (!(line_vertical_overlap(last_edge, c.left_edge) >= overlap_threshold)) continue;
         bool separated = false;
         for (const LineF& s : separators)
-          if (rects_separated_by_line(last, r, s)) { separated = true; break; }
+          if (rects_separated_by_line(last.r, c.r, s)) { separated = true; break; }
         if (separated) continue;
-        int key = f2i(r.cx);
-        if (best_i < 0 || key < best_key) { best_i = (int)i; best_key = key; }  // first minimum (:59)
+        if (best_i < 0 || c.key < best_key) { best_i = (int)i; best_key = c.key; }  // first minimum (:59)
       }
       if (best_i < 0) break;
-      line.push_back(sorted[(size_t)best_i]);
+      last = sorted[(size_t)best_i];
+      line.push_back(last.r);
       sorted.erase(sorted.begin() + best_i);
     }
     lines.push_back(std::move(line));
