@@ -509,7 +509,7 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
       Value X = get(n.inputs[0]);
       OCRS_CHECK(!X.is_int && X.shape.size() == 4, kRunFailed, "Conv: expected 4-D input");
       int N_ = (int)X.shape[0], C_ = (int)X.shape[1], H_ = (int)X.shape[2], W_ = (int)X.shape[3];
-      int ptok = prof ? prof->begin(prof_prefix + "ConvTC", st) : -1;
+      int ptok = prof ? prof->begin(prof_prefix + "ConvChain(total)", st) : -1;
       const double flops_before = flops;
       auto alloc_bf16 = [&](int64_t elems) { return std::make_shared<Storage>((size_t)elems * 2, st); };
       std::shared_ptr<Storage> cur_hi, cur_lo;
@@ -533,9 +533,12 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
         int Co = u.w->Cout;
         int64_t oe = (int64_t)N_ * H_ * W_ * Co;
         auto o_hi = alloc_bf16(oe), o_lo = alloc_bf16(oe);
+        int ktok = prof ? prof->begin(prof_prefix + "conv3x3_tc_kernel", st) : -1;
         tc::conv3x3((const __nv_bfloat16*)cur_hi->ptr, (const __nv_bfloat16*)cur_lo->ptr, *u.w, (__nv_bfloat16*)o_hi->ptr,
                     (__nv_bfloat16*)o_lo->ptr, N_, H_, W_, u.relu, st);
-        flops += 2.0 * N_ * H_ * W_ * (double)Co * C_ * 9.0;
+        const double cf = 2.0 * N_ * H_ * W_ * (double)Co * C_ * 9.0;
+        if (prof) prof->end(ktok, st, cf, 4.0 * N_ * H_ * W_ * (double)(Co + C_));
+        flops += cf;
         cur_hi = o_hi; cur_lo = o_lo; C_ = Co;
         if (u.pool_node >= 0) {
           int OH = H_ / u.ph, OW = W_ / u.pw;

@@ -177,6 +177,7 @@ def collate(items):
         x[k, 0, :, : img.shape[1]] = img
     targets = torch.tensor([c for _, ids in items for c in ids], dtype=torch.long)
     lens = torch.tensor([len(ids) for _, ids in items], dtype=torch.long)
+    collate.widths = [it[0].shape[1] for it in items]
     return torch.from_numpy(x), targets, lens
 
 
@@ -223,6 +224,13 @@ def train_rec(minutes: float, out_path: str, threads: int, resume: str | None = 
             g["lr"] = lr0 * (0.5 * (1 + np.cos(np.pi * frac))) + 2e-5
         logp = net(x)  # [T, N, C]
         T = logp.shape[0]
+        # characters decoded at x >= line width are discarded by the pipeline (recognition.rs:278):
+        # forbid non-blank emissions in the right padding so every character is emitted inside the line
+        mask = torch.zeros_like(logp)
+        for k, wk in enumerate(collate.widths):
+            tv = max((wk - 4) // 4, 1)
+            mask[tv:, k, 1:] = -1e4
+        logp = logp + mask
         loss = ctc(logp, targets, torch.full((len(items),), T, dtype=torch.long), lens)
         opt.zero_grad()
         loss.backward()
@@ -236,7 +244,10 @@ def train_rec(minutes: float, out_path: str, threads: int, resume: str | None = 
                 ok = 0
                 for i in range(0, len(val), 8):
                     xv, _, _ = collate(val[i:i + 8])
-                    for got, (_, ids) in zip(greedy(net(xv)), val[i:i + 8]):
+                    lp = net(xv)
+                    for k, wk in enumerate(collate.widths):
+                        lp[max(-(-wk // 4), 1):, k, 1:] = -1e4  # what the pipeline would drop
+                    for got, (_, ids) in zip(greedy(lp), val[i:i + 8]):
                         ok += int(got == ids)
             acc = ok / len(val)
             log(f"rec step {step} val exact-line accuracy {acc:.3f}")
