@@ -159,6 +159,10 @@ struct Model::Impl {
     int C = 0, H = 0, classes = 0;
   } head;
   std::vector<int> tc_member;  // node is executed as part of a chain started earlier
+  // detection-net fusions (fp32 CUDA cores)
+  std::vector<int> dwpw_partner;     // per depthwise Conv node: index of the fused pointwise Conv (-1 = none)
+  struct HeadFuse { int conv1x1 = -1, sigmoid = -1; };
+  std::map<int, HeadFuse> head_fuse; // per ConvTranspose node: fused 1x1 conv + sigmoid
   bool tc_enabled = false;
 };
 
@@ -222,6 +226,80 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
         m->fused_bias_[i] = other;
         m->skip_[j] = 1;
         impl->out_rename[i] = c.outputs[0];
+      }
+    }
+  }
+
+  // ---- depthwise 3x3 + pointwise 1x1 fusion; ConvTranspose(2x2,s2)+ReLU+Conv1x1+Sigmoid fusion ----
+  impl->dwpw_partner.assign(nn_, -1);
+  if (std::getenv("OCRS_B200_DISABLE_DET_FUSION") == nullptr) {
+    auto sole = [&](const std::string& name) -> int {
+      if (graph_outs.count(name)) return -1;
+      int found = -1, cnt = 0;
+      for (int j = 0; j < nn_; ++j) {
+        if (m->skip_[j]) continue;
+        for (const auto& in : g.nodes[j].inputs)
+          if (in == name) { ++cnt; found = j; }
+      }
+      return cnt == 1 ? found : -1;
+    };
+    auto winit = [&](const Node& n, size_t idx) -> const TensorData* {
+      if (n.inputs.size() <= idx || n.inputs[idx].empty()) return nullptr;
+      auto it = g.initializers.find(n.inputs[idx]);
+      return it == g.initializers.end() ? nullptr : &it->second;
+    };
+    for (int i = 0; i < nn_; ++i) {
+      const Node& n = g.nodes[i];
+      if (m->skip_[i]) continue;
+      if (n.op == "Conv" && !m->fuse_relu_[i]) {
+        const TensorData* w = winit(n, 1);
+        if (!w || w->dims.size() != 4) continue;
+        int grp = (int)n.attr_i("group", 1);
+        auto pads = n.attr_ints("pads", {0, 0, 0, 0});
+        auto st = n.attr_ints("strides", {1, 1});
+        auto dl = n.attr_ints("dilations", {1, 1});
+        bool is_dw = grp == w->dims[0] && w->dims[1] == 1 && w->dims[2] == 3 && w->dims[3] == 3 && pads == std::vector<int64_t>{1, 1, 1, 1} &&
+                     st[0] == st[1] && (st[0] == 1 || st[0] == 2) && dl == std::vector<int64_t>{1, 1} &&
+                     (n.inputs.size() < 3 || n.inputs[2].empty() || winit(n, 2));
+        if (!is_dw) continue;
+        int j = sole(n.outputs[0]);
+        if (j < 0 || g.nodes[j].op != "Conv" || g.nodes[j].inputs[0] != n.outputs[0]) continue;
+        const Node& pn = g.nodes[j];
+        const TensorData* pw = winit(pn, 1);
+        if (!pw || pw->dims.size() != 4 || pw->dims[2] != 1 || pw->dims[3] != 1 || pn.attr_i("group", 1) != 1) continue;
+        if (pn.attr_ints("pads", {0, 0, 0, 0}) != std::vector<int64_t>{0, 0, 0, 0} ||
+            pn.attr_ints("strides", {1, 1}) != std::vector<int64_t>{1, 1}) continue;
+        if (pn.inputs.size() > 2 && !pn.inputs[2].empty() && !winit(pn, 2)) continue;
+        if (pw->dims[1] != w->dims[0] || !nn::dwpw_supported((int)w->dims[0], (int)pw->dims[0])) continue;
+        impl->dwpw_partner[i] = j;
+        m->skip_[j] = 1;
+        impl->out_rename[i] = impl->out_rename[j].empty() ? pn.outputs[0] : impl->out_rename[j];
+      } else if (n.op == "ConvTranspose" && m->fuse_relu_[i]) {
+        const TensorData* w = winit(n, 1);
+        if (!w || w->dims.size() != 4 || w->dims[2] != 2 || w->dims[3] != 2 || n.attr_i("group", 1) != 1) continue;
+        if (n.attr_ints("strides", {1, 1}) != std::vector<int64_t>{2, 2} ||
+            n.attr_ints("pads", {0, 0, 0, 0}) != std::vector<int64_t>{0, 0, 0, 0}) continue;
+        if (w->dims[0] > 16 || w->dims[1] > 16) continue;
+        int j = sole(impl->out_rename[i]);
+        if (j < 0 || g.nodes[j].op != "Conv" || m->fuse_relu_[j]) continue;
+        const Node& cn = g.nodes[j];
+        const TensorData* w2 = winit(cn, 1);
+        if (!w2 || w2->dims.size() != 4 || w2->dims[0] != 1 || w2->dims[1] != w->dims[1] || w2->dims[2] != 1 || w2->dims[3] != 1) continue;
+        if (cn.attr_i("group", 1) != 1 || cn.attr_ints("pads", {0, 0, 0, 0}) != std::vector<int64_t>{0, 0, 0, 0} ||
+            cn.attr_ints("strides", {1, 1}) != std::vector<int64_t>{1, 1}) continue;
+        if (cn.inputs.size() > 2 && !cn.inputs[2].empty() && !winit(cn, 2)) continue;
+        int k = sole(cn.outputs[0]);
+        if (k < 0 || g.nodes[k].op != "Sigmoid") {
+          // the Sigmoid may produce the graph output: `sole` rejects graph outputs only for the *input* name
+          continue;
+        }
+        Impl::HeadFuse hf;
+        hf.conv1x1 = j;
+        hf.sigmoid = k;
+        impl->head_fuse[i] = hf;
+        m->skip_[j] = 1;
+        m->skip_[k] = 1;
+        impl->out_rename[i] = g.nodes[k].outputs[0];
       }
     }
   }
@@ -573,7 +651,25 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
     const double flops_before = flops;
     int ptok = prof ? prof->begin(prof_prefix + op, st) : -1;
 
-    if (op == "Conv") {
+    if (op == "Conv" && impl->dwpw_partner[ni] >= 0) {
+      // depthwise 3x3 + pointwise 1x1 (+ReLU) in one kernel
+      const Node& pn = g.nodes[impl->dwpw_partner[ni]];
+      const Value& X = in[0];
+      OCRS_CHECK(!X.is_int && X.shape.size() == 4, kRunFailed, "Conv: expected 4-D input");
+      Value PW = get(pn.inputs[1]);
+      const float* dwb = has(2) ? in[2].t.data : nullptr;
+      const float* pwb = (pn.inputs.size() > 2 && !pn.inputs[2].empty()) ? get(pn.inputs[2]).t.data : nullptr;
+      int N_ = (int)X.shape[0], C_ = (int)X.shape[1], H_ = (int)X.shape[2], W_ = (int)X.shape[3];
+      OCRS_CHECK(in[1].shape[0] == C_, kRunFailed, "Conv: channel mismatch");
+      int K_ = (int)PW.shape[0];
+      int stride = (int)n.attr_ints("strides", {1, 1})[0];
+      int OH = (H_ + 2 - 3) / stride + 1, OW = (W_ + 2 - 3) / stride + 1;
+      DTensor Y = alloc_tensor({N_, K_, OH, OW}, st);
+      nn::dwpw_conv(X.t.data, in[1].t.data, dwb, PW.t.data, pwb, Y.data, N_, C_, H_, W_, K_, stride,
+                    fuse_relu_[impl->dwpw_partner[ni]], st);
+      flops += 2.0 * N_ * OH * OW * (double)C_ * (9.0 + K_);
+      out.push_back(dev_value(Y));
+    } else if (op == "Conv") {
       const Value& X = in[0];
       const Value& W = in[1];
       OCRS_CHECK(!X.is_int && X.shape.size() == 4 && W.shape.size() == 4, kRunFailed, "Conv: expected 4-D x/w");
@@ -615,10 +711,26 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
       p.OH = (int)((p.H - 1) * strides[0] - pads[0] - pads[2] + p.R + opad[0]);
       p.OW = (int)((p.W - 1) * strides[1] - pads[1] - pads[3] + p.S + opad[1]);
       p.relu = fuse_relu_[ni];
-      DTensor Y = alloc_tensor({p.N, p.K, p.OH, p.OW}, st);
-      nn::conv_transpose2d(X.t.data, W.t.data, has(2) ? in[2].t.data : nullptr, Y.data, p, st);
-      flops += 2.0 * p.N * p.C * p.H * p.W * (double)(p.K / p.groups) * p.R * p.S;
-      out.push_back(dev_value(Y));
+      const bool k2s2 = p.R == 2 && p.S == 2 && p.stride_h == 2 && p.stride_w == 2 && pads[0] == 0 && pads[1] == 0 &&
+                        pads[2] == 0 && pads[3] == 0 && opad[0] == 0 && opad[1] == 0 && p.groups == 1;
+      auto hf = impl->head_fuse.find(ni);
+      if (hf != impl->head_fuse.end() && k2s2) {
+        const Node& cn = g.nodes[hf->second.conv1x1];
+        Value W2 = get(cn.inputs[1]);
+        const float* b2 = (cn.inputs.size() > 2 && !cn.inputs[2].empty()) ? get(cn.inputs[2]).t.data : nullptr;
+        DTensor Y = alloc_tensor({p.N, 1, p.OH, p.OW}, st);
+        nn::conv_transpose_2x2s2_head(X.t.data, W.t.data, has(2) ? in[2].t.data : nullptr, W2.t.data, b2, Y.data, p.N,
+                                      p.C, p.H, p.W, p.K, st);
+        flops += 2.0 * p.N * p.H * p.W * 4.0 * ((double)p.C * p.K + p.K);
+        out.push_back(dev_value(Y));
+      } else {
+        OCRS_CHECK(hf == impl->head_fuse.end(), kInternal, "head fusion planned for an unsupported ConvTranspose");
+        DTensor Y = alloc_tensor({p.N, p.K, p.OH, p.OW}, st);
+        if (k2s2) nn::conv_transpose_2x2s2(X.t.data, W.t.data, has(2) ? in[2].t.data : nullptr, Y.data, p.N, p.C, p.H, p.W, p.K, p.relu, st);
+        else nn::conv_transpose2d(X.t.data, W.t.data, has(2) ? in[2].t.data : nullptr, Y.data, p, st);
+        flops += 2.0 * p.N * p.C * p.H * p.W * (double)(p.K / p.groups) * p.R * p.S;
+        out.push_back(dev_value(Y));
+      }
     } else if (op == "MaxPool" || op == "AveragePool") {
       const Value& X = in[0];
       OCRS_CHECK(X.shape.size() == 4, kRunFailed, op + ": expected 4-D input");

@@ -187,6 +187,158 @@ __global__ void conv_transpose_kernel(const float* __restrict__ x, const float* 
   y[idx] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused depthwise 3x3 + pointwise 1x1 (+ReLU).  One thread per output pixel, KOUT accumulators in
+// registers, all weights in shared memory.  Removes the depthwise intermediate (write + read).
+// ---------------------------------------------------------------------------------------------
+template <int KOUT>
+__global__ void __launch_bounds__(128)
+dwpw_kernel(const float* __restrict__ x, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+            const float* __restrict__ pw_w, const float* __restrict__ pw_b, float* __restrict__ y, int N, int C, int H,
+            int W, int OH, int OW, int stride, int relu) {
+  extern __shared__ float sm[];
+  float* s_dw = sm;                 // [C][9]
+  float* s_db = s_dw + C * 9;       // [C]
+  float* s_pw = s_db + C;           // [C][KOUT]  (transposed for broadcast reads)
+  float* s_pb = s_pw + C * KOUT;    // [KOUT]
+  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) s_dw[i] = dw_w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = dw_b ? dw_b[i] : 0.f;
+  for (int i = threadIdx.x; i < C * KOUT; i += blockDim.x) {
+    int c = i / KOUT, k = i - c * KOUT;
+    s_pw[i] = pw_w[k * C + c];
+  }
+  for (int i = threadIdx.x; i < KOUT; i += blockDim.x) s_pb[i] = pw_b ? pw_b[i] : 0.f;
+  __syncthreads();
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  const int n = blockIdx.z;
+  if (ox >= OW) return;
+  float acc[KOUT];
+#pragma unroll
+  for (int k = 0; k < KOUT; ++k) acc[k] = s_pb[k];
+  const int iy0 = oy * stride - 1, ix0 = ox * stride - 1;
+  const float* xn = x + (int64_t)n * C * H * W;
+  for (int c = 0; c < C; ++c) {
+    const float* xc = xn + (int64_t)c * H * W;
+    const float* wd = s_dw + c * 9;
+    float v = s_db[c];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = iy0 + r;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int ix = ix0 + q;
+        if (ix < 0 || ix >= W) continue;
+        v = fmaf(__ldg(xc + (int64_t)iy * W + ix), wd[r * 3 + q], v);
+      }
+    }
+    const float* wp = s_pw + c * KOUT;
+#pragma unroll
+    for (int k = 0; k < KOUT; ++k) acc[k] = fmaf(v, wp[k], acc[k]);
+  }
+  float* yn = y + (int64_t)n * KOUT * OH * OW + (int64_t)oy * OW + ox;
+#pragma unroll
+  for (int k = 0; k < KOUT; ++k) {
+    float v = acc[k];
+    if (relu) v = fmaxf(v, 0.f);
+    yn[(int64_t)k * OH * OW] = v;
+  }
+}
+
+// ConvTranspose 2x2 stride 2: one thread per input pixel and chunk of 8 output channels.
+constexpr int CT_KB = 8;
+__global__ void __launch_bounds__(128)
+convt2x2_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ y, int N, int C, int H, int W, int K, int relu) {
+  extern __shared__ float sw[];  // [C][CT_KB][4]
+  const int k0 = blockIdx.y * CT_KB;
+  for (int i = threadIdx.x; i < C * CT_KB * 4; i += blockDim.x) {
+    int c = i / (CT_KB * 4), r = i - c * CT_KB * 4, kk = r / 4, t = r - kk * 4;
+    sw[i] = (k0 + kk < K) ? w[((int64_t)c * K + k0 + kk) * 4 + t] : 0.f;
+  }
+  __syncthreads();
+  const int64_t HW = (int64_t)H * W;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * HW) return;
+  const int n = (int)(idx / HW);
+  const int64_t rem = idx - (int64_t)n * HW;
+  const int iy = (int)(rem / W), ix = (int)(rem - (int64_t)iy * W);
+  float acc[CT_KB][4];
+#pragma unroll
+  for (int kk = 0; kk < CT_KB; ++kk) {
+    const float bb = (b && k0 + kk < K) ? b[k0 + kk] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[kk][t] = bb;
+  }
+  const float* xp = x + (int64_t)n * C * HW + rem;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(xp + (int64_t)c * HW);
+    const float* wc = sw + c * CT_KB * 4;
+#pragma unroll
+    for (int kk = 0; kk < CT_KB; ++kk)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[kk][t] = fmaf(v, wc[kk * 4 + t], acc[kk][t]);
+  }
+  const int OW = 2 * W;
+  const int64_t OHW = 4 * HW;
+#pragma unroll
+  for (int kk = 0; kk < CT_KB; ++kk) {
+    if (k0 + kk >= K) break;
+    float* yo = y + ((int64_t)n * K + k0 + kk) * OHW + (int64_t)(2 * iy) * OW + 2 * ix;
+    float2 top = make_float2(acc[kk][0], acc[kk][1]), bot = make_float2(acc[kk][2], acc[kk][3]);
+    if (relu) {
+      top.x = fmaxf(top.x, 0.f); top.y = fmaxf(top.y, 0.f);
+      bot.x = fmaxf(bot.x, 0.f); bot.y = fmaxf(bot.y, 0.f);
+    }
+    *reinterpret_cast<float2*>(yo) = top;
+    *reinterpret_cast<float2*>(yo + OW) = bot;
+  }
+}
+
+// ConvT 2x2 s2 (C -> Km) + ReLU + Conv1x1 (Km -> 1) + Sigmoid; one thread per input pixel.
+__global__ void __launch_bounds__(128)
+convt2x2_head_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                     const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ y, int N, int C,
+                     int H, int W, int Km) {
+  __shared__ float sw[16 * 16 * 4 + 16 + 16 + 1];
+  float* s_b = sw + C * Km * 4;
+  float* s_w2 = s_b + Km;
+  for (int i = threadIdx.x; i < C * Km * 4; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Km; i += blockDim.x) {
+    s_b[i] = b ? b[i] : 0.f;
+    s_w2[i] = w2[i];
+  }
+  if (threadIdx.x == 0) s_w2[Km] = b2 ? b2[0] : 0.f;
+  __syncthreads();
+  const int64_t HW = (int64_t)H * W;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * HW) return;
+  const int n = (int)(idx / HW);
+  const int64_t rem = idx - (int64_t)n * HW;
+  const int iy = (int)(rem / W), ix = (int)(rem - (int64_t)iy * W);
+  float xin[16];
+  const float* xp = x + (int64_t)n * C * HW + rem;
+  for (int c = 0; c < C; ++c) xin[c] = __ldg(xp + (int64_t)c * HW);
+  float o[4] = {s_w2[Km], s_w2[Km], s_w2[Km], s_w2[Km]};
+  for (int k = 0; k < Km; ++k) {
+    float a[4] = {s_b[k], s_b[k], s_b[k], s_b[k]};
+    for (int c = 0; c < C; ++c) {
+      const float* wc = sw + (c * Km + k) * 4;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) a[t] = fmaf(xin[c], wc[t], a[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[t] = fmaf(fmaxf(a[t], 0.f), s_w2[k], o[t]);
+  }
+  const int OW = 2 * W;
+  float* yo = y + (int64_t)n * 4 * HW + (int64_t)(2 * iy) * OW + 2 * ix;
+  float2 top = make_float2(1.f / (1.f + expf(-o[0])), 1.f / (1.f + expf(-o[1])));
+  float2 bot = make_float2(1.f / (1.f + expf(-o[2])), 1.f / (1.f + expf(-o[3])));
+  *reinterpret_cast<float2*>(yo) = top;
+  *reinterpret_cast<float2*>(yo + OW) = bot;
+}
+
 template <bool kMax>
 __global__ void pool_kernel(const float* __restrict__ x, float* __restrict__ y, PoolParams p) {
   int64_t total = (int64_t)p.NC * p.OH * p.OW;
@@ -452,6 +604,47 @@ void conv_transpose2d(const float* x, const float* w, const float* b, float* y, 
   int64_t total = (int64_t)p.N * p.K * p.OH * p.OW;
   if (total == 0) return;
   conv_transpose_kernel<<<grid1d(total), kThreads, 0, st>>>(x, w, b, y, p);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+bool dwpw_supported(int C, int K) { return (K == 8 || K == 16 || K == 32) && C >= 1 && C <= 64; }
+
+void dwpw_conv(const float* x, const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_b, float* y,
+               int N, int C, int H, int W, int K, int stride, int relu, cudaStream_t st) {
+  const int OH = (H + 2 - 3) / stride + 1, OW = (W + 2 - 3) / stride + 1;
+  if (N == 0 || OH <= 0 || OW <= 0) return;
+  dim3 grid((unsigned)ceil_div(OW, 128), (unsigned)OH, (unsigned)N);
+  size_t smem = (size_t)(C * 9 + C + C * K + K) * sizeof(float);
+  if (K == 8) dwpw_kernel<8><<<grid, 128, smem, st>>>(x, dw_w, dw_b, pw_w, pw_b, y, N, C, H, W, OH, OW, stride, relu);
+  else if (K == 16) dwpw_kernel<16><<<grid, 128, smem, st>>>(x, dw_w, dw_b, pw_w, pw_b, y, N, C, H, W, OH, OW, stride, relu);
+  else dwpw_kernel<32><<<grid, 128, smem, st>>>(x, dw_w, dw_b, pw_w, pw_b, y, N, C, H, W, OH, OW, stride, relu);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void conv_transpose_2x2s2(const float* x, const float* w, const float* b, float* y, int N, int C, int H, int W, int K,
+                          int relu, cudaStream_t st) {
+  int64_t total = (int64_t)N * H * W;
+  if (!total || !K) return;
+  static bool attr = false;
+  size_t smem = (size_t)C * CT_KB * 4 * sizeof(float);
+  if (!attr && smem > 48 * 1024) {
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(convt2x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid((unsigned)ceil_div(total, 128), (unsigned)ceil_div(K, CT_KB));
+  convt2x2_kernel<<<grid, 128, smem, st>>>(x, w, b, y, N, C, H, W, K, relu);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void conv_transpose_2x2s2_head(const float* x, const float* w, const float* b, const float* w2, const float* b2,
+                               float* y, int N, int C, int H, int W, int Km, cudaStream_t st) {
+  int64_t total = (int64_t)N * H * W;
+  if (!total) return;
+  OCRS_CHECK(C <= 16 && Km <= 16, kInternal, "conv_transpose_2x2s2_head: channel count > 16");
+  convt2x2_head_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(x, w, b, w2, b2, y, N, C, H, W, Km);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }

@@ -31,6 +31,21 @@ struct ConvTParams {
 // w: [C, K/groups, R, S]
 void conv_transpose2d(const float* x, const float* w, const float* b, float* y, const ConvTParams& p, cudaStream_t st);
 
+// Fused depthwise 3x3 (pad 1, stride s) + pointwise 1x1 (+ ReLU): y = relu?(pw(dw(x))).
+// x [N,C,H,W]; dw_w [C][9], dw_b [C]; pw_w [K][C], pw_b [K]; y [N,K,OH,OW].  K in {8,16,32}, C <= 64.
+bool dwpw_supported(int C, int K);
+void dwpw_conv(const float* x, const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_b, float* y,
+               int N, int C, int H, int W, int K, int stride, int relu, cudaStream_t st);
+
+// ConvTranspose 2x2 stride 2 (no padding), any C -> K, optional ReLU.  w: [C][K][2][2].
+void conv_transpose_2x2s2(const float* x, const float* w, const float* b, float* y, int N, int C, int H, int W, int K,
+                          int relu, cudaStream_t st);
+
+// ConvTranspose 2x2 s2 (C -> Km) + ReLU, then Conv 1x1 (Km -> 1) + Sigmoid, fused; C, Km <= 16.
+// y: [N,1,2H,2W].
+void conv_transpose_2x2s2_head(const float* x, const float* w, const float* b, const float* w2, const float* b2,
+                               float* y, int N, int C, int H, int W, int Km, cudaStream_t st);
+
 struct PoolParams {
   int NC, H, W, R, S, stride_h, stride_w, pad_t, pad_l, OH, OW;
   int count_include_pad;
