@@ -74,3 +74,14 @@ def test_config3_1024x768(engines, seed):
     batched = eng.ocr_batch([inp, inp])
     assert text_of(batched[0]) == text_of(texts) == text_of(batched[1])
     assert eng.get_text(inp) == "\n".join(t for t in text_of(texts) if t is not None)
+
+
+def test_engine_reads_the_page(engines):
+    """With the trained fixtures the CUDA engine actually reads the text (ground truth of the
+    synthetic generator), not merely agrees with the oracle."""
+    eng, _ = engines
+    page, texts = make_page(7)
+    inp = eng.prepare_input(ob.ImageSource.from_tensor(page, ob.DimOrder.Hwc))
+    got = eng.get_text(inp).split("\n")
+    assert len(got) == len(texts)
+    assert sum(1 for g in got if g in texts) >= 0.9 * len(texts)
