@@ -64,7 +64,6 @@ struct Engine::HostTimer {
   std::chrono::steady_clock::time_point t0;
   HostTimer(Engine* eng, const char* n) : e(eng), name(n), t0(std::chrono::steady_clock::now()) {}
   ~HostTimer() {
-    if (!e->prof_.enabled) return;
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     auto& slot = e->host_ms_[name];
     slot.first += ms;

@@ -341,16 +341,32 @@ constexpr int kCl = 8;                                 // CTAs per cluster
 constexpr int kAPlane = 4 * 128 * 128;                 // R slice plane: 4 K-subtiles x [128 rows x 128 B] = 64 KB
 constexpr int kHBuf = 2 * kHPlane;                     // one h buffer (hi + lo) = 32 KB
 constexpr int kExBytes = 3 * NL * 32 * 4;              // gate pre-activation exchange [3][NL][32] f32
-constexpr int kStageBf = 4 * 1024;                     // per-warp bf16 staging [8 lines][32 units] x (hi, lo)
+constexpr int kGateWarps = 16;                         // 4 line groups x 4 TMEM lane quarters
+constexpr int kGateThreads = kGateWarps * 32;
+constexpr int kStageBf = kGateWarps * 256;             // per warp: [hi|lo][2 lines][32 units] bf16
+constexpr int kClThreads = kGateThreads + 64;          // + TMA/init warp + MMA warp
 constexpr int kClSmem = 2 * kAPlane + 2 * kHBuf + kExBytes + kStageBf + 1024 + 256;
 
-__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(192, 1)
+// fast gate functions for the latency-critical recurrence: MUFU exp + approximate divide
+// (|error| ~1e-7, far inside the 1e-3 log-prob budget; saturate correctly for large |x|)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads, 1)
 gru_cluster_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
                    const float* __restrict__ xw, const float* __restrict__ rb, const float* __restrict__ h0,
                    float* __restrict__ Y, float* __restrict__ Yh, const SeqLine* __restrict__ lines, int n_lines,
-                   int D, int64_t y_dstride, int rev0, int rev1) {
+                   int D, int64_t y_dstride, int rev0, int rev1, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t base = (smem0 + 1023u) & ~1023u;
   const uint32_t a_hi = base, a_lo = base + kAPlane;
   const uint32_t hbuf0 = base + 2 * kAPlane;           // buffer b at hbuf0 + b*kHBuf: [hi plane | lo plane]
   const uint32_t ex = hbuf0 + 2 * kHBuf;
@@ -360,6 +376,7 @@ gru_cluster_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_con
   const uint32_t d_full_bar = bar_base + 8;
   const uint32_t h_ready_bar0 = bar_base + 16;         // [2]
   const uint32_t tmem_slot = bar_base + 32;
+  float* exf = reinterpret_cast<float*>(smem_raw + (ex - smem0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -384,7 +401,7 @@ gru_cluster_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 4) {
+  if (warp == kGateWarps) {
     // ---- one-time load of this CTA's R slice: rows [g*32, g*32+32) <- R[d][g*256 + rank*32 ...] ----
     if (lane == 0) {
       mbar_expect_tx(r_full_bar, 2 * 12 * 32 * 128);
@@ -396,9 +413,9 @@ gru_cluster_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_con
           tma_load_2d(a_lo + off, &tm_r_lo, kk * 64, row, r_full_bar);
         }
     }
-  } else if (warp < 4) {
+  } else if (warp < kGateWarps) {
     // ---- h_{-1}: every CTA fills its own copy of buffer 0 (all 256 units) ----
-    for (int e = threadIdx.x; e < NL * 256; e += 128) {
+    for (int e = threadIdx.x; e < NL * 256; e += kGateThreads) {
       const int l = e >> 8, u = e & 255;
       float v = 0.f;
       if (h0 != nullptr && l < n_in_tile && tl[l].valid) v = h0[((size_t)d * n_lines + tile * NL + l) * 256 + u];
@@ -409,20 +426,27 @@ gru_cluster_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_con
       asm volatile("st.shared.b16 [%0], %1;" ::"r"(hbuf0 + off), "h"(__bfloat16_as_ushort(hi)) : "memory");
       asm volatile("st.shared.b16 [%0], %1;" ::"r"(hbuf0 + kHPlane + off), "h"(__bfloat16_as_ushort(lo)) : "memory");
     }
-    fence_proxy_async_all();
+    fence_proxy_async();
   }
   __syncthreads();
   cluster_sync_all();  // every CTA's barriers are initialised before anyone arrives remotely
 
-  if (warp == 5) {
+  if (warp == kGateWarps + 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NL >> 3) << 17) | ((128u >> 4) << 24);
       mbar_wait(r_full_bar, 0);
+      long long m_wait = 0, m_issue = 0;
       for (int step = 0; step < steps; ++step) {
         const int b = step & 1;
-        if (step > 0) mbar_wait_cluster(h_ready_bar0 + 8 * b, ((step - 1) >> 1) & 1);
+        const long long c0 = clock64();
+        if (step > 0) {
+          mbar_wait(h_ready_bar0 + 8 * b, ((step - 1) >> 1) & 1);  // relaxed spin ...
+          fence_acq_rel_cluster();                                 // ... then one cluster-scope acquire
+        }
         tc_fence_after();
+        const long long c1 = clock64();
+        m_wait += c1 - c0;
         const uint32_t hb = hbuf0 + b * kHBuf;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -437,40 +461,42 @@ gru_cluster_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_con
           }
         }
         umma_commit(d_full_bar);
+        m_issue += clock64() - c1;
       }
+      if (dbg && blockIdx.x == 0 && blockIdx.y == 0) { dbg[0] = m_wait; dbg[1] = m_issue; dbg[7] = steps; }
     }
-  } else if (warp < 4) {
-    // ---------------- gate math ----------------
-    // phase A: warp g < 3 drains gate g (TMEM lanes 32g..32g+31 = units, columns = lines) into `ex`
-    // phase B: thread (warp w, lane) owns unit = lane of this CTA's slice and lines w*8 .. w*8+7
+  } else if (warp < kGateWarps) {
+    // ---------------- gate math: 16 warps ----------------
+    // phase A: warp (q, g) = (warp / 4, warp % 4), g < 3, drains gate g of lines 8q..8q+7 (TMEM lanes 32g.. = units)
+    // phase B: warp w owns lines 2w, 2w+1 for unit = lane of this CTA's slice
+    const int q = warp >> 2, g = warp & 3;
     const int unit = (int)rank * 32 + lane;
-    float h[8];
+    const int l0 = 2 * warp;
+    float h[2];
+    int lT[2];
+    int64_t lx[2], lxs[2], ly[2], lys[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int l = warp * 8 + i;
-      h[i] = (h0 != nullptr && l < n_in_tile && tl[l].valid) ? h0[((size_t)d * n_lines + tile * NL + l) * 256 + unit] : 0.f;
-    }
-    const float rbz = rb[(size_t)d * 768 + unit], rbr = rb[(size_t)d * 768 + 256 + unit], rbn = rb[(size_t)d * 768 + 512 + unit];
-    // per-line descriptors of my 8 lines
-    int lT[8];
-    int64_t lx[8], lxs[8], ly[8], lys[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int l = warp * 8 + i;
+    for (int i = 0; i < 2; ++i) {
+      const int l = l0 + i;
       const bool ok = l < n_in_tile && tl[l].valid;
+      h[i] = (h0 != nullptr && ok) ? h0[((size_t)d * n_lines + tile * NL + l) * 256 + unit] : 0.f;
       lT[i] = ok ? tl[l].T : 0;
       lx[i] = ok ? tl[l].xw_base : 0;
       lxs[i] = ok ? tl[l].xw_tstride : 0;
       ly[i] = ok ? tl[l].y_base : 0;
       lys[i] = ok ? tl[l].y_tstride : 0;
     }
-    const uint32_t my_stage = stage + warp * (8 * 32 * 2 * 2);  // [hi: 8 lines x 32 units][lo: ...] bf16
+    const float rbz = rb[(size_t)d * 768 + unit], rbr = rb[(size_t)d * 768 + 256 + unit], rbn = rb[(size_t)d * 768 + 512 + unit];
+    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_raw + (stage - smem0)) + warp * 128;  // [hi: 2x32][lo: 2x32]
+    const uint32_t my_stage = stage + warp * 256;
+    long long e_wait = 0, e_drain = 0, e_math = 0, e_xchg = 0, e_sig = 0;
     for (int step = 0; step < steps; ++step) {
       const int b = step & 1, nb = b ^ 1;
+      const long long t0 = clock64();
       // prefetch the input projections of this step (overlaps the MMAs)
-      float xz[8], xr[8], xn[8];
+      float xz[2], xr[2], xn[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 2; ++i) {
         xz[i] = xr[i] = xn[i] = 0.f;
         if (step < lT[i]) {
           const int t = rev ? (lT[i] - 1 - step) : step;
@@ -482,66 +508,81 @@ gru_cluster_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_con
       }
       mbar_wait(d_full_bar, step & 1);
       tc_fence_after();
-      if (warp < 3) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), acc);
+      const long long t1 = clock64();
+      e_wait += t1 - t0;
+      if (g < 3) {
+        uint32_t acc[8];
+        tmem_ld8(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * 8), acc);
 #pragma unroll
-        for (int l = 0; l < NL; ++l)
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(ex + (uint32_t)(((warp * NL + l) * 32 + lane) * 4)), "r"(acc[l]) : "memory");
+        for (int j = 0; j < 8; ++j) exf[(g * NL + q * 8 + j) * 32 + lane] = __uint_as_float(acc[j]);
       }
       tc_fence_before();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kGateThreads);
+      const long long t2 = clock64();
+      e_drain += t2 - t1;
+      {
+        float pz[2], pr[2], pn[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int l = warp * 8 + i;
-        float hn = h[i];
-        if (step < lT[i]) {
-          float pz, pr, pn;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pz) : "r"(ex + (uint32_t)(((0 * NL + l) * 32 + lane) * 4)));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pr) : "r"(ex + (uint32_t)(((1 * NL + l) * 32 + lane) * 4)));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pn) : "r"(ex + (uint32_t)(((2 * NL + l) * 32 + lane) * 4)));
-          const float z = sigmoidf_(xz[i] + pz + rbz);
-          const float r = sigmoidf_(xr[i] + pr + rbr);
-          const float nn_ = tanhf(xn[i] + r * (pn + rbn));
-          hn = (1.f - z) * nn_ + z * h[i];
-          h[i] = hn;
-          const int t = rev ? (lT[i] - 1 - step) : step;
-          Y[ly[i] + (int64_t)t * lys[i] + (int64_t)d * y_dstride + unit] = hn;
+        for (int i = 0; i < 2; ++i) {
+          pz[i] = exf[(0 * NL + l0 + i) * 32 + lane];
+          pr[i] = exf[(1 * NL + l0 + i) * 32 + lane];
+          pn[i] = exf[(2 * NL + l0 + i) * 32 + lane];
         }
-        __nv_bfloat16 hi, lo;
-        split_bf16(hn, hi, lo);
-        asm volatile("st.shared.b16 [%0], %1;" ::"r"(my_stage + (uint32_t)((i * 32 + lane) * 2)), "h"(__bfloat16_as_ushort(hi)) : "memory");
-        asm volatile("st.shared.b16 [%0], %1;" ::"r"(my_stage + 512u + (uint32_t)((i * 32 + lane) * 2)), "h"(__bfloat16_as_ushort(lo)) : "memory");
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const bool act = step < lT[i];
+          const float z = fast_sigmoid(xz[i] + pz[i] + rbz);
+          const float r = fast_sigmoid(xr[i] + pr[i] + rbr);
+          const float nn_ = fast_tanh(xn[i] + r * (pn[i] + rbn));
+          const float hn = act ? ((1.f - z) * nn_ + z * h[i]) : h[i];
+          h[i] = hn;
+          if (act) {
+            const int t = rev ? (lT[i] - 1 - step) : step;
+            Y[ly[i] + (int64_t)t * lys[i] + (int64_t)d * y_dstride + unit] = hn;
+          }
+          __nv_bfloat16 hi, lo;
+          split_bf16(hn, hi, lo);
+          stg[i * 32 + lane] = hi;
+          stg[64 + i * 32 + lane] = lo;
+        }
       }
       __syncwarp();
+      const long long t3 = clock64();
+      e_math += t3 - t2;
       if (step + 1 < steps) {
-        // lane -> (line i = lane / 4, 16-byte chunk c = lane % 4 = units 8c..8c+7 of my slice)
-        const int i = lane >> 2, c = lane & 3;
-        const int l = warp * 8 + i;
-        uint4 vhi, vlo;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vhi.x), "=r"(vhi.y), "=r"(vhi.z), "=r"(vhi.w) : "r"(my_stage + (uint32_t)(i * 64 + c * 16)));
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vlo.x), "=r"(vlo.y), "=r"(vlo.z), "=r"(vlo.w) : "r"(my_stage + 512u + (uint32_t)(i * 64 + c * 16)));
-        const int kk = (int)rank >> 1;
-        const int chunk = (((int)rank & 1) * 4 + c) ^ (l & 7);
-        const uint32_t off = (uint32_t)(kk * kHSub + (l >> 3) * 1024 + (l & 7) * 128 + chunk * 16);
-        const uint32_t dst_hi = hbuf0 + nb * kHBuf + off, dst_lo = dst_hi + kHPlane;
+        if (lane < 16) {
+          // lane -> (plane p, line i, 16-byte chunk c = units 8c..8c+7 of my slice)
+          const int c = lane & 3, i = (lane >> 2) & 1, p = lane >> 3;
+          const int l = l0 + i;
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(my_stage + (uint32_t)(p * 128 + i * 64 + c * 16)));
+          const int kk = (int)rank >> 1;
+          const int chunk = (((int)rank & 1) * 4 + c) ^ (l & 7);
+          const uint32_t dst = hbuf0 + nb * kHBuf + p * kHPlane +
+                               (uint32_t)(kk * kHSub + (l >> 3) * 1024 + (l & 7) * 128 + chunk * 16);
 #pragma unroll
-        for (int p = 0; p < kCl; ++p) {
-          st_cluster_v4(mapa(dst_hi, (uint32_t)p), vhi);
-          st_cluster_v4(mapa(dst_lo, (uint32_t)p), vlo);
+          for (int pc = 0; pc < kCl; ++pc) st_cluster_v4(mapa(dst, (uint32_t)pc), v);
+          fence_proxy_async_all();
         }
-        fence_proxy_async_all();
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kGateThreads);
+      const long long t4 = clock64();
+      e_xchg += t4 - t3;
       if (step + 1 < steps && threadIdx.x == 0) {
+        fence_acq_rel_cluster();  // one cluster-scope release for the whole CTA's DSMEM writes
 #pragma unroll
-        for (int p = 0; p < kCl; ++p) mbar_arrive_remote(mapa(h_ready_bar0 + 8 * nb, (uint32_t)p));
+        for (int pc = 0; pc < kCl; ++pc) mbar_arrive_remote_relaxed(mapa(h_ready_bar0 + 8 * nb, (uint32_t)pc));
       }
+      e_sig += clock64() - t4;
+    }
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      dbg[2] = e_wait; dbg[3] = e_drain; dbg[4] = e_math; dbg[5] = e_xchg; dbg[6] = e_sig;
     }
     if (Yh != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int l = warp * 8 + i;
+      for (int i = 0; i < 2; ++i) {
+        const int l = l0 + i;
         if (l < n_in_tile && tl[l].valid) Yh[((size_t)d * n_lines + tile * NL + l) * 256 + unit] = h[i];
       }
     }
@@ -658,8 +699,8 @@ void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* 
       attr = true;
     }
     dim3 grid((unsigned)(n_tiles * kCl), (unsigned)D);
-    gru_cluster_kernel<<<grid, 192, kClSmem, st>>>(tr_hi, tr_lo, xw, w.rb.as<float>(), h0, Y, Yh, d_desc, N, D,
-                                                   (int64_t)N * H, reverse[0], D > 1 ? reverse[1] : 0);
+    gru_cluster_kernel<<<grid, kClThreads, kClSmem, st>>>(tr_hi, tr_lo, xw, w.rb.as<float>(), h0, Y, Yh, d_desc, N, D,
+                                                          (int64_t)N * H, reverse[0], D > 1 ? reverse[1] : 0, nullptr);
     count_launch();
   }
   OCRS_CUDA_CHECK(cudaGetLastError());
@@ -713,9 +754,25 @@ void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, cons
     attr2 = true;
   }
   dim3 grid((unsigned)(n_tiles * kCl), (unsigned)D);
-  gru_cluster_kernel<<<grid, 192, kClSmem, st>>>(tr_hi, tr_lo, xw, w.rb.as<float>(), nullptr, Y, nullptr, d_desc, n_lines, D,
-                                                 y_dstride, reverse[0], D > 1 ? reverse[1] : 0);
+  static const bool dbg_on = std::getenv("OCRS_B200_GRU_DEBUG") != nullptr;
+  long long* d_dbg = nullptr;
+  if (dbg_on) {
+    d_dbg = static_cast<long long*>(alloc(8 * sizeof(long long)));
+    OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 8 * sizeof(long long), st));
+  }
+  gru_cluster_kernel<<<grid, kClThreads, kClSmem, st>>>(tr_hi, tr_lo, xw, w.rb.as<float>(), nullptr, Y, nullptr, d_desc, n_lines,
+                                                        D, y_dstride, reverse[0], D > 1 ? reverse[1] : 0, d_dbg);
   count_launch();
+  if (dbg_on) {
+    long long hdbg[8];
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(hdbg, d_dbg, sizeof(hdbg), cudaMemcpyDeviceToHost, st));
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st));
+    double n = (double)std::max<long long>(hdbg[7], 1);
+    fprintf(stderr,
+            "[gru dbg] steps %lld | MMA thread: wait h_ready %.0f, issue+commit %.0f | gate warp0: wait d_full %.0f, drain %.0f, "
+            "math %.0f, exchange+fence %.0f, signal %.0f (cycles/step)\n",
+            hdbg[7], hdbg[0] / n, hdbg[1] / n, hdbg[2] / n, hdbg[3] / n, hdbg[4] / n, hdbg[5] / n, hdbg[6] / n);
+  }
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -123,6 +123,12 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+// relaxed remote arrive: pair with ONE fence_acq_rel_cluster() before a batch of arrives (a
+// release-qualified arrive costs MEMBAR.ALL.GPU + ERRBAR each)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
