@@ -163,6 +163,10 @@ def run_gpu(args):
 
     det, rec = ensure_models()
     eng = ob.OcrEngine(ob.OcrEngineParams(detection_model=det, recognition_model=rec, device=local))
+    # `--in-flight 2`: a second engine instance (own streams and buffers) on the same GPU lets the host
+    # phases of one batch (layout analysis, result assembly) overlap the kernels of the other
+    engines = [eng] + [ob.OcrEngine(ob.OcrEngineParams(detection_model=det, recognition_model=rec, device=local))
+                       for _ in range(max(1, args.in_flight) - 1)]
     pages = make_batch(rank)
     # host copies in pinned memory (e2e) and device copies (kernel-only `value`)
     pinned = [torch.from_numpy(p).pin_memory() for p in pages]
@@ -179,39 +183,80 @@ def run_gpu(args):
         if world > 1:
             gather_texts(results, device=f"cuda:{local}")
 
-    def step_resident():
-        inputs = [eng.prepare_input_device(t.data_ptr(), 0, ob.DimOrder.Hwc, PAGE_H, PAGE_W, 3) for t in resident]
-        res = eng.ocr_batch_text(inputs)
-        gather_text(res)
-        return res
+    def step_resident(e=None):
+        e = e or eng
+        inputs = [e.prepare_input_device(t.data_ptr(), 0, ob.DimOrder.Hwc, PAGE_H, PAGE_W, 3) for t in resident]
+        return e.ocr_batch_text(inputs)
 
-    def step_e2e():
-        inputs = [eng.prepare_input(ob.ImageSource(t.numpy(), ob.DimOrder.Hwc)) for t in pinned]
-        res = eng.ocr_batch_text(inputs)
-        gather_text(res)
-        return res
+    def step_e2e(e=None):
+        e = e or eng
+        inputs = [e.prepare_input(ob.ImageSource(t.numpy(), ob.DimOrder.Hwc)) for t in pinned]
+        return e.ocr_batch_text(inputs)
+
+    def run_steps(fn, steps):
+        """Runs `steps` batches, at most len(engines) in flight (one host thread per engine); the text
+        of every finished batch is gathered to rank 0."""
+        if len(engines) == 1:
+            for _ in range(steps):
+                gather_text(fn(eng))
+            return
+        import queue
+        todo = queue.Queue()
+        for i in range(steps):
+            todo.put(i)
+        done = queue.Queue()
+        errs = []
+
+        def worker(e):
+            try:
+                while True:
+                    try:
+                        todo.get_nowait()
+                    except queue.Empty:
+                        return
+                    done.put(fn(e))
+            except Exception as ex:  # noqa: BLE001
+                errs.append(ex)
+                done.put(None)
+
+        ts = [threading.Thread(target=worker, args=(e,)) for e in engines]
+        [t.start() for t in ts]
+        for _ in range(steps):
+            res = done.get()
+            if res is None:
+                break
+            gather_text(res)  # collectives stay on the main thread, in completion order
+        [t.join() for t in ts]
+        if errs:
+            raise errs[0]
 
     def timed(fn, steps):
         barrier()
         launches0 = ob.kernel_launch_count()
-        h2d0, d2h0 = eng.transfer_bytes()
+        tb0 = [e.transfer_bytes() for e in engines]
         eng.timer_start()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
+        run_steps(fn, steps)
+        for e2 in engines[1:]:
+            e2.timer_start()  # (orders a marker behind everything enqueued on that engine's stream)
+            e2.timer_stop()
         ms = eng.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
+        ms = max(ms, wall) if len(engines) > 1 else ms  # several streams: the host clock brackets them all
         barrier()
-        h2d1, d2h1 = eng.transfer_bytes()
+        tb1 = [e.transfer_bytes() for e in engines]
+        h2d0 = sum(t[0] for t in tb0); d2h0 = sum(t[1] for t in tb0)
+        h2d1 = sum(t[0] for t in tb1); d2h1 = sum(t[1] for t in tb1)
         t = torch.tensor([ms, wall], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), ob.kernel_launch_count() - launches0, (h2d1 - h2d0) / steps, (d2h1 - d2h0) / steps
 
-    for _ in range(args.warmup):
-        step_resident()
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    for e in engines:
+        for _ in range(args.warmup):
+            step_resident(e)
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e(e)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -227,7 +272,7 @@ def run_gpu(args):
     barrier()
     res = None
     for _ in range(max(1, min(3, args.steps))):
-        res = step_resident()
+        res = step_resident(eng)
     prof = eng.profile(reset=True)
     eng.set_profiling(False)
     stats = eng.stats(reset=True)
@@ -290,7 +335,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pages_per_gpu": BATCH, "page_hw": [PAGE_H, PAGE_W],
+        "config": {"workload": WORKLOAD, "pages_per_gpu": BATCH, "page_hw": [PAGE_H, PAGE_W], "batches_in_flight": len(engines),
                    "weights": "models/*.onnx", "l2": "inputs per step (18.9 MB u8 + activations >> 126 MB L2 over a step)",
                    "words_per_page": stats["words"] / max(1, BATCH * max(1, min(3, args.steps))),
                    "lines_per_page": stats["lines"] / max(1, BATCH * max(1, min(3, args.steps)))},
@@ -313,6 +358,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight per GPU (engine instances)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
