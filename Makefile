@@ -9,7 +9,7 @@ NVFLAGS   := $(ARCH) $(CXXFLAGS)
 LIB       := ocrs_b200/libocrs_b200.so
 
 # "exact" translation units: no FMA contraction on the device either
-EXACT_CU  := $(CSRC)/image_kernels.cu
+EXACT_CU  := $(CSRC)/image_kernels.cu $(CSRC)/ctc_beam.cu
 FAST_CU   := $(filter-out $(EXACT_CU),$(wildcard $(CSRC)/*.cu))
 CPP       := $(wildcard $(CSRC)/*.cpp)
 
@@ -22,6 +22,9 @@ $(BUILD):
 	mkdir -p $(BUILD)
 
 $(BUILD)/image_kernels.o: $(CSRC)/image_kernels.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+
+$(BUILD)/ctc_beam.o: $(CSRC)/ctc_beam.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 
 $(BUILD)/%.o: $(CSRC)/%.cu $(HDRS) | $(BUILD)

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <exception>
 #include <map>
+#include <deque>
 #include <thread>
 
 #include "layout.h"
@@ -128,6 +129,8 @@ Engine::Engine(const EngineParams& p) {
   debug_ = p.debug;
   decode_method_ = p.decode_method;
   beam_width_ = p.beam_width;
+  OCRS_CHECK(decode_method_ != DecodeMethod::kBeamSearch || (beam_width_ >= 1 && beam_width_ <= (uint32_t)img::kMaxBeamWidth),
+             kInvalidArg, "beam width must be in [1, " + std::to_string(img::kMaxBeamWidth) + "]");
   alphabet_ = utf8_to_codepoints(p.has_alphabet ? p.alphabet_utf8 : std::string(kDefaultAlphabet));  // lib.rs:149-151
   if (p.has_allowed_chars) {  // lib.rs:153-170
     std::vector<uint32_t> allowed = utf8_to_codepoints(p.allowed_chars_utf8);
@@ -554,16 +557,50 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
                "output column count (" + std::to_string(shape[2]) + ") does not match alphabet size (" +
                    std::to_string(n_classes) + ")");  // recognition.rs:487-493
   };
-  auto run_ctc = [&](Chunk& c, const float* logits_ptr) {
+  // CTC decode of a set of lines sharing one logits buffer: greedy = one argmax launch + one
+  // collapse launch; beam search = one block per line (recognition.rs:509-515)
+  std::deque<std::vector<img::CtcLine>> cl_keep;  // descriptors must outlive their async upload
+  auto decode_lines = [&](const float* logits_ptr, int64_t rows, std::vector<img::CtcLine>&& cl_in) {
+    cl_keep.push_back(std::move(cl_in));
+    std::vector<img::CtcLine>& cl = cl_keep.back();
+    const bool beam = decode_method_ == DecodeMethod::kBeamSearch;
+    int64_t n_nodes = 0;
+    if (beam)
+      for (auto& L : cl) {
+        L.node_off = n_nodes;
+        n_nodes += img::ctc_beam_nodes_per_line(L.T, (int)beam_width_);
+      }
+    const size_t lab_bytes = ((size_t)rows * 4 + 15) / 16 * 16;
+    const size_t desc_bytes = (cl.size() * sizeof(img::CtcLine) + 15) / 16 * 16;
+    ctc_scratch_.reserve(lab_bytes + desc_bytes + (size_t)n_nodes * 12 + 64);
+    int32_t* row_labels = ctc_scratch_.as<int32_t>();
+    auto* d_cl = reinterpret_cast<img::CtcLine*>(ctc_scratch_.as<char>() + lab_bytes);
+    int32_t* d_nodes = reinterpret_cast<int32_t*>(ctc_scratch_.as<char>() + lab_bytes + desc_bytes);
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(d_cl, cl.data(), cl.size() * sizeof(img::CtcLine), cudaMemcpyHostToDevice, st_));
+    h2d_bytes_ += (int64_t)(cl.size() * sizeof(img::CtcLine));
+    const uint8_t* excl = has_excluded_ ? d_excluded_.as<uint8_t>() : nullptr;
+    int tkt = prof_.begin(beam ? "stage/ctc_beam" : "stage/ctc_greedy", st_);
+    if (beam)
+      img::ctc_beam_search(logits_ptr, (int)n_classes, excl, d_cl, (int)cl.size(), (int)beam_width_, d_nodes,
+                           ctc_out_.as<int32_t>(), st_);
+    else
+      img::ctc_greedy_packed(logits_ptr, rows, (int)n_classes, excl, row_labels, d_cl, (int)cl.size(),
+                             ctc_out_.as<int32_t>(), st_);
+    prof_.end(tkt, st_, 0, 4.0 * (double)rows * (double)n_classes);
+  };
+  auto chunk_lines = [&](const Chunk& c, int64_t row_off, std::vector<img::CtcLine>* cl) {
     OCRS_CHECK(c.T <= c.gw, kWrongOutput, "recognition output longer than its input");
     stats_.n_timesteps += (int64_t)c.T * c.count;
-    ctc_scratch_.reserve((size_t)c.count * c.T * 4 + 4);
-    int32_t* o = ctc_out_.as<int32_t>() + c.out_off;
-    int tkt = prof_.begin("stage/ctc_greedy", st_);
-    img::ctc_greedy(logits_ptr, c.T, c.count, (int)n_classes, has_excluded_ ? d_excluded_.as<uint8_t>() : nullptr,
-                    ctc_scratch_.as<int32_t>(), o, o + (int64_t)c.count * c.gw, o + (int64_t)c.count * c.gw * 2, st_);
-    prof_.end(tkt, st_, 0, 4.0 * (double)c.T * c.count * (double)n_classes);
-    // ctc_scratch_ is reused by the next chunk on the same stream: ordering is preserved.
+    for (int b = 0; b < c.count; ++b) {
+      img::CtcLine L{};
+      L.base = row_off + b;
+      L.stride = c.count;
+      L.T = c.T;
+      L.lab_off = c.out_off + (int64_t)b * c.T;
+      L.pos_off = c.out_off + (int64_t)c.count * c.gw + (int64_t)b * c.T;
+      L.cnt_off = c.out_off + (int64_t)c.count * c.gw * 2 + b;
+      cl->push_back(L);
+    }
   };
   std::vector<DTensor> feats;  // per-group feature sequences (packed path)
   if (rec_->has_seq_head()) {
@@ -611,7 +648,10 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
     DTensor logits = rec_->run_seq_head(reinterpret_cast<const float*>(packed->ptr), rows, groups, st_, &cost, &prof_, "rec/");
     prof_.end(tkh, st_, cost.flops, 0);
     stats_.rec_flops += cost.flops;
-    for (size_t g = 0; g < chunks.size(); ++g) run_ctc(chunks[g], logits.data + groups[g].row_off * (int64_t)n_classes);
+    std::vector<img::CtcLine> cl;
+    cl.reserve((size_t)n_lines);
+    for (size_t g = 0; g < chunks.size(); ++g) chunk_lines(chunks[g], groups[g].row_off, &cl);
+    decode_lines(logits.data, rows, std::move(cl));
   } else {
     for (auto& c : chunks) {
       float* in_ptr = rec_batch_.as<float>() + descs[c.first].dst_off;
@@ -623,7 +663,9 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
       stats_.rec_batches += 1;
       check_logits(logits.shape, c.count);
       c.T = (int)logits.shape[0];
-      run_ctc(c, logits.data);
+      std::vector<img::CtcLine> cl;
+      chunk_lines(c, 0, &cl);
+      decode_lines(logits.data, (int64_t)c.T * c.count, std::move(cl));
     }
   }
   OCRS_CUDA_CHECK(cudaMemcpyAsync(h_pin_.ptr, ctc_out_.ptr, (size_t)out_total * 4, cudaMemcpyDeviceToHost, st_));

@@ -510,6 +510,45 @@ __global__ void ctc_collapse_kernel(const int32_t* __restrict__ labels, int T, i
   counts[b] = n;
 }
 
+__global__ void ctc_argmax_rows_kernel(const float* __restrict__ logits, int64_t rows, int C,
+                                       const uint8_t* __restrict__ excluded, int32_t* __restrict__ labels) {
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* row = logits + warp * C;
+  float best = -INFINITY;
+  int bi = INT_MAX;
+  for (int c = lane; c < C; c += 32) {
+    float v = (excluded && excluded[c]) ? -INFINITY : row[c];
+    if (bi == INT_MAX || v > best) { best = v; bi = c; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != INT_MAX && (bi == INT_MAX || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+  }
+  if (lane == 0) labels[warp] = bi;
+}
+
+__global__ void ctc_collapse_lines_kernel(const int32_t* __restrict__ labels, const CtcLine* __restrict__ lines,
+                                          int n_lines, int32_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lines) return;
+  const CtcLine L = lines[i];
+  int last = 0, n = 0;
+  for (int pos = 0; pos < L.T; ++pos) {
+    int v = labels[L.base + (int64_t)pos * L.stride];
+    if (v == last) continue;
+    last = v;
+    if (v > 0) {
+      out[L.lab_off + n] = v;
+      out[L.pos_off + n] = pos;
+      ++n;
+    }
+  }
+  out[L.cnt_off] = n;
+}
+
 }  // namespace
 
 // ================================== host launchers ===========================================
@@ -622,6 +661,18 @@ void ctc_greedy(const float* logits, int T, int B, int C, const uint8_t* exclude
   if (T > 0) ctc_argmax_kernel<<<grid1d((int64_t)T * B * 32), kThreads, 0, st>>>(logits, T, B, C, excluded, scratch_labels);
   count_launch();
   ctc_collapse_kernel<<<grid1d(B, 64), 64, 0, st>>>(scratch_labels, T, B, labels_out, pos_out, counts_out);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void ctc_greedy_packed(const float* logits, int64_t rows, int C, const uint8_t* excluded, int32_t* row_labels,
+                       const CtcLine* lines, int n_lines, int32_t* out, cudaStream_t st) {
+  if (n_lines == 0) return;
+  if (rows > 0) {
+    ctc_argmax_rows_kernel<<<grid1d(rows * 32), kThreads, 0, st>>>(logits, rows, C, excluded, row_labels);
+    count_launch();
+  }
+  ctc_collapse_lines_kernel<<<grid1d(n_lines, 32), 32, 0, st>>>(row_labels, lines, n_lines, out);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }

@@ -82,5 +82,25 @@ void crop_lines(const float* const* pages, const int* page_h, const int* page_w,
 void ctc_greedy(const float* logits, int T, int B, int C, const uint8_t* excluded, int32_t* scratch_labels,
                 int32_t* labels_out, int32_t* pos_out, int32_t* counts_out, cudaStream_t st);
 
+// Packed variant: one argmax launch over all rows of all width groups, one collapse launch over
+// all lines.  logits: [rows, C]; line i reads rows base + t*stride, t < T.
+struct CtcLine {
+  int64_t base, stride;
+  int32_t T, pad;
+  int64_t lab_off, pos_off, cnt_off;  // element offsets into `out`
+  int64_t node_off;                   // beam search only: first trie node of this line in `nodes`
+};
+void ctc_greedy_packed(const float* logits, int64_t rows, int C, const uint8_t* excluded, int32_t* row_labels,
+                       const CtcLine* lines, int n_lines, int32_t* out, cudaStream_t st);
+
+// CTC prefix beam search (`DecodeMethod::BeamSearch { width }`, ocrs/src/recognition.rs:199-205,
+// 512-514), one thread block per line.  Same line descriptors and output layout as the greedy
+// decoder; `nodes` is scratch of 3 int32 per trie node, ctc_beam_nodes_per_line(T, width) nodes per
+// line starting at CtcLine::node_off.
+constexpr int kMaxBeamWidth = 1024;
+int64_t ctc_beam_nodes_per_line(int T, int width);
+void ctc_beam_search(const float* logits, int C, const uint8_t* excluded, const CtcLine* lines, int n_lines, int width,
+                     int32_t* nodes, int32_t* out, cudaStream_t st);
+
 }  // namespace img
 }  // namespace ocrs
