@@ -42,7 +42,11 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks / clock-event reasons sampled DURING the timed region (B200_PROFILING.md's clocks
+    line).  NVML is initialised in `prepare()` -- before the warm-up -- because attaching a new
+    NVML client (what spawning `nvidia-smi` does) can stall the GPU for >100 ms; the timed region
+    then only sees light in-process queries every 50 ms.  Falls back to an `nvidia-smi -lms` child
+    started in prepare() whose samples are filtered to the timed window."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -50,48 +54,102 @@ class ClockSampler:
 
     def __init__(self, device_index: int):
         self.idx = device_index
+        self.nvml = None
+        self.handle = None
         self.proc = None
-        self.lines = []
+        self.samples = []   # (t, sm_mhz, sm_max_mhz, [reasons])
+        self.active = False
+        self.alive = False
+        self.t0 = self.t1 = None
 
-    def start(self):
+    def prepare(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:  # noqa: BLE001
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.alive = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        n = self.nvml
+        bits = {}
+        for nm, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                         ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                         ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                         ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            alt = attr.replace("ClocksEventReason", "ClocksThrottleReason")
+            v = getattr(n, attr, None) or getattr(n, alt, None)
+            if v is not None:
+                bits[nm] = int(v)
+        while self.alive:
+            if self.active:
+                try:
+                    sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    try:
+                        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:  # noqa: BLE001
+                        r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.samples.append((time.perf_counter(), sm, self.smax, [k for k, b in bits.items() if r & b]))
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.05)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
+    def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
+                self.samples.append((time.perf_counter(), float(f[1]), float(f[2]),
+                                     [nm for nm, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+    def start(self):
+        self.t0 = time.perf_counter()
+        self.active = True
+
+    def stop(self):
+        self.t1 = time.perf_counter()
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.active = False
+        self.alive = False
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        win = [s for s in self.samples if self.t0 <= s[0] <= self.t1 + 0.12]
+        sm = [s[1] for s in win]
+        smax = [s[2] for s in win]
+        reasons = sorted({r for s in win for r in s[3]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_batch(rank: int):
@@ -252,13 +310,15 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), ob.kernel_launch_count() - launches0, (h2d1 - h2d0) / steps, (d2h1 - d2h0) / steps
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()  # attach the NVML client before the warm-up, not inside the timed region
     for e in engines:
         for _ in range(args.warmup):
             step_resident(e)
         for _ in range(max(1, args.warmup // 2)):
             step_e2e(e)
 
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     eng.profile(reset=True)  # clear host-section timers

@@ -1,5 +1,6 @@
 // ONNX graph executor (host orchestration; kernels live in nn_kernels.cu).
 #include "executor.h"
+#include <mutex>
 
 #include <algorithm>
 #include <cstdlib>
@@ -79,6 +80,28 @@ void configure_device_pool(int device) {
   OCRS_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t thr = UINT64_MAX;
   OCRS_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  // Pre-size the pool once per device: activations are allocated stream-ordered on several
+  // streams, and a pool that has to grow from the OS in the middle of a batch stalls every
+  // stream of the device.  One allocate + free leaves the memory cached in the pool.
+  static std::mutex mu;
+  static std::set<int> warmed;
+  std::lock_guard<std::mutex> lk(mu);
+  if (warmed.insert(device).second) {
+    size_t mb = 3072;
+    if (const char* e = std::getenv("OCRS_B200_POOL_PREWARM_MB")) mb = (size_t)std::strtoull(e, nullptr, 10);
+    size_t free_b = 0, total_b = 0;
+    OCRS_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    size_t bytes = std::min(mb << 20, free_b / 4);
+    if (bytes > 0) {
+      void* p = nullptr;
+      if (cudaMallocAsync(&p, bytes, (cudaStream_t)0) == cudaSuccess) {
+        cudaFreeAsync(p, (cudaStream_t)0);
+        cudaStreamSynchronize((cudaStream_t)0);
+      } else {
+        cudaGetLastError();  // not fatal: the pool simply grows on demand
+      }
+    }
+  }
 }
 
 namespace {

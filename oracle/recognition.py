@@ -158,7 +158,8 @@ def ctc_decode_beam(seq: np.ndarray, width: int) -> Tuple[List[DecodeStep], floa
     (Hannun et al. 2014) in log space, no language model.  Each prefix keeps
     (log p ending in blank, log p ending in non-blank); after every timestep the `width` most
     probable prefixes survive (ties: earlier-created prefix first).  `pos` of an emitted label
-    is the timestep at which the label was appended on the surviving path."""
+    is the timestep at which that prefix first entered the beam (it is kept while the prefix
+    survives, like the greedy decoder's "first timestep of the run")."""
     T, C = seq.shape
     NEG = -math.inf
     # prefix (tuple of labels) -> [p_blank, p_non_blank, positions tuple, creation order]
@@ -171,6 +172,8 @@ def ctc_decode_beam(seq: np.ndarray, width: int) -> Tuple[List[DecodeStep], floa
             nonlocal order
             e = nxt.get(prefix)
             if e is None:
+                if prefix in beams:  # re-reached through its parent: keep the original timesteps
+                    positions = beams[prefix][2]
                 e = [NEG, NEG, positions, order]
                 order += 1
                 nxt[prefix] = e

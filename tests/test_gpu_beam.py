@@ -83,7 +83,7 @@ def test_beam_sums_paths_greedy_does_not(tmp_path):
     _, rec = fake_paths(tmp_path)
     greedy = ob.OcrEngine(ob.OcrEngineParams(recognition_model=rec, alphabet=ALPHABET))
     ginp = greedy.prepare_input(ob.ImageSource.from_tensor(img, ob.DimOrder.Chw))
-    assert text_of(greedy.recognize_text(ginp, [_full_line(W)])) == [""]
+    assert text_of(greedy.recognize_text(ginp, [_full_line(W)])) == [None]  # no chars -> None (recognition.rs:305-309)
 
 
 def test_several_lines_and_allowed_chars(tmp_path):
