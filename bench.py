@@ -251,12 +251,15 @@ def run_gpu(args):
         inputs = [e.prepare_input(ob.ImageSource(t.numpy(), ob.DimOrder.Hwc)) for t in pinned]
         return e.ocr_batch_text(inputs)
 
+    step_done = []  # completion time of every step (diagnostic: largest gap is reported)
+
     def run_steps(fn, steps):
         """Runs `steps` batches, at most len(engines) in flight (one host thread per engine); the text
         of every finished batch is gathered to rank 0."""
         if len(engines) == 1:
             for _ in range(steps):
                 gather_text(fn(eng))
+                step_done.append(time.perf_counter())
             return
         import queue
         todo = queue.Queue()
@@ -281,6 +284,7 @@ def run_gpu(args):
         [t.start() for t in ts]
         for _ in range(steps):
             res = done.get()
+            step_done.append(time.perf_counter())
             if res is None:
                 break
             gather_text(res)  # collectives stay on the main thread, in completion order
@@ -288,13 +292,18 @@ def run_gpu(args):
         if errs:
             raise errs[0]
 
+    gaps = []  # per timed() call: largest interval between two step completions, ms
+
     def timed(fn, steps):
         barrier()
         launches0 = ob.kernel_launch_count()
         tb0 = [e.transfer_bytes() for e in engines]
         eng.timer_start()
         t0 = time.perf_counter()
+        del step_done[:]
+        step_done.append(t0)
         run_steps(fn, steps)
+        gaps.append(max(b - a for a, b in zip(step_done, step_done[1:])) * 1e3 if len(step_done) > 1 else 0.0)
         for e2 in engines[1:]:
             e2.timer_start()  # (orders a marker behind everything enqueued on that engine's stream)
             e2.timer_stop()
@@ -404,6 +413,7 @@ def run_gpu(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "stage_ms_per_step": stage_ms, "host_ms_per_step": host_real, "host_ms_per_step_serial_profile": host_ms,
         "wall_ms_per_step": wall / args.steps,
+        "max_step_gap_ms": {"value": round(gaps[0], 2), "e2e": round(gaps[1], 2)} if len(gaps) >= 2 else None,
         "op_ms_per_step": {k: round(v["ms"] / max(1, min(3, args.steps)), 3) for k, v in ops.items()},
     }
     print(json.dumps(line), flush=True)

@@ -179,6 +179,12 @@ int ocrs_b200_model_run(const ocrs_b200_model* cm, const float* in, const int64_
       float* host = cmalloc<float>((size_t)y.numel());
       cudaError_t e = cudaMemcpyAsync(host, y.data, (size_t)y.numel() * 4, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess && m->model->take_tc_overflow()) {
+        // split-fp16 range overflow: the model now runs its convolutions in fp32; repeat the call
+        y = m->model->run(x, st, &cost);
+        e = cudaMemcpyAsync(host, y.data, (size_t)y.numel() * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      }
       if (e != cudaSuccess) {
         std::free(host);
         throw Error(kCuda, std::string("CUDA error ") + cudaGetErrorString(e));

@@ -2,12 +2,12 @@
 //
 // Tile: 128 output pixels (TH rows x TW columns of one image) x COUT channels per CTA.
 // K loop: 9 taps x (Cin / KC) channel chunks; per k-block TMA loads
-//   A_hi, A_lo : [128 pixels][KC] bf16, box {KC, TW, TH, 1} of the NHWC activation at
+//   A_hi, A_lo : [128 pixels][KC] fp16, box {KC, TW, TH, 1} of the NHWC activation at
 //                (c0, w0 + kw - 1, h0 + kh - 1, n) -- the halo / zero padding is TMA out-of-bounds fill
-//   B_hi, B_lo : [COUT][KC] bf16 from the [COUT][9*Cin] weight matrix
+//   B_hi, B_lo : [COUT][KC] fp16 from the [COUT][9*Cin] weight matrix
 // into 128B- (KC = 64) or 64B- (KC = 32) swizzled shared memory; one elected thread issues
 //   D += A_hi*B_hi ; D += A_hi*B_lo ; D += A_lo*B_hi        (tcgen05.mma kind::f16, fp32 accumulate in TMEM)
-// and the four warps drain TMEM (tcgen05.ld 32x32b), add bias, ReLU, split to bf16 hi/lo, store NHWC.
+// and the four warps drain TMEM (tcgen05.ld 32x32b), add bias, ReLU, split to fp16 hi/lo, store NHWC.
 #include "conv_tc.h"
 
 #include "tc_host.h"
@@ -15,6 +15,7 @@
 
 #include <cuda.h>
 
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -24,6 +25,29 @@ namespace tc {
 namespace {
 
 using namespace ptx;
+
+// ---- split-fp16 helpers: x = hi + lo, both fp16 (22 significant bits; |x| must stay below 65504:
+// larger values raise the model's overflow flag and the executor reruns on the fp32 kernels) ----
+__device__ __forceinline__ void split1(float v, uint16_t& hi, uint16_t& lo, int* ovf) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
+  if (!(fabsf(v) <= 65504.f)) *ovf = 1;  // also catches NaN
+}
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo, int* ovf) {
+  uint16_t h0, l0, h1, l1;
+  split1(v0, h0, l0, ovf);
+  split1(v1, h1, l1, ovf);
+  hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
+  lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+}
+__device__ __forceinline__ float join_lo(uint32_t hi, uint32_t lo) {
+  return __half2float(__ushort_as_half((uint16_t)(hi & 0xFFFFu))) + __half2float(__ushort_as_half((uint16_t)(lo & 0xFFFFu)));
+}
+__device__ __forceinline__ float join_hi(uint32_t hi, uint32_t lo) {
+  return __half2float(__ushort_as_half((uint16_t)(hi >> 16))) + __half2float(__ushort_as_half((uint16_t)(lo >> 16)));
+}
 
 template <int KC, int COUT>
 struct Cfg {
@@ -38,8 +62,8 @@ template <int KC, int COUT>
 __global__ void __launch_bounds__(128, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi,
-                  __nv_bfloat16* __restrict__ out_lo, int N, int H, int W, int Cin, int TW, int TH, int relu) {
+                  const float* __restrict__ bias, act_t* __restrict__ out_hi,
+                  act_t* __restrict__ out_lo, int N, int H, int W, int Cin, int TW, int TH, int relu, int* __restrict__ ovf) {
   using C = Cfg<KC, COUT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -93,7 +117,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+    // c_format F32 (bit 4), a/b format F16 (0 at bits 7, 10), N >> 3 at 17, M >> 4 at 24
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % C::kStages;
       const uint32_t ph = (kb / C::kStages) & 1;
@@ -103,7 +128,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       const uint32_t a_hi = st, a_lo = st + C::kABytes, b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
 #pragma unroll
       for (int k = 0; k < KC / 16; ++k) {
-        const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle atom
+        const uint32_t koff = k * 32;  // 16 fp16 = 32 bytes along K inside the swizzle atom
         const uint64_t da_hi = make_desc<KC>(a_hi + koff), da_lo = make_desc<KC>(a_lo + koff);
         const uint64_t db_hi = make_desc<KC>(b_hi + koff), db_lo = make_desc<KC>(b_lo + koff);
         umma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
@@ -137,11 +162,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         v0 = fmaxf(v0, 0.f);
         v1 = fmaxf(v1, 0.f);
       }
-      __nv_bfloat16 h0b = __float2bfloat16_rn(v0), h1b = __float2bfloat16_rn(v1);
-      __nv_bfloat16 l0b = __float2bfloat16_rn(v0 - __bfloat162float(h0b));
-      __nv_bfloat16 l1b = __float2bfloat16_rn(v1 - __bfloat162float(h1b));
-      hi_pack[j / 2] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
-      lo_pack[j / 2] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+      split2(v0, v1, hi_pack[j / 2], lo_pack[j / 2], ovf);
     }
     if (valid) {
       uint4* dh = reinterpret_cast<uint4*>(out_hi + pix * COUT + c0);
@@ -161,13 +182,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
 // ------------------------------------------------------------------------------------------
 // layout converters / pooling (bandwidth-bound helpers)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
 
-__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                          __nv_bfloat16* __restrict__ lo, int C, int64_t HW, int64_t total_pix) {
+__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, act_t* __restrict__ hi,
+                                          act_t* __restrict__ lo, int C, int64_t HW, int64_t total_pix, int* __restrict__ ovf) {
   // one thread per (pixel, 8-channel group): coalesced reads along pixels, 16-byte writes
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int groups = C / 8;
@@ -179,17 +196,13 @@ __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, __nv_bflo
   uint32_t ph[4], pl[4];
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(src[(int64_t)j * HW], h0, l0);
-    split_bf16(src[(int64_t)(j + 1) * HW], h1, l1);
-    ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    split2(src[(int64_t)j * HW], src[(int64_t)(j + 1) * HW], ph[j / 2], pl[j / 2], ovf);
   }
   *reinterpret_cast<uint4*>(hi + pix * C + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
   *reinterpret_cast<uint4*>(lo + pix * C + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
-__global__ void nhwc_split_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+__global__ void nhwc_split_to_nchw_kernel(const act_t* __restrict__ hi, const act_t* __restrict__ lo,
                                           float* __restrict__ y, int C, int64_t HW, int64_t total_pix) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int groups = C / 8;
@@ -203,15 +216,15 @@ __global__ void nhwc_split_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, 
   float* dst = y + (n * C + (int64_t)g * 8) * HW + rem;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float a = __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-    float b = __uint_as_float(hh[j] & 0xFFFF0000u) + __uint_as_float(ll[j] & 0xFFFF0000u);
+    float a = join_lo(hh[j], ll[j]);
+    float b = join_hi(hh[j], ll[j]);
     dst[(int64_t)(2 * j) * HW] = a;
     dst[(int64_t)(2 * j + 1) * HW] = b;
   }
 }
 
-__global__ void maxpool_nhwc_split_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
-                                          __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int N,
+__global__ void maxpool_nhwc_split_kernel(const act_t* __restrict__ x_hi, const act_t* __restrict__ x_lo,
+                                          act_t* __restrict__ y_hi, act_t* __restrict__ y_lo, int N,
                                           int H, int W, int C, int ph, int pw) {
   const int OH = H / ph, OW = W / pw, groups = C / 8;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,8 +247,8 @@ __global__ void maxpool_nhwc_split_kernel(const __nv_bfloat16* __restrict__ x_hi
       const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float a = __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-        float b = __uint_as_float(hh[j] & 0xFFFF0000u) + __uint_as_float(ll[j] & 0xFFFF0000u);
+        float a = join_lo(hh[j], ll[j]);
+        float b = join_hi(hh[j], ll[j]);
         if (a > best[2 * j]) {
           best[2 * j] = a;
           bh[j] = (bh[j] & 0xFFFF0000u) | (hh[j] & 0xFFFFu);
@@ -256,7 +269,7 @@ __global__ void maxpool_nhwc_split_kernel(const __nv_bfloat16* __restrict__ x_hi
 template <int COUT>
 __global__ void __launch_bounds__(128)
 stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
-            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int N, int H, int W) {
+            act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, int N, int H, int W, int* __restrict__ ovf) {
   __shared__ float sw[COUT * 9 + COUT];
   for (int i = threadIdx.x; i < COUT * 10; i += blockDim.x) sw[i] = i < COUT * 9 ? wgt[i] : bias[i - COUT * 9];
   __syncthreads();
@@ -275,8 +288,8 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const fl
       p[r][c] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xi + (int64_t)ih * W + iw) : 0.f;
     }
   }
-  __nv_bfloat16* oh_ptr = out_hi + idx * COUT;
-  __nv_bfloat16* ol_ptr = out_lo + idx * COUT;
+  act_t* oh_ptr = out_hi + idx * COUT;
+  act_t* ol_ptr = out_lo + idx * COUT;
 #pragma unroll 1
   for (int c8 = 0; c8 < COUT; c8 += 8) {
     uint32_t ph[4], pl[4];
@@ -296,14 +309,14 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const fl
           best = fmaxf(best, a);
         }
       const float v = fmaxf(best + sw[COUT * 9 + c8 + j], 0.f);
-      __nv_bfloat16 hi, lo;
-      split_bf16(v, hi, lo);
+      uint16_t hi, lo;
+      split1(v, hi, lo, ovf);
       if (j & 1) {
-        ph[j / 2] |= (uint32_t)__bfloat16_as_ushort(hi) << 16;
-        pl[j / 2] |= (uint32_t)__bfloat16_as_ushort(lo) << 16;
+        ph[j / 2] |= (uint32_t)hi << 16;
+        pl[j / 2] |= (uint32_t)lo << 16;
       } else {
-        ph[j / 2] = (uint32_t)__bfloat16_as_ushort(hi);
-        pl[j / 2] = (uint32_t)__bfloat16_as_ushort(lo);
+        ph[j / 2] = (uint32_t)hi;
+        pl[j / 2] = (uint32_t)lo;
       }
     }
     *reinterpret_cast<uint4*>(oh_ptr + c8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -315,8 +328,8 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const fl
 // host side
 // ------------------------------------------------------------------------------------------
 template <int KC, int COUT>
-void launch_conv(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvWeightsTC& w, __nv_bfloat16* y_hi,
-                 __nv_bfloat16* y_lo, int N, int H, int W, int relu, cudaStream_t st) {
+void launch_conv(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, act_t* y_hi,
+                 act_t* y_lo, int N, int H, int W, int relu, int* ovf, cudaStream_t st) {
   using C = Cfg<KC, COUT>;
   const int Cin = w.Cin;
   int TW = W > 64 ? 128 : (W > 32 ? 64 : (W > 16 ? 32 : 16));
@@ -341,7 +354,7 @@ void launch_conv(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const Con
   const int tiles = N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
   conv3x3_tc_kernel<KC, COUT><<<tiles, 128, C::kSmemBytes, st>>>(tm_x_hi, tm_x_lo, tm_w_hi, tm_w_lo,
                                                                    w.bias.as<float>(), y_hi, y_lo, N, H, W, Cin, TW, TH,
-                                                                   relu);
+                                                                   relu, ovf);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -385,13 +398,13 @@ std::unique_ptr<StemWeights> prepare_stem(const float* w, const float* b, int Co
   return s;
 }
 
-void stem_conv_relu_pool2(const float* x, const StemWeights& w, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int N, int H,
-                          int W, cudaStream_t st) {
+void stem_conv_relu_pool2(const float* x, const StemWeights& w, act_t* y_hi, act_t* y_lo, int N, int H,
+                          int W, int* ovf, cudaStream_t st) {
   int64_t total = (int64_t)N * (H / 2) * (W / 2);
   if (!total) return;
   unsigned grid = (unsigned)ceil_div(total, 128);
-  if (w.Cout == 32) stem_kernel<32><<<grid, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, N, H, W);
-  else stem_kernel<64><<<grid, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, N, H, W);
+  if (w.Cout == 32) stem_kernel<32><<<grid, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, N, H, W, ovf);
+  else stem_kernel<64><<<grid, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, N, H, W, ovf);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -401,14 +414,15 @@ std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, i
   out->Cin = Cin;
   out->Cout = Cout;
   const size_t K = (size_t)9 * Cin;
-  std::vector<__nv_bfloat16> hi(K * Cout), lo(K * Cout);
+  std::vector<act_t> hi(K * Cout), lo(K * Cout);
   for (int co = 0; co < Cout; ++co)
     for (int ci = 0; ci < Cin; ++ci)
       for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw) {
           float v = w[(((size_t)co * Cin + ci) * 3 + kh) * 3 + kw];
-          __nv_bfloat16 h = __float2bfloat16_rn(v);
-          __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+          OCRS_CHECK(std::fabs(v) <= 65504.f, kModelLoad, "conv weight exceeds the fp16 range of the tensor-core path");
+          act_t h = __float2half_rn(v);
+          act_t l = __float2half_rn(v - __half2float(h));
           size_t k = (size_t)(kh * 3 + kw) * Cin + ci;
           hi[(size_t)co * K + k] = h;
           lo[(size_t)co * K + k] = l;
@@ -424,28 +438,28 @@ std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, i
   return out;
 }
 
-void conv3x3(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvWeightsTC& w, __nv_bfloat16* y_hi,
-             __nv_bfloat16* y_lo, int N, int H, int W, int relu, cudaStream_t st) {
+void conv3x3(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, act_t* y_hi,
+             act_t* y_lo, int N, int H, int W, int relu, int* ovf, cudaStream_t st) {
   if (N == 0 || H == 0 || W == 0) return;
   const bool k64 = (w.Cin % 64 == 0);
-  if (k64 && w.Cout == 128) launch_conv<64, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, st);
-  else if (k64 && w.Cout == 64) launch_conv<64, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, st);
-  else if (!k64 && w.Cout == 128) launch_conv<32, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, st);
-  else if (!k64 && w.Cout == 64) launch_conv<32, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, st);
+  if (k64 && w.Cout == 128) launch_conv<64, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ovf, st);
+  else if (k64 && w.Cout == 64) launch_conv<64, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ovf, st);
+  else if (!k64 && w.Cout == 128) launch_conv<32, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ovf, st);
+  else if (!k64 && w.Cout == 64) launch_conv<32, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ovf, st);
   else throw Error(kInternal, "conv3x3 (tensor core): unsupported channel configuration");
 }
 
-void nchw_to_nhwc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int C, int H, int W,
+void nchw_to_nhwc_split(const float* x, act_t* hi, act_t* lo, int N, int C, int H, int W, int* ovf,
                         cudaStream_t st) {
   OCRS_CHECK(C % 8 == 0, kInternal, "nchw_to_nhwc_split: C must be a multiple of 8");
   int64_t HW = (int64_t)H * W, total_pix = (int64_t)N * HW, total = total_pix * (C / 8);
   if (!total) return;
-  nchw_to_nhwc_split_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(x, hi, lo, C, HW, total_pix);
+  nchw_to_nhwc_split_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(x, hi, lo, C, HW, total_pix, ovf);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
-void nhwc_split_to_nchw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* y, int N, int C, int H, int W,
+void nhwc_split_to_nchw(const act_t* hi, const act_t* lo, float* y, int N, int C, int H, int W,
                         cudaStream_t st) {
   OCRS_CHECK(C % 8 == 0, kInternal, "nhwc_split_to_nchw: C must be a multiple of 8");
   int64_t HW = (int64_t)H * W, total_pix = (int64_t)N * HW, total = total_pix * (C / 8);
@@ -455,8 +469,8 @@ void nhwc_split_to_nchw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float*
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
-void maxpool_nhwc_split(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, __nv_bfloat16* y_hi,
-                        __nv_bfloat16* y_lo, int N, int H, int W, int C, int ph, int pw, cudaStream_t st) {
+void maxpool_nhwc_split(const act_t* x_hi, const act_t* x_lo, act_t* y_hi,
+                        act_t* y_lo, int N, int H, int W, int C, int ph, int pw, cudaStream_t st) {
   OCRS_CHECK(C % 8 == 0, kInternal, "maxpool_nhwc_split: C must be a multiple of 8");
   int64_t total = (int64_t)N * (H / ph) * (W / pw) * (C / 8);
   if (!total) return;

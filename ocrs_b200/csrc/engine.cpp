@@ -427,6 +427,16 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
   OCRS_CHECK(rec_ != nullptr, kModelNotLoaded, "Recognition model not loaded");  // lib.rs:254
   OCRS_CHECK(pages.size() == lines_per_page.size(), kInvalidArg, "pages / lines size mismatch");
   std::lock_guard<std::mutex> lk(mu_);
+  auto result = recognize_text_locked(pages, lines_per_page);
+  // split-fp16 range overflow in the tensor-core convolutions: the model has switched itself to
+  // the fp32 kernels, repeat the call once
+  if (rec_->take_tc_overflow()) result = recognize_text_locked(pages, lines_per_page);
+  return result;
+}
+
+std::vector<std::vector<TextLine>> Engine::recognize_text_locked(
+    const std::vector<const OcrInput*>& pages,
+    const std::vector<std::vector<std::vector<RotatedRect>>>& lines_per_page) {
   OCRS_CUDA_CHECK(cudaSetDevice(device_));
   const int n_pages = (int)pages.size();
   const int rec_h = (int)rec_input_height();

@@ -82,6 +82,9 @@ class Engine {
   std::vector<std::vector<TextLine>> recognize_text(
       const std::vector<const OcrInput*>& pages,
       const std::vector<std::vector<std::vector<geom::RotatedRect>>>& lines_per_page);
+  std::vector<std::vector<TextLine>> recognize_text_locked(
+      const std::vector<const OcrInput*>& pages,
+      const std::vector<std::vector<std::vector<geom::RotatedRect>>>& lines_per_page);  // caller holds mu_
   // lib.rs:268 / recognition.rs:366-393: returns [input_height, resized_width] row-major.
   std::vector<float> prepare_recognition_input(const OcrInput& in, const std::vector<geom::RotatedRect>& line,
                                                int* out_h, int* out_w);

@@ -1,5 +1,6 @@
 // ONNX graph executor (host orchestration; kernels live in nn_kernels.cu).
 #include "executor.h"
+#include <atomic>
 #include <mutex>
 
 #include <algorithm>
@@ -87,7 +88,7 @@ void configure_device_pool(int device) {
   static std::set<int> warmed;
   std::lock_guard<std::mutex> lk(mu);
   if (warmed.insert(device).second) {
-    size_t mb = 3072;
+    size_t mb = 12288;
     if (const char* e = std::getenv("OCRS_B200_POOL_PREWARM_MB")) mb = (size_t)std::strtoull(e, nullptr, 10);
     size_t free_b = 0, total_b = 0;
     OCRS_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
@@ -187,6 +188,8 @@ struct Model::Impl {
   struct HeadFuse { int conv1x1 = -1, sigmoid = -1; };
   std::map<int, HeadFuse> head_fuse; // per ConvTranspose node: fused 1x1 conv + sigmoid
   bool tc_enabled = false;
+  std::atomic<bool> tc_conv_on{true};  // cleared for good after an fp16 range overflow
+  DeviceBuffer tc_ovf;                  // int32 flag written by the split-fp16 kernels
 };
 
 Model::Model() = default;
@@ -339,6 +342,8 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
   impl->tc_member.assign(nn_, 0);
   impl->tc_enabled = tc::available() && std::getenv("OCRS_B200_DISABLE_TC") == nullptr;
   if (impl->tc_enabled) {
+    impl->tc_ovf.reserve(4);
+    OCRS_CUDA_CHECK(cudaMemset(impl->tc_ovf.ptr, 0, 4));
     auto published = [&](int i) { return impl->out_rename[i].empty() ? g.nodes[i].outputs[0] : impl->out_rename[i]; };
     auto conv_ok = [&](const Node& n) {
       if (n.op != "Conv" || n.inputs.size() < 2) return false;
@@ -601,42 +606,43 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
   };
 
   for (int ni = 0; ni < (int)g.nodes.size(); ++ni) {
-    if (skip_[ni] || impl->tc_member[ni]) continue;
+    if (skip_[ni] || (impl->tc_member[ni] && impl->tc_conv_on.load(std::memory_order_relaxed))) continue;
     const Node& n = g.nodes[ni];
-    auto chain_it = impl->tc_chains.find(ni);
+    auto chain_it = impl->tc_conv_on.load(std::memory_order_relaxed) ? impl->tc_chains.find(ni) : impl->tc_chains.end();
     if (chain_it != impl->tc_chains.end()) {
-      // ---- Conv3x3(+ReLU)(+MaxPool) chain on the tensor cores (NHWC split-bf16) ----
+      int* ovf = impl->tc_ovf.as<int>();
+      // ---- Conv3x3(+ReLU)(+MaxPool) chain on the tensor cores (NHWC split-fp16) ----
       const TcChain& ch = chain_it->second;
       Value X = get(n.inputs[0]);
       OCRS_CHECK(!X.is_int && X.shape.size() == 4, kRunFailed, "Conv: expected 4-D input");
       int N_ = (int)X.shape[0], C_ = (int)X.shape[1], H_ = (int)X.shape[2], W_ = (int)X.shape[3];
       int ptok = prof ? prof->begin(prof_prefix + "ConvChain(total)", st) : -1;
       const double flops_before = flops;
-      auto alloc_bf16 = [&](int64_t elems) { return std::make_shared<Storage>((size_t)elems * 2, st); };
+      auto alloc_half = [&](int64_t elems) { return std::make_shared<Storage>((size_t)elems * 2, st); };
       std::shared_ptr<Storage> cur_hi, cur_lo;
       if (ch.stem) {
         OCRS_CHECK(C_ == 1, kRunFailed, "Conv: channel mismatch");
         int Co = ch.stem->Cout;
         flops += 2.0 * N_ * H_ * W_ * (double)Co * 9.0;
         int64_t oe = (int64_t)N_ * (H_ / 2) * (W_ / 2) * Co;
-        cur_hi = alloc_bf16(oe);
-        cur_lo = alloc_bf16(oe);
-        tc::stem_conv_relu_pool2(X.t.data, *ch.stem, (__nv_bfloat16*)cur_hi->ptr, (__nv_bfloat16*)cur_lo->ptr, N_, H_, W_, st);
+        cur_hi = alloc_half(oe);
+        cur_lo = alloc_half(oe);
+        tc::stem_conv_relu_pool2(X.t.data, *ch.stem, (tc::act_t*)cur_hi->ptr, (tc::act_t*)cur_lo->ptr, N_, H_, W_, ovf, st);
         H_ /= 2; W_ /= 2; C_ = Co;
       } else {
         int64_t elems = (int64_t)N_ * H_ * W_ * C_;
-        cur_hi = alloc_bf16(elems);
-        cur_lo = alloc_bf16(elems);
-        tc::nchw_to_nhwc_split(X.t.data, (__nv_bfloat16*)cur_hi->ptr, (__nv_bfloat16*)cur_lo->ptr, N_, C_, H_, W_, st);
+        cur_hi = alloc_half(elems);
+        cur_lo = alloc_half(elems);
+        tc::nchw_to_nhwc_split(X.t.data, (tc::act_t*)cur_hi->ptr, (tc::act_t*)cur_lo->ptr, N_, C_, H_, W_, ovf, st);
       }
       OCRS_CHECK(C_ == ch.units[0].w->Cin, kRunFailed, "Conv: channel mismatch");
       for (const TcUnit& u : ch.units) {
         int Co = u.w->Cout;
         int64_t oe = (int64_t)N_ * H_ * W_ * Co;
-        auto o_hi = alloc_bf16(oe), o_lo = alloc_bf16(oe);
+        auto o_hi = alloc_half(oe), o_lo = alloc_half(oe);
         int ktok = prof ? prof->begin(prof_prefix + "conv3x3_tc_kernel", st) : -1;
-        tc::conv3x3((const __nv_bfloat16*)cur_hi->ptr, (const __nv_bfloat16*)cur_lo->ptr, *u.w, (__nv_bfloat16*)o_hi->ptr,
-                    (__nv_bfloat16*)o_lo->ptr, N_, H_, W_, u.relu, st);
+        tc::conv3x3((const tc::act_t*)cur_hi->ptr, (const tc::act_t*)cur_lo->ptr, *u.w, (tc::act_t*)o_hi->ptr,
+                    (tc::act_t*)o_lo->ptr, N_, H_, W_, u.relu, ovf, st);
         const double cf = 2.0 * N_ * H_ * W_ * (double)Co * C_ * 9.0;
         if (prof) prof->end(ktok, st, cf, 4.0 * N_ * H_ * W_ * (double)(Co + C_));
         flops += cf;
@@ -644,14 +650,14 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
         if (u.pool_node >= 0) {
           int OH = H_ / u.ph, OW = W_ / u.pw;
           int64_t pe = (int64_t)N_ * OH * OW * C_;
-          auto p_hi = alloc_bf16(pe), p_lo = alloc_bf16(pe);
-          tc::maxpool_nhwc_split((const __nv_bfloat16*)cur_hi->ptr, (const __nv_bfloat16*)cur_lo->ptr,
-                                 (__nv_bfloat16*)p_hi->ptr, (__nv_bfloat16*)p_lo->ptr, N_, H_, W_, C_, u.ph, u.pw, st);
+          auto p_hi = alloc_half(pe), p_lo = alloc_half(pe);
+          tc::maxpool_nhwc_split((const tc::act_t*)cur_hi->ptr, (const tc::act_t*)cur_lo->ptr,
+                                 (tc::act_t*)p_hi->ptr, (tc::act_t*)p_lo->ptr, N_, H_, W_, C_, u.ph, u.pw, st);
           cur_hi = p_hi; cur_lo = p_lo; H_ = OH; W_ = OW;
         }
       }
       DTensor Y = alloc_tensor({N_, C_, H_, W_}, st);
-      tc::nhwc_split_to_nchw((const __nv_bfloat16*)cur_hi->ptr, (const __nv_bfloat16*)cur_lo->ptr, Y.data, N_, C_, H_, W_, st);
+      tc::nhwc_split_to_nchw((const tc::act_t*)cur_hi->ptr, (const tc::act_t*)cur_lo->ptr, Y.data, N_, C_, H_, W_, st);
       if (prof) prof->end(ptok, st, flops - flops_before);
       env[ch.out_name] = dev_value(Y);
       if (stop_at && *stop_at == ch.out_name) {
@@ -1166,6 +1172,17 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
 bool Model::has_seq_head() const { return impl_->head.present; }
 int Model::seq_head_channels() const { return impl_->head.C; }
 int Model::seq_head_classes() const { return impl_->head.classes; }
+
+bool Model::take_tc_overflow() const {
+  Impl* impl = impl_.get();
+  if (!impl->tc_enabled || !impl->tc_ovf.ptr || !impl->tc_conv_on.load()) return false;
+  int flag = 0;
+  OCRS_CUDA_CHECK(cudaMemcpy(&flag, impl->tc_ovf.ptr, 4, cudaMemcpyDeviceToHost));
+  if (!flag) return false;
+  impl->tc_conv_on.store(false);
+  OCRS_CUDA_CHECK(cudaMemset(impl->tc_ovf.ptr, 0, 4));
+  return true;
+}
 
 DTensor Model::run_prefix(const DTensor& input, cudaStream_t st, ModelCost* cost, Profiler* prof,
                           const std::string& prof_prefix) const {

@@ -80,6 +80,12 @@ class Model {
   DTensor run_seq_head(const float* X, int64_t rows, const std::vector<PackedGroup>& groups, cudaStream_t st,
                        ModelCost* cost = nullptr, Profiler* prof = nullptr, const std::string& prof_prefix = "") const;
 
+  // The tensor-core conv path carries activations as split fp16; a kernel that meets |x| > 65504
+  // raises a device flag.  Call after synchronising the stream(s) a run used: returns true when
+  // the flag was raised, in which case the tensor-core conv chains are switched off for this
+  // model (fp32 CUDA-core kernels from then on) and the caller must repeat the run.
+  bool take_tc_overflow() const;
+
   size_t weight_bytes() const { return weight_bytes_; }
   const onnx::Graph& graph() const { return graph_; }
 

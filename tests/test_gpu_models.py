@@ -69,3 +69,18 @@ def test_concurrent_runs_on_one_handle(models):
     [t.join() for t in ts]
     for i in range(4):
         assert np.abs(outs[i] - orec.run(xs[i])).max() < LOGIT_TOL
+
+
+def test_fp16_range_overflow_falls_back_to_fp32():
+    """The tensor-core convolutions carry activations as split fp16.  An input that drives an
+    activation past 65504 raises the device flag and the run is repeated on the fp32 kernels
+    (never a silent inf/NaN); the model then stays on the fp32 path."""
+    _, rec_path = model_paths()
+    rec, orec = ob.Model(rec_path), OnnxModel(rec_path)
+    rng = np.random.default_rng(0)
+    big = (rng.uniform(-0.5, 0.5, (2, 1, 64, 100)) * 4e5).astype(np.float32)
+    got, exp = rec.run(big), orec.run(big)
+    assert np.isfinite(got).all()
+    assert np.abs(got - exp).max() <= 2e-4 * np.abs(exp).max()
+    x = rng.uniform(-0.5, 0.5, (2, 1, 64, 100)).astype(np.float32)
+    assert np.abs(rec.run(x) - orec.run(x)).max() < 1e-4   # fp32 kernels from now on
