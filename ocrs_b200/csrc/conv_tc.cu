@@ -1,13 +1,15 @@
 // tcgen05 / TMEM / TMA implicit-GEMM 3x3 convolution (sm_100a).  See conv_tc.h.
 //
-// Tile: 128 output pixels (TH rows x TW columns of one image) x COUT channels per CTA.
+// Tile: 128 output pixels (8 rows x 16 columns of one image) x COUT channels; persistent CTAs
+// (one per SM) walk the tiles.
 // K loop: 9 taps x (Cin / KC) channel chunks; per k-block TMA loads
 //   A_hi, A_lo : [128 pixels][KC] fp16, box {KC, TW, TH, 1} of the NHWC activation at
 //                (c0, w0 + kw - 1, h0 + kh - 1, n) -- the halo / zero padding is TMA out-of-bounds fill
 //   B_hi, B_lo : [COUT][KC] fp16 from the [COUT][9*Cin] weight matrix
 // into 128B- (KC = 64) or 64B- (KC = 32) swizzled shared memory; one elected thread issues
-//   D += A_hi*B_hi ; D += A_hi*B_lo ; D += A_lo*B_hi        (tcgen05.mma kind::f16, fp32 accumulate in TMEM)
-// and the four warps drain TMEM (tcgen05.ld 32x32b), add bias, ReLU, split to fp16 hi/lo, store NHWC.
+//   HH += A_hi*B_hi ; X += A_hi*B_lo ; X += A_lo*B_hi       (tcgen05.mma kind::f16, fp32 accumulate in TMEM)
+// and four warps promote HH to registers every 128 K-elements, then add X, bias, ReLU, optional
+// max-pool, split to fp16 hi/lo and store NHWC (see the kernel comment for the numerics).
 #include "conv_tc.h"
 
 #include "tc_host.h"
@@ -15,7 +17,9 @@
 
 #include <cuda.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -56,41 +60,59 @@ struct Cfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = (kStageBytes * 4 + 2048 <= 200 * 1024) ? 4 : 3;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kGroupKb = 128 / KC;      // k-blocks per promotion group (128 K-elements)
+  static constexpr int kTmemCols = 4 * COUT;     // HH[2] | X[2]
 };
 
+constexpr int kTW = 16, kTH = 8;   // pixel tile: 8 rows x 16 columns = 128 TMEM lanes, lane = th*16 + tw
+constexpr int kConvThreads = 192;  // warps 0-3: promotion + epilogue, warp 4: TMA, warp 5: MMA
+
+// Numerics.  tcgen05.mma truncates its fp32 accumulator toward zero after every instruction
+// (measured: -0.5 ulp of the running sum per MMA, tools/diag_tc_rounding.py), so a K = 1152
+// dot product issued as 216 MMAs into one accumulator ends ~100 ulp low.  Therefore:
+//   * the cross terms (hi*lo + lo*hi, 2/3 of the MMAs, 2^-11 of the magnitude) get their own
+//     accumulator X, whose truncation is negligible in absolute terms;
+//   * the hi*hi partial sums are promoted to fp32 registers (round-to-nearest adds on the CUDA
+//     cores) every 128 K-elements, double-buffered in TMEM so the tensor pipe never waits.
+// The same warps then run the epilogue (bias, ReLU, optional 2x2 / 2x1 max-pool through warp
+// shuffles, split to fp16 hi/lo, NHWC store) while the MMA warp is already on the next tile.
 template <int KC, int COUT>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                  const float* __restrict__ bias, act_t* __restrict__ out_hi,
-                  act_t* __restrict__ out_lo, int N, int H, int W, int Cin, int TW, int TH, int relu, int* __restrict__ ovf) {
+                  const float* __restrict__ bias, act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, int N, int H,
+                  int W, int Cin, int relu, int ph, int pw, float promo_scale, int* __restrict__ ovf) {
   using C = Cfg<KC, COUT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + C::kStages * C::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::kStages);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 1);
+  const uint32_t aux = bar_base + 8u * (2 * C::kStages);
+  auto hh_full = [&](int b) { return aux + 8u * b; };
+  auto hh_empty = [&](int b) { return aux + 8u * (2 + b); };
+  auto x_full = [&](int b) { return aux + 8u * (4 + b); };
+  auto x_empty = [&](int b) { return aux + 8u * (6 + b); };
+  const uint32_t tmem_slot = aux + 8u * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
-  int t = blockIdx.x;
-  const int tw_i = t % tiles_w;
-  t /= tiles_w;
-  const int th_i = t % tiles_h;
-  const int n = t / tiles_h;
-  const int w0 = tw_i * TW, h0 = th_i * TH;
+  const int tiles_w = (W + kTW - 1) / kTW, tiles_h = (H + kTH - 1) / kTH;
+  const int n_tiles = N * tiles_h * tiles_w;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(hh_full(b), 1);
+      mbar_init(hh_empty(b), 4);
+      mbar_init(x_full(b), 1);
+      mbar_init(x_empty(b), 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, COUT);
+  if (warp == 4) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -99,84 +121,153 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
 
   const int chunks = Cin / KC;
   const int nkb = 9 * chunks;
+  const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
 
-  if (warp == 0 && lane == 0) {
-    // ---------------- TMA producer ----------------
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % C::kStages;
-      const uint32_t ph = (kb / C::kStages) & 1;
-      mbar_wait(empty_bar(s), ph ^ 1);
-      const uint32_t st = base + s * C::kStageBytes;
-      mbar_expect_tx(full_bar(s), C::kStageBytes);
-      const int tap = kb / chunks, c0 = (kb - tap * chunks) * KC;
-      const int kh = tap / 3, kw = tap - kh * 3;
-      tma_load_4d(st, &tm_x_hi, c0, w0 + kw - 1, h0 + kh - 1, n, full_bar(s));
-      tma_load_4d(st + C::kABytes, &tm_x_lo, c0, w0 + kw - 1, h0 + kh - 1, n, full_bar(s));
-      tma_load_2d(st + 2 * C::kABytes, &tm_w_hi, tap * Cin + c0, 0, full_bar(s));
-      tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tm_w_lo, tap * Cin + c0, 0, full_bar(s));
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer ----------------
-    // c_format F32 (bit 4), a/b format F16 (0 at bits 7, 10), N >> 3 at 17, M >> 4 at 24
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % C::kStages;
-      const uint32_t ph = (kb / C::kStages) & 1;
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      const uint32_t st = base + s * C::kStageBytes;
-      const uint32_t a_hi = st, a_lo = st + C::kABytes, b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
-#pragma unroll
-      for (int k = 0; k < KC / 16; ++k) {
-        const uint32_t koff = k * 32;  // 16 fp16 = 32 bytes along K inside the swizzle atom
-        const uint64_t da_hi = make_desc<KC>(a_hi + koff), da_lo = make_desc<KC>(a_lo + koff);
-        const uint64_t db_hi = make_desc<KC>(b_hi + koff), db_lo = make_desc<KC>(b_lo + koff);
-        umma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
-        umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
-        umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int w0 = (t % tiles_w) * kTW;
+        t /= tiles_w;
+        const int h0 = (t % tiles_h) * kTH;
+        const int n = t / tiles_h;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t par = (it / C::kStages) & 1;
+          mbar_wait(empty_bar(s), par ^ 1);
+          const uint32_t st = base + s * C::kStageBytes;
+          mbar_expect_tx(full_bar(s), C::kStageBytes);
+          const int tap = kb / chunks, c0 = (kb - tap * chunks) * KC;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d(st, &tm_x_hi, c0, w0 + kw - 1, h0 + kh - 1, n, full_bar(s));
+          tma_load_4d(st + C::kABytes, &tm_x_lo, c0, w0 + kw - 1, h0 + kh - 1, n, full_bar(s));
+          tma_load_2d(st + 2 * C::kABytes, &tm_w_hi, tap * Cin + c0, 0, full_bar(s));
+          tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tm_w_lo, tap * Cin + c0, 0, full_bar(s));
+        }
       }
-      umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
     }
-    umma_commit(tmem_full_bar);
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      // c_format F32 (bit 4), a/b format F16 (0 at bits 7, 10), N >> 3 at 17, M >> 4 at 24
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t it = 0, gc = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t tp = ti & 1;
+        const uint32_t d_x = tmem_base + 2 * COUT + tp * COUT;
+        mbar_wait(x_empty(tp), ((ti >> 1) & 1) ^ 1);
+        int kb = 0;
+        for (int g = 0; g < ngroups; ++g, ++gc) {
+          const uint32_t b = gc & 1;
+          const uint32_t d_hh = tmem_base + b * COUT;
+          mbar_wait(hh_empty(b), ((gc >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const int kb_end = min(kb + C::kGroupKb, nkb);
+          for (int kb0 = kb; kb < kb_end; ++kb, ++it) {
+            const int s = it % C::kStages;
+            const uint32_t par = (it / C::kStages) & 1;
+            mbar_wait(full_bar(s), par);
+            tc_fence_after();
+            const uint32_t st = base + s * C::kStageBytes;
+            const uint32_t a_hi = st, a_lo = st + C::kABytes, b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              const uint32_t koff = k * 32;  // 16 fp16 = 32 bytes along K inside the swizzle atom
+              const uint64_t da_hi = make_desc<KC>(a_hi + koff), da_lo = make_desc<KC>(a_lo + koff);
+              const uint64_t db_hi = make_desc<KC>(b_hi + koff), db_lo = make_desc<KC>(b_lo + koff);
+              umma_bf16(d_hh, da_hi, db_hi, idesc, (kb != kb0 || k) ? 1u : 0u);
+              umma_bf16(d_x, da_hi, db_lo, idesc, (kb | k) ? 1u : 0u);
+              umma_bf16(d_x, da_lo, db_hi, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+          }
+          umma_commit(hh_full(b));
+        }
+        umma_commit(x_full(tp));
+      }
+    }
+  } else {
+    // ---------------- promotion + epilogue: warps 0-3, TMEM lanes 32*warp .. +31 ----------------
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int th = warp * 2 + (lane >> 4), tw = lane & 15;
+    const int OH = H / ph, OW = W / pw;
+    uint32_t gc = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      int t = tile;
+      const int w0 = (t % tiles_w) * kTW;
+      t /= tiles_w;
+      const int h0 = (t % tiles_h) * kTH;
+      const int n = t / tiles_h;
+      float acc[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+      for (int g = 0; g < ngroups; ++g, ++gc) {
+        const uint32_t b = gc & 1;
+        mbar_wait(hh_full(b), (gc >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_base + b * COUT + (uint32_t)c0, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(__uint_as_float(r[j]), promo_scale, acc[c0 + j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hh_empty(b));
+      }
+      const uint32_t tp = ti & 1;
+      mbar_wait(x_full(tp), (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + 2 * COUT + tp * COUT + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_empty(tp));
+
+      const int h = h0 + th, w = w0 + tw;
+      const int oh = h / ph, ow = w / pw;
+      const bool writer = (ph == 1 || (lane & 16) == 0) && (pw == 1 || (lane & 1) == 0) && oh < OH && ow < OW;
+      const size_t opix = ((size_t)n * OH + oh) * OW + ow;
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 8) {
+        uint32_t hp[4], lp[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          float v0 = acc[c0 + j] + __ldg(bias + c0 + j);
+          float v1 = acc[c0 + j + 1] + __ldg(bias + c0 + j + 1);
+          if (relu) {
+            v0 = fmaxf(v0, 0.f);
+            v1 = fmaxf(v1, 0.f);
+          }
+          if (ph == 2) {
+            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 16));
+            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 16));
+          }
+          if (pw == 2) {
+            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
+            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
+          }
+          split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
+        }
+        if (writer) {
+          *reinterpret_cast<uint4*>(out_hi + opix * COUT + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(out_lo + opix * COUT + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        }
+      }
+    }
   }
   __syncwarp();
-
-  // ---------------- epilogue: all four warps ----------------
-  mbar_wait(tmem_full_bar, 0);
-  tc_fence_after();
-  const int p = warp * 32 + lane;  // TMEM lane == pixel index inside the tile
-  const int th = p / TW, tw = p - th * TW;
-  const int h = h0 + th, w = w0 + tw;
-  const bool valid = (th < TH) && (h < H) && (w < W);
-  const size_t pix = ((size_t)n * H + h) * W + w;
-#pragma unroll 1
-  for (int c0 = 0; c0 < COUT; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-    uint32_t hi_pack[16], lo_pack[16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float v0 = __uint_as_float(r[j]) + bias[c0 + j];
-      float v1 = __uint_as_float(r[j + 1]) + bias[c0 + j + 1];
-      if (relu) {
-        v0 = fmaxf(v0, 0.f);
-        v1 = fmaxf(v1, 0.f);
-      }
-      split2(v0, v1, hi_pack[j / 2], lo_pack[j / 2], ovf);
-    }
-    if (valid) {
-      uint4* dh = reinterpret_cast<uint4*>(out_hi + pix * COUT + c0);
-      uint4* dl = reinterpret_cast<uint4*>(out_lo + pix * COUT + c0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        dh[q] = make_uint4(hi_pack[4 * q], hi_pack[4 * q + 1], hi_pack[4 * q + 2], hi_pack[4 * q + 3]);
-        dl[q] = make_uint4(lo_pack[4 * q], lo_pack[4 * q + 1], lo_pack[4 * q + 2], lo_pack[4 * q + 3]);
-      }
-    }
-  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, COUT);
+  if (warp == 4) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -327,17 +418,38 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const fl
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  OCRS_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    OCRS_CUDA_CHECK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// Scale applied to every promoted hi*hi partial sum.  1 + kappa * 0.5 * 8 * 2^-23 would undo the
+// expected truncation of the 8 MMAs behind a partial (see the kernel comment); kappa = 0 (off)
+// unless OCRS_B200_TC_DEBIAS says otherwise.
+float promo_scale() {
+  static const float s = [] {
+    const char* e = std::getenv("OCRS_B200_TC_DEBIAS");
+    const double kappa = e ? std::atof(e) : 0.0;
+    return (float)(1.0 + kappa * 0.5 * 8.0 / 8388608.0);
+  }();
+  return s;
+}
+
 template <int KC, int COUT>
 void launch_conv(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, act_t* y_hi,
-                 act_t* y_lo, int N, int H, int W, int relu, int* ovf, cudaStream_t st) {
+                 act_t* y_lo, int N, int H, int W, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
   using C = Cfg<KC, COUT>;
   const int Cin = w.Cin;
-  int TW = W > 64 ? 128 : (W > 32 ? 64 : (W > 16 ? 32 : 16));
-  int TH = 128 / TW;
   const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-  uint32_t xb[4] = {(uint32_t)KC, (uint32_t)TW, (uint32_t)TH, 1};
+  uint32_t xb[4] = {(uint32_t)KC, (uint32_t)kTW, (uint32_t)kTH, 1};
   CUtensorMap tm_x_hi = make_map(x_hi, 4, xd, xs, xb, swz);
   CUtensorMap tm_x_lo = make_map(x_lo, 4, xd, xs, xb, swz);
   uint64_t wd[2] = {(uint64_t)9 * Cin, (uint64_t)COUT};
@@ -345,16 +457,13 @@ void launch_conv(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, a
   uint32_t wb[2] = {(uint32_t)KC, (uint32_t)COUT};
   CUtensorMap tm_w_hi = make_map(w.w_hi.ptr, 2, wd, ws, wb, swz);
   CUtensorMap tm_w_lo = make_map(w.w_lo.ptr, 2, wd, ws, wb, swz);
-  static bool attr_set = false;
-  if (!attr_set) {
-    OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes));
-    attr_set = true;
-  }
-  const int tiles = N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
-  conv3x3_tc_kernel<KC, COUT><<<tiles, 128, C::kSmemBytes, st>>>(tm_x_hi, tm_x_lo, tm_w_hi, tm_w_lo,
-                                                                   w.bias.as<float>(), y_hi, y_lo, N, H, W, Cin, TW, TH,
-                                                                   relu, ovf);
+  OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::kSmemBytes));  // per-device attribute, cheap to repeat
+  const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+  const int grid = std::min(tiles, sm_count());
+  conv3x3_tc_kernel<KC, COUT><<<grid, kConvThreads, C::kSmemBytes, st>>>(tm_x_hi, tm_x_lo, tm_w_hi, tm_w_lo,
+                                                                           w.bias.as<float>(), y_hi, y_lo, N, H, W, Cin,
+                                                                           relu, ph, pw, promo_scale(), ovf);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -439,13 +548,14 @@ std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, i
 }
 
 void conv3x3(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, act_t* y_hi,
-             act_t* y_lo, int N, int H, int W, int relu, int* ovf, cudaStream_t st) {
+             act_t* y_lo, int N, int H, int W, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
   if (N == 0 || H == 0 || W == 0) return;
+  OCRS_CHECK((ph == 1 || ph == 2) && (pw == 1 || pw == 2), kInternal, "conv3x3 (tensor core): fused pool must be 1 or 2");
   const bool k64 = (w.Cin % 64 == 0);
-  if (k64 && w.Cout == 128) launch_conv<64, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ovf, st);
-  else if (k64 && w.Cout == 64) launch_conv<64, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ovf, st);
-  else if (!k64 && w.Cout == 128) launch_conv<32, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ovf, st);
-  else if (!k64 && w.Cout == 64) launch_conv<32, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ovf, st);
+  if (k64 && w.Cout == 128) launch_conv<64, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ph, pw, ovf, st);
+  else if (k64 && w.Cout == 64) launch_conv<64, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ph, pw, ovf, st);
+  else if (!k64 && w.Cout == 128) launch_conv<32, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ph, pw, ovf, st);
+  else if (!k64 && w.Cout == 64) launch_conv<32, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ph, pw, ovf, st);
   else throw Error(kInternal, "conv3x3 (tensor core): unsupported channel configuration");
 }
 

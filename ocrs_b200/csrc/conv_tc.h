@@ -42,9 +42,10 @@ bool conv_supported(int Cin, int Cout, int R, int S, int stride_h, int stride_w,
 // Re-lays out ONNX weights [Cout][Cin][3][3] (+ bias, may be null) for the kernel.
 std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, int Cin, int Cout);
 
-// y = relu?(conv3x3(x) + bias); x, y: NHWC split fp16.  x: [N,H,W,Cin], y: [N,H,W,Cout].
+// y = maxpool_{ph x pw}(relu?(conv3x3(x) + bias)); x, y: NHWC split fp16.  x: [N,H,W,Cin],
+// y: [N,H/ph,W/pw,Cout]; ph, pw in {1, 2} (kernel == stride, no padding, floor).
 void conv3x3(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, act_t* y_hi,
-             act_t* y_lo, int N, int H, int W, int relu, int* ovf, cudaStream_t st);
+             act_t* y_lo, int N, int H, int W, int relu, int ph, int pw, int* ovf, cudaStream_t st);
 
 // First layer of the CRNN: conv3x3(1 -> Cout, stride 1, pad 1) + bias + ReLU + MaxPool(2,2), fused,
 // CUDA cores (K = 9 is not tensor-core work).  x: [N,1,H,W] f32; out: NHWC split fp16 [N,H/2,W/2,Cout].

@@ -638,16 +638,19 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
       OCRS_CHECK(C_ == ch.units[0].w->Cin, kRunFailed, "Conv: channel mismatch");
       for (const TcUnit& u : ch.units) {
         int Co = u.w->Cout;
-        int64_t oe = (int64_t)N_ * H_ * W_ * Co;
+        const bool has_pool = u.pool_node >= 0;
+        const bool fuse_pool = has_pool && (u.ph == 1 || u.ph == 2) && (u.pw == 1 || u.pw == 2);
+        const int fph = fuse_pool ? u.ph : 1, fpw = fuse_pool ? u.pw : 1;
+        int64_t oe = (int64_t)N_ * (H_ / fph) * (W_ / fpw) * Co;
         auto o_hi = alloc_half(oe), o_lo = alloc_half(oe);
         int ktok = prof ? prof->begin(prof_prefix + "conv3x3_tc_kernel", st) : -1;
         tc::conv3x3((const tc::act_t*)cur_hi->ptr, (const tc::act_t*)cur_lo->ptr, *u.w, (tc::act_t*)o_hi->ptr,
-                    (tc::act_t*)o_lo->ptr, N_, H_, W_, u.relu, ovf, st);
+                    (tc::act_t*)o_lo->ptr, N_, H_, W_, u.relu, fph, fpw, ovf, st);
         const double cf = 2.0 * N_ * H_ * W_ * (double)Co * C_ * 9.0;
-        if (prof) prof->end(ktok, st, cf, 4.0 * N_ * H_ * W_ * (double)(Co + C_));
+        if (prof) prof->end(ktok, st, cf, 4.0 * N_ * (H_ * W_ * (double)C_ + (H_ / fph) * (W_ / fpw) * (double)Co));
         flops += cf;
-        cur_hi = o_hi; cur_lo = o_lo; C_ = Co;
-        if (u.pool_node >= 0) {
+        cur_hi = o_hi; cur_lo = o_lo; C_ = Co; H_ /= fph; W_ /= fpw;
+        if (has_pool && !fuse_pool) {
           int OH = H_ / u.ph, OW = W_ / u.pw;
           int64_t pe = (int64_t)N_ * OH * OW * C_;
           auto p_hi = alloc_half(pe), p_lo = alloc_half(pe);
