@@ -314,6 +314,35 @@ __global__ void nhwc_split_to_nchw_kernel(const act_t* __restrict__ hi, const ac
   }
 }
 
+__global__ void nhwc_split_avg_to_seq_kernel(const act_t* __restrict__ hi, const act_t* __restrict__ lo,
+                                             float* __restrict__ y, int N, int C, int H, int W) {
+  // one thread per (n, w, 8-channel group): mean over h, written at [w][n][c]
+  const int groups = C / 8;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * W * groups) return;
+  const int g = (int)(idx % groups);
+  const int w = (int)((idx / groups) % W);
+  const int n = (int)(idx / ((int64_t)groups * W));
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int h = 0; h < H; ++h) {
+    const int64_t pix = ((int64_t)n * H + h) * W + w;
+    const uint4 vh = *reinterpret_cast<const uint4*>(hi + pix * C + g * 8);
+    const uint4 vl = *reinterpret_cast<const uint4*>(lo + pix * C + g * 8);
+    const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] += join_lo(hh[j], ll[j]);
+      acc[2 * j + 1] += join_hi(hh[j], ll[j]);
+    }
+  }
+  const float inv = (float)H;
+  float4* dst = reinterpret_cast<float4*>(y + ((int64_t)w * N + n) * C + g * 8);
+  dst[0] = make_float4(acc[0] / inv, acc[1] / inv, acc[2] / inv, acc[3] / inv);
+  dst[1] = make_float4(acc[4] / inv, acc[5] / inv, acc[6] / inv, acc[7] / inv);
+}
+
 __global__ void maxpool_nhwc_split_kernel(const act_t* __restrict__ x_hi, const act_t* __restrict__ x_lo,
                                           act_t* __restrict__ y_hi, act_t* __restrict__ y_lo, int N,
                                           int H, int W, int C, int ph, int pw) {
@@ -575,6 +604,15 @@ void nhwc_split_to_nchw(const act_t* hi, const act_t* lo, float* y, int N, int C
   int64_t HW = (int64_t)H * W, total_pix = (int64_t)N * HW, total = total_pix * (C / 8);
   if (!total) return;
   nhwc_split_to_nchw_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(hi, lo, y, C, HW, total_pix);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void nhwc_split_avg_to_seq(const act_t* hi, const act_t* lo, float* y, int N, int C, int H, int W, cudaStream_t st) {
+  OCRS_CHECK(C % 8 == 0, kInternal, "nhwc_split_avg_to_seq: C must be a multiple of 8");
+  int64_t total = (int64_t)N * W * (C / 8);
+  if (!total) return;
+  nhwc_split_avg_to_seq_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(hi, lo, y, N, C, H, W);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }

@@ -65,6 +65,9 @@ void nchw_to_nhwc_split(const float* x, act_t* hi, act_t* lo, int N, int C, int 
                         cudaStream_t st);
 void nhwc_split_to_nchw(const act_t* hi, const act_t* lo, float* y, int N, int C, int H, int W,
                         cudaStream_t st);
+// Tail of the CRNN's conv stack fused into one pass: AveragePool over the full height (H -> 1),
+// squeeze, and the [N,C,W] -> [W,N,C] transpose.  x: NHWC split fp16 [N,H,W,C]; y: f32 [W,N,C].
+void nhwc_split_avg_to_seq(const act_t* hi, const act_t* lo, float* y, int N, int C, int H, int W, cudaStream_t st);
 // max-pool with kernel == stride == (ph, pw), no padding; NHWC split in and out.
 void maxpool_nhwc_split(const act_t* x_hi, const act_t* x_lo, act_t* y_hi,
                         act_t* y_lo, int N, int H, int W, int C, int ph, int pw, cudaStream_t st);

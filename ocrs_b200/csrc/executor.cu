@@ -165,6 +165,9 @@ struct TcChain {
   std::unique_ptr<tc::StemWeights> stem;  // optional fused first layer: Conv(1->C)+ReLU+MaxPool(2,2)
   std::vector<TcUnit> units;
   std::string out_name;  // published name of the chain's result
+  // optional fused tail: AveragePool((kh,1)) -> Reshape([0,C,-1]) -> Transpose(2,0,1), applied when
+  // the chain's output height equals kh at run time
+  struct Tail { int avg_node = -1, reshape_node = -1, transpose_node = -1, kh = 0; std::string out_name; } tail;
 };
 
 struct Model::Impl {
@@ -440,6 +443,35 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
         }
         break;
       }
+      {  // fused tail (see TcChain::Tail)
+        const int an = sole_consumer(chain.out_name);
+        if (an >= 0 && !m->skip_[an] && g.nodes[an].op == "AveragePool" && g.nodes[an].inputs[0] == chain.out_name &&
+            g.nodes[an].attr_s("auto_pad", "NOTSET") == "NOTSET" && g.nodes[an].attr_i("ceil_mode", 0) == 0) {
+          const Node& a = g.nodes[an];
+          auto ks = a.attr_ints("kernel_shape", {});
+          auto ps = a.attr_ints("pads", {0, 0, 0, 0});
+          auto ss = a.attr_ints("strides", {1, 1});
+          const bool a_ok = ks.size() == 2 && ks[1] == 1 && ks[0] >= 1 && ss.size() == 2 && ss[1] == 1 &&
+                            ps == std::vector<int64_t>{0, 0, 0, 0};
+          const int rn = a_ok ? sole_consumer(a.outputs[0]) : -1;
+          if (rn >= 0 && !m->skip_[rn] && g.nodes[rn].op == "Reshape" && g.nodes[rn].inputs.size() == 2 &&
+              g.nodes[rn].inputs[0] == a.outputs[0] && g.initializers.count(g.nodes[rn].inputs[1])) {
+            const auto shp = g.initializers.at(g.nodes[rn].inputs[1]).as_int64();
+            const int64_t cout = g.initializers.at(g.nodes[chain.units.back().conv_node].inputs[1]).dims[0];
+            const bool r_ok = shp.size() == 3 && shp[0] == 0 && (shp[1] == cout || shp[1] == 0) && shp[2] == -1 &&
+                              g.nodes[rn].attr_i("allowzero", 0) == 0;
+            const int tn = r_ok ? sole_consumer(g.nodes[rn].outputs[0]) : -1;
+            if (tn >= 0 && !m->skip_[tn] && g.nodes[tn].op == "Transpose" && g.nodes[tn].inputs[0] == g.nodes[rn].outputs[0] &&
+                g.nodes[tn].attr_ints("perm", {}) == std::vector<int64_t>{2, 0, 1}) {
+              chain.tail.avg_node = an;
+              chain.tail.reshape_node = rn;
+              chain.tail.transpose_node = tn;
+              chain.tail.kh = (int)ks[0];
+              chain.tail.out_name = published(tn);
+            }
+          }
+        }
+      }
       for (int sn : stem_nodes) impl->tc_member[sn] = 1;
       for (size_t k = 0; k < chain.units.size(); ++k) {
         if (k > 0) impl->tc_member[chain.units[k].conv_node] = 1;
@@ -605,8 +637,9 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
     return int_value(td.as_int64(), td.dims);
   };
 
+  std::vector<char> dyn_skip(g.nodes.size(), 0);  // nodes absorbed by a run-time fusion of this run
   for (int ni = 0; ni < (int)g.nodes.size(); ++ni) {
-    if (skip_[ni] || (impl->tc_member[ni] && impl->tc_conv_on.load(std::memory_order_relaxed))) continue;
+    if (skip_[ni] || dyn_skip[ni] || (impl->tc_member[ni] && impl->tc_conv_on.load(std::memory_order_relaxed))) continue;
     const Node& n = g.nodes[ni];
     auto chain_it = impl->tc_conv_on.load(std::memory_order_relaxed) ? impl->tc_chains.find(ni) : impl->tc_chains.end();
     if (chain_it != impl->tc_chains.end()) {
@@ -658,6 +691,23 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
                                  (tc::act_t*)p_hi->ptr, (tc::act_t*)p_lo->ptr, N_, H_, W_, C_, u.ph, u.pw, st);
           cur_hi = p_hi; cur_lo = p_lo; H_ = OH; W_ = OW;
         }
+      }
+      if (ch.tail.avg_node >= 0 && ch.tail.kh == H_) {
+        // conv stack -> feature sequence in one pass: mean over the height, [W, N, C]
+        DTensor S = alloc_tensor({W_, N_, C_}, st);
+        int ttok = prof ? prof->begin(prof_prefix + "AvgPool+Transpose(fused)", st) : -1;
+        tc::nhwc_split_avg_to_seq((const tc::act_t*)cur_hi->ptr, (const tc::act_t*)cur_lo->ptr, S.data, N_, C_, H_, W_, st);
+        if (prof) prof->end(ttok, st, 0, 4.0 * N_ * W_ * (double)C_ * (H_ + 1));
+        if (prof) prof->end(ptok, st, flops - flops_before);
+        dyn_skip[ch.tail.avg_node] = dyn_skip[ch.tail.reshape_node] = dyn_skip[ch.tail.transpose_node] = 1;
+        env[ch.tail.out_name] = dev_value(S);
+        if (stop_at && *stop_at == ch.tail.out_name) {
+          if (cost) { cost->flops = flops; cost->min_bytes = 0; }
+          return S;
+        }
+        auto it0 = remaining.find(n.inputs[0]);
+        if (it0 != remaining.end() && --it0->second <= 0) env.erase(n.inputs[0]);
+        continue;
       }
       DTensor Y = alloc_tensor({N_, C_, H_, W_}, st);
       tc::nhwc_split_to_nchw((const tc::act_t*)cur_hi->ptr, (const tc::act_t*)cur_lo->ptr, Y.data, N_, C_, H_, W_, st);
