@@ -144,6 +144,21 @@ int ocrs_b200_engine_find_text_lines(ocrs_b200_engine* e, const ocrs_b200_input*
 /* Same computation without an engine handle (pure host code; usable without a GPU). */
 int ocrs_b200_find_text_lines(const ocrs_b200_rotated_rect* words, size_t n_words, ocrs_b200_rotated_rect** out_words,
                               size_t** line_offsets, size_t* n_lines);
+/* ---- text items (ocrs/src/text_items.rs) and CLI output formats (ocrs-cli/src/output.rs) -------
+ * Pure host code, usable without a GPU.
+ * `TextItem::rotated_rect` (text_items.rs:18-30): min-area rect of all corners of the items'
+ * character rects, oriented towards "up" = (x 0, y -1).  rects: n >= 1 character boxes. */
+int ocrs_b200_text_item_rotated_rect(const ocrs_b200_rect* char_rects, size_t n, ocrs_b200_rotated_rect* out);
+/* `RotatedRect::corners` rounded like `rounded_vertex_coords` (output.rs:24-27): xy[2*i], xy[2*i+1]
+ * = round-half-away(x), round-half-away(y) of corner i. */
+int ocrs_b200_rotated_rect_vertices(const ocrs_b200_rotated_rect* r, int32_t xy[8]);
+/* `format_text_output` (output.rs:87-94) and `format_json_output` (output.rs:97-100, HierText-style
+ * document of output.rs:34-76) of one page's recognition result.  *utf8 is malloc'ed, NUL terminated.
+ * The JSON is pretty-printed with 2-space indentation like serde_json::to_string_pretty. */
+int ocrs_b200_format_text_output(const ocrs_b200_text_result* lines, char** utf8);
+int ocrs_b200_format_json_output(const ocrs_b200_text_result* lines, const char* input_path, int image_height,
+                                 int image_width, char** utf8);
+
 int ocrs_b200_engine_recognize_text(ocrs_b200_engine* e, const ocrs_b200_input* in,
                                     const ocrs_b200_rotated_rect* words, const size_t* line_offsets, size_t n_lines,
                                     ocrs_b200_text_result** out);

@@ -90,6 +90,10 @@ SIGNATURES = {
     "ocrs_b200_engine_recognize_text": (C.c_int, [C.c_void_p, C.c_void_p, P(RotatedRectC), P(C.c_size_t), C.c_size_t,
                                                   P(P(TextResultC))]),
     "ocrs_b200_text_result_free": (None, [P(TextResultC)]),
+    "ocrs_b200_text_item_rotated_rect": (C.c_int, [P(RectC), C.c_size_t, P(RotatedRectC)]),
+    "ocrs_b200_rotated_rect_vertices": (C.c_int, [P(RotatedRectC), P(C.c_int32)]),
+    "ocrs_b200_format_text_output": (C.c_int, [P(TextResultC), P(C.c_void_p)]),
+    "ocrs_b200_format_json_output": (C.c_int, [P(TextResultC), C.c_char_p, C.c_int, C.c_int, P(C.c_void_p)]),
     "ocrs_b200_engine_prepare_recognition_input": (C.c_int, [C.c_void_p, C.c_void_p, P(RotatedRectC), C.c_size_t,
                                                              P(P(C.c_float)), P(C.c_int), P(C.c_int)]),
     "ocrs_b200_engine_detection_threshold": (C.c_float, [C.c_void_p]),

@@ -10,6 +10,7 @@
 #include "engine.h"
 #include "executor.h"
 #include "layout.h"
+#include "text_output.h"
 
 using namespace ocrs;
 
@@ -381,6 +382,63 @@ int ocrs_b200_engine_find_text_lines(ocrs_b200_engine* e, const ocrs_b200_input*
     return OCRS_B200_ERR_INVALID_ARG;
   }
   return ocrs_b200_find_text_lines(words, n_words, out_words, line_offsets, n_lines);
+}
+
+namespace {
+std::vector<TextLine> from_text_result(const ocrs_b200_text_result* r) {
+  OCRS_CHECK(r && r->n_lines >= 0 && (r->n_lines == 0 || (r->line_present && r->char_offsets)), kInvalidArg, "null argument");
+  std::vector<TextLine> lines((size_t)r->n_lines);
+  for (int32_t i = 0; i < r->n_lines; ++i) {
+    lines[i].present = r->line_present[i] != 0;
+    if (!lines[i].present) continue;
+    OCRS_CHECK(r->char_offsets[i + 1] > r->char_offsets[i], kInvalidArg, "Text lines must not be empty");  // text_items.rs:71
+    for (int64_t k = r->char_offsets[i]; k < r->char_offsets[i + 1]; ++k) {
+      const ocrs_b200_rect& cr = r->char_rects[k];
+      lines[i].chars.push_back(TextChar{r->chars[k], geom::RectI{cr.top, cr.left, cr.bottom, cr.right}});
+    }
+  }
+  return lines;
+}
+char* dup_string(const std::string& s) {
+  char* out = cmalloc<char>(s.size() + 1);
+  std::memcpy(out, s.data(), s.size());
+  out[s.size()] = 0;
+  return out;
+}
+}  // namespace
+
+int ocrs_b200_text_item_rotated_rect(const ocrs_b200_rect* char_rects, size_t n, ocrs_b200_rotated_rect* out) {
+  return guard([&] {
+    OCRS_CHECK(char_rects && out && n > 0, kInvalidArg, "null argument or empty item");
+    std::vector<geom::RectI> rects(n);
+    for (size_t i = 0; i < n; ++i) rects[i] = geom::RectI{char_rects[i].top, char_rects[i].left, char_rects[i].bottom, char_rects[i].right};
+    geom::RotatedRect rr = textout::item_rotated_rect(rects.data(), n);
+    std::memcpy(out, &rr, sizeof rr);
+  });
+}
+
+int ocrs_b200_rotated_rect_vertices(const ocrs_b200_rotated_rect* r, int32_t xy[8]) {
+  return guard([&] {
+    OCRS_CHECK(r && xy, kInvalidArg, "null argument");
+    geom::RotatedRect rr;
+    std::memcpy(&rr, r, sizeof rr);
+    textout::rounded_vertices(rr, xy);
+  });
+}
+
+int ocrs_b200_format_text_output(const ocrs_b200_text_result* lines, char** utf8) {
+  return guard([&] {
+    OCRS_CHECK(utf8, kInvalidArg, "null argument");
+    *utf8 = dup_string(textout::format_text(from_text_result(lines)));
+  });
+}
+
+int ocrs_b200_format_json_output(const ocrs_b200_text_result* lines, const char* input_path, int image_height,
+                                 int image_width, char** utf8) {
+  return guard([&] {
+    OCRS_CHECK(utf8 && input_path, kInvalidArg, "null argument");
+    *utf8 = dup_string(textout::format_json(from_text_result(lines), input_path, image_height, image_width));
+  });
 }
 
 int ocrs_b200_engine_recognize_text(ocrs_b200_engine* e, const ocrs_b200_input* in,

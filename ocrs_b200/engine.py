@@ -85,6 +85,13 @@ class RotatedRect:
     def raw(self):
         return (self.cx, self.cy, self.ux, self.uy, self.w, self.h)
 
+    def rounded_vertices(self) -> List[List[int]]:
+        """`rounded_vertex_coords` (ocrs-cli/src/output.rs:24-27): the four corners as [x, y]."""
+        xy = (C.c_int32 * 8)()
+        rr = RotatedRectC(*self.raw())
+        check(lib.ocrs_b200_rotated_rect_vertices(C.byref(rr), xy))
+        return [[xy[2 * i], xy[2 * i + 1]] for i in range(4)]
+
 
 @dataclass
 class Rect:
@@ -104,27 +111,115 @@ class TextChar:
     rect: Rect
 
 
-@dataclass
-class TextLine:
-    """text_items.rs:59-66"""
+def _rects_c(chars: Sequence["TextChar"]):
+    arr = (RectC * max(len(chars), 1))()
+    for i, c in enumerate(chars):
+        arr[i] = RectC(c.rect.top, c.rect.left, c.rect.bottom, c.rect.right)
+    return arr
+
+
+class TextItem:
+    """`trait TextItem` (text_items.rs:8-31): a non-empty run of recognised characters."""
     chars: List[TextChar]
 
     def __str__(self) -> str:
         return "".join(c.char for c in self.chars)
 
-    def words(self) -> List[List[TextChar]]:
-        """text_items.rs:76-82"""
+    def bounding_rect(self) -> Rect:
+        """text_items.rs:13-15"""
+        return Rect(min(c.rect.top for c in self.chars), min(c.rect.left for c in self.chars),
+                    max(c.rect.bottom for c in self.chars), max(c.rect.right for c in self.chars))
+
+    def rotated_rect(self) -> RotatedRect:
+        """text_items.rs:18-30: min-area rect of all character corners, oriented upright."""
+        out = RotatedRectC()
+        check(lib.ocrs_b200_text_item_rotated_rect(_rects_c(self.chars), len(self.chars), C.byref(out)))
+        return RotatedRect(out.cx, out.cy, out.ux, out.uy, out.w, out.h)
+
+
+@dataclass
+class TextWord(TextItem):
+    """text_items.rs:92-101"""
+    chars: List[TextChar]
+
+    def __post_init__(self):
+        assert self.chars, "Text words must not be empty"
+
+    __str__ = TextItem.__str__
+
+
+@dataclass
+class TextLine(TextItem):
+    """text_items.rs:59-82"""
+    chars: List[TextChar]
+
+    def __post_init__(self):
+        assert self.chars, "Text lines must not be empty"
+
+    __str__ = TextItem.__str__
+
+    def words(self) -> List[TextWord]:
+        """text_items.rs:76-82: split on ' ', empty pieces dropped."""
         out, cur = [], []
         for c in self.chars:
             if c.char == " ":
                 if cur:
-                    out.append(cur)
+                    out.append(TextWord(cur))
                 cur = []
             else:
                 cur.append(c)
         if cur:
-            out.append(cur)
+            out.append(TextWord(cur))
         return out
+
+
+def _to_text_result(lines: Sequence[Optional[TextLine]]):
+    """Flattens `[Option<TextLine>]` into the C ABI's ocrs_b200_text_result (arrays kept alive by the tuple)."""
+    n = len(lines)
+    total = sum(len(l.chars) for l in lines if l is not None)
+    present = (C.c_uint8 * max(n, 1))()
+    offs = (C.c_int64 * (n + 1))()
+    chars = (C.c_uint32 * max(total, 1))()
+    rects = (RectC * max(total, 1))()
+    k = 0
+    for i, l in enumerate(lines):
+        offs[i] = k
+        present[i] = 0 if l is None else 1
+        if l is None:
+            continue
+        for c in l.chars:
+            chars[k] = ord(c.char)
+            rects[k] = RectC(c.rect.top, c.rect.left, c.rect.bottom, c.rect.right)
+            k += 1
+    offs[n] = k
+    res = TextResultC(n, C.cast(present, C.POINTER(C.c_uint8)), C.cast(offs, C.POINTER(C.c_int64)),
+                      C.cast(chars, C.POINTER(C.c_uint32)), C.cast(rects, C.POINTER(RectC)))
+    return res, (present, offs, chars, rects)
+
+
+def _take_string(ptr: C.c_void_p) -> str:
+    try:
+        return C.string_at(ptr).decode("utf-8")
+    finally:
+        lib.ocrs_b200_free(ptr)
+
+
+def format_text_output(text_lines: Sequence[Optional[TextLine]]) -> str:
+    """`format_text_output` (ocrs-cli/src/output.rs:87-94): recognised lines joined with '\n'."""
+    res, keep = _to_text_result(text_lines)
+    out = C.c_void_p()
+    check(lib.ocrs_b200_format_text_output(C.byref(res), C.byref(out)))
+    return _take_string(out)
+
+
+def format_json_output(input_path: str, input_hw: Sequence[int], text_lines: Sequence[Optional[TextLine]]) -> str:
+    """`format_json_output` (ocrs-cli/src/output.rs:97-100): HierText-style JSON document with one
+    paragraph holding every line, words split on spaces, vertices = rounded rotated-rect corners."""
+    res, keep = _to_text_result(text_lines)
+    out = C.c_void_p()
+    check(lib.ocrs_b200_format_json_output(C.byref(res), input_path.encode("utf-8"), int(input_hw[0]), int(input_hw[1]),
+                                           C.byref(out)))
+    return _take_string(out)
 
 
 @dataclass
