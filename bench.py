@@ -152,6 +152,17 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def measured_traffic(kernel: str):
+    """DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01b_conv_traffic.json")
+    try:
+        with open(path) as fp:
+            d = json.load(fp)
+        return d if d.get("kernel") == kernel else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def make_batch(rank: int):
     from tools.synth import make_page
     return [np.ascontiguousarray(make_page(200 + rank * BATCH + i, PAGE_H, PAGE_W)[0]) for i in range(BATCH)]
@@ -374,7 +385,14 @@ def run_gpu(args):
                         "launches_per_step": dom["launches"] / max(1, min(3, args.steps)),
                         "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
                         "note": "achieved = fp32-equivalent conv/GEMM FLOPs (2*MACs) per launch / CUDA-event time; the "
-                                "kernel issues 3 bf16 MMAs per product term (split-bf16), so its own ceiling is peak/3"}
+                                "kernel issues 3 fp16 MMAs per product term (split operands), so its own ceiling is "
+                                "peak/3; ncu shows it limited by L2->shared-memory operand traffic (~39 B/clk/SM), "
+                                "tensor pipe 51% active (profiles/r01b_ncu_summary.md)"}
+            tr = measured_traffic(dom_name)
+            if tr is not None:
+                roofline["traffic"] = tr["dram_bytes_per_algorithmic_byte"] * roofline["algorithmic_bytes_per_launch"]
+                roofline["traffic_source"] = ("DRAM bytes (read+write) per algorithmic byte = %.3f from " % tr["dram_bytes_per_algorithmic_byte"]
+                                              + tr["source"] + ", applied to this run's algorithmic bytes per launch")
         else:
             achieved = dom["bytes"] / dom["launches"] / sec_per_launch / 1e9
             roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
