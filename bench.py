@@ -333,11 +333,13 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.prepare()  # attach the NVML client before the warm-up, not inside the timed region
+    # warm-up runs the whole step, including the gather (the first NCCL collective builds the
+    # communicator, ~100 ms, and must not land in the timed region)
     for e in engines:
         for _ in range(args.warmup):
-            step_resident(e)
+            gather_text(step_resident(e))
         for _ in range(max(1, args.warmup // 2)):
-            step_e2e(e)
+            gather_text(step_e2e(e))
 
     if rank == 0:
         sampler.start()
