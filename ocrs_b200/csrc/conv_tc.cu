@@ -67,6 +67,97 @@ struct Cfg {
 constexpr int kTW = 16, kTH = 8;   // pixel tile: 8 rows x 16 columns = 128 TMEM lanes, lane = th*16 + tw
 constexpr int kConvThreads = 192;  // warps 0-3: promotion + epilogue, warp 4: TMA, warp 5: MMA
 
+// Promotion + epilogue role of warps 0-3 (TMEM lanes 32*warp .. +31), shared by both conv kernels.
+// Tile = 128 pixels, TWD columns wide (lane = th*TWD + tw); `aux` holds the barriers
+// hh_full[2] | hh_empty[2] | x_full[2] | x_empty[2].  Per tile: add every promoted hi*hi partial
+// (TMEM -> registers, fp32 round-to-nearest), add the cross-term accumulator, then bias, ReLU,
+// optional 2x2 / 2x1 / 1x2 max-pool through warp shuffles, fp16 split, NHWC store.
+template <int COUT, int TWD>
+__device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, int warp, int lane, int n_tiles,
+                                              int tiles_w, int tiles_h, int TH, int ngroups, int H, int W, int relu,
+                                              int ph, int pw, float promo_scale, const float* __restrict__ bias,
+                                              act_t* __restrict__ out_hi, act_t* __restrict__ out_lo,
+                                              int* __restrict__ ovf) {
+  auto hh_full = [&](int b) { return aux + 8u * b; };
+  auto hh_empty = [&](int b) { return aux + 8u * (2 + b); };
+  auto x_full = [&](int b) { return aux + 8u * (4 + b); };
+  auto x_empty = [&](int b) { return aux + 8u * (6 + b); };
+  constexpr int kRowsPerWarp = 32 / TWD;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int th = warp * kRowsPerWarp + lane / TWD, tw = lane % TWD;
+  const int OH = H / ph, OW = W / pw;
+  uint32_t gc = 0, ti = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+    int t = tile;
+    const int w0 = (t % tiles_w) * TWD;
+    t /= tiles_w;
+    const int h0 = (t % tiles_h) * TH;
+    const int n = t / tiles_h;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int g = 0; g < ngroups; ++g, ++gc) {
+      const uint32_t b = gc & 1;
+      mbar_wait(hh_full(b), (gc >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + b * COUT + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(__uint_as_float(r[j]), promo_scale, acc[c0 + j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(hh_empty(b));
+    }
+    const uint32_t tp = ti & 1;
+    mbar_wait(x_full(tp), (ti >> 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + lane_base + 2 * COUT + tp * COUT + (uint32_t)c0, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(x_empty(tp));
+
+    const int h = h0 + th, w = w0 + tw;
+    const int oh = h / ph, ow = w / pw;
+    const bool writer = (ph == 1 || (lane & TWD) == 0) && (pw == 1 || (lane & 1) == 0) && oh < OH && ow < OW;
+    const size_t opix = ((size_t)n * OH + oh) * OW + ow;
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 8) {
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float v0 = acc[c0 + j] + __ldg(bias + c0 + j);
+        float v1 = acc[c0 + j + 1] + __ldg(bias + c0 + j + 1);
+        if (relu) {
+          v0 = fmaxf(v0, 0.f);
+          v1 = fmaxf(v1, 0.f);
+        }
+        if (ph == 2) {
+          v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, TWD));
+          v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, TWD));
+        }
+        if (pw == 2) {
+          v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
+          v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
+        }
+        split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
+      }
+      if (writer) {
+        *reinterpret_cast<uint4*>(out_hi + opix * COUT + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(out_lo + opix * COUT + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+      }
+    }
+  }
+}
+
 // Numerics.  tcgen05.mma truncates its fp32 accumulator toward zero after every instruction
 // (measured: -0.5 ulp of the running sum per MMA, tools/diag_tc_rounding.py), so a K = 1152
 // dot product issued as 216 MMAs into one accumulator ends ~100 ulp low.  Therefore:
@@ -189,80 +280,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       }
     }
   } else {
-    // ---------------- promotion + epilogue: warps 0-3, TMEM lanes 32*warp .. +31 ----------------
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int th = warp * 2 + (lane >> 4), tw = lane & 15;
-    const int OH = H / ph, OW = W / pw;
-    uint32_t gc = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      int t = tile;
-      const int w0 = (t % tiles_w) * kTW;
-      t /= tiles_w;
-      const int h0 = (t % tiles_h) * kTH;
-      const int n = t / tiles_h;
-      float acc[COUT];
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
-      for (int g = 0; g < ngroups; ++g, ++gc) {
-        const uint32_t b = gc & 1;
-        mbar_wait(hh_full(b), (gc >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_base + b * COUT + (uint32_t)c0, r);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(__uint_as_float(r[j]), promo_scale, acc[c0 + j]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(hh_empty(b));
-      }
-      const uint32_t tp = ti & 1;
-      mbar_wait(x_full(tp), (ti >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_base + 2 * COUT + tp * COUT + (uint32_t)c0, r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(x_empty(tp));
-
-      const int h = h0 + th, w = w0 + tw;
-      const int oh = h / ph, ow = w / pw;
-      const bool writer = (ph == 1 || (lane & 16) == 0) && (pw == 1 || (lane & 1) == 0) && oh < OH && ow < OW;
-      const size_t opix = ((size_t)n * OH + oh) * OW + ow;
-#pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 8) {
-        uint32_t hp[4], lp[4];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          float v0 = acc[c0 + j] + __ldg(bias + c0 + j);
-          float v1 = acc[c0 + j + 1] + __ldg(bias + c0 + j + 1);
-          if (relu) {
-            v0 = fmaxf(v0, 0.f);
-            v1 = fmaxf(v1, 0.f);
-          }
-          if (ph == 2) {
-            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 16));
-            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 16));
-          }
-          if (pw == 2) {
-            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
-            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
-          }
-          split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
-        }
-        if (writer) {
-          *reinterpret_cast<uint4*>(out_hi + opix * COUT + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(out_lo + opix * COUT + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-        }
-      }
-    }
+    epilogue_role<COUT, kTW>(tmem_base, aux, warp, lane, n_tiles, tiles_w, tiles_h, kTH, ngroups, H, W, relu, ph, pw,
+                             promo_scale, bias, out_hi, out_lo, ovf);
   }
   __syncwarp();
   tc_fence_before();

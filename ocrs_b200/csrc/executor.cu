@@ -676,7 +676,11 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
         const int fph = fuse_pool ? u.ph : 1, fpw = fuse_pool ? u.pw : 1;
         int64_t oe = (int64_t)N_ * (H_ / fph) * (W_ / fpw) * Co;
         auto o_hi = alloc_half(oe), o_lo = alloc_half(oe);
-        int ktok = prof ? prof->begin(prof_prefix + "conv3x3_tc_kernel", st) : -1;
+        static const bool prof_layers = std::getenv("OCRS_B200_PROF_LAYERS") != nullptr;  // per-layer op names (diagnostics)
+        int ktok = prof ? prof->begin(prof_prefix + "conv3x3_tc_kernel" +
+                                          (prof_layers ? "/" + std::to_string(C_) + "->" + std::to_string(Co) + "@" + std::to_string(H_) : std::string()),
+                                      st)
+                        : -1;
         tc::conv3x3((const tc::act_t*)cur_hi->ptr, (const tc::act_t*)cur_lo->ptr, *u.w, (tc::act_t*)o_hi->ptr,
                     (tc::act_t*)o_lo->ptr, N_, H_, W_, u.relu, fph, fpw, ovf, st);
         const double cf = 2.0 * N_ * H_ * W_ * (double)Co * C_ * 9.0;
