@@ -142,203 +142,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent recurrent kernel.  H = 256.  CTA = (tile of NL lines, direction).
-//   D[gate row (6 tiles x 128 lanes)][line] = R[768 x 256] * h_{t-1}^T[256 x NL]
-// TMEM column of (tile, line) = tile * NL + line, tile = gate * 2 + unit / 128, lane = unit % 128,
-// so one thread finds z, r, n of its unit in the same lane of three column blocks.
-// ------------------------------------------------------------------------------------------
-constexpr int NL = 32;
-constexpr int kRecStages = 4;
-constexpr int kRTile = 128 * 64 * 2;                 // one plane of one R stage (16 KB)
-constexpr int kRecStageBytes = 2 * kRTile;
-constexpr int kHSub = NL * 128;                      // one 64-wide K sub-tile of h (bytes)
-constexpr int kHPlane = 4 * kHSub;                   // h plane (hi or lo): [NL][256] bf16
-constexpr int kRecSmem = kRecStages * kRecStageBytes + 2 * kHPlane + 1024 + 256;
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
-__global__ void __launch_bounds__(192, 1)
-gru_rec_tc_kernel(const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
-                  const float* __restrict__ xw, const float* __restrict__ rb, const float* __restrict__ h0,
-                  float* __restrict__ Y, float* __restrict__ Yh, int T, int N, int D, int rev0, int rev1) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t h_hi = base + kRecStages * kRecStageBytes;
-  const uint32_t h_lo = h_hi + kHPlane;
-  const uint32_t bar_base = h_lo + kHPlane;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kRecStages + s); };
-  const uint32_t d_full_bar = bar_base + 8u * (2 * kRecStages);
-  const uint32_t h_ready_bar = d_full_bar + 8u;
-  const uint32_t tmem_slot = h_ready_bar + 8u;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = blockIdx.y;
-  const int line0 = blockIdx.x * NL;
-  const int rev = d == 0 ? rev0 : rev1;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kRecStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    mbar_init(d_full_bar, 1);
-    mbar_init(h_ready_bar, 128);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 4) {
-    // ---------------- TMA producer: streams R (24 stages per step) ----------------
-    if (lane == 0) {
-      int it = 0;
-      for (int step = 0; step < T; ++step) {
-        for (int tile = 0; tile < 6; ++tile) {
-          for (int kk = 0; kk < 4; ++kk, ++it) {
-            const int s = it % kRecStages;
-            const uint32_t ph = (it / kRecStages) & 1;
-            mbar_wait(empty_bar(s), ph ^ 1);
-            const uint32_t st = base + s * kRecStageBytes;
-            mbar_expect_tx(full_bar(s), kRecStageBytes);
-            tma_load_2d(st, &tm_r_hi, kk * 64, d * 768 + tile * 128, full_bar(s));
-            tma_load_2d(st + kRTile, &tm_r_lo, kk * 64, d * 768 + tile * 128, full_bar(s));
-          }
-        }
-      }
-    }
-  } else if (warp == 5) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NL >> 3) << 17) | ((128u >> 4) << 24);
-      int it = 0;
-      for (int step = 0; step < T; ++step) {
-        mbar_wait(h_ready_bar, step & 1);
-        tc_fence_after();
-        for (int tile = 0; tile < 6; ++tile) {
-          const uint32_t dcol = tmem_base + (uint32_t)(tile * NL);
-          for (int kk = 0; kk < 4; ++kk, ++it) {
-            const int s = it % kRecStages;
-            const uint32_t ph = (it / kRecStages) & 1;
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const uint32_t st = base + s * kRecStageBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t koff = k * 32;
-              const uint64_t da_hi = make_desc<64>(st + koff), da_lo = make_desc<64>(st + kRTile + koff);
-              const uint64_t db_hi = make_desc<64>(h_hi + kk * kHSub + koff), db_lo = make_desc<64>(h_lo + kk * kHSub + koff);
-              umma_bf16(dcol, da_hi, db_hi, idesc, (kk | k) ? 1u : 0u);
-              umma_bf16(dcol, da_hi, db_lo, idesc, 1u);
-              umma_bf16(dcol, da_lo, db_hi, idesc, 1u);
-            }
-            umma_commit(empty_bar(s));
-          }
-        }
-        umma_commit(d_full_bar);
-      }
-    }
-  } else {
-    // ---------------- gate math: warps 0..3, thread = TMEM lane L -> units L and 128 + L ----------------
-    const int L = warp * 32 + lane;
-    float h[2][NL];
-    // h_{-1}
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int l = 0; l < NL; ++l) {
-        const int line = line0 + l;
-        h[j][l] = (h0 != nullptr && line < N) ? h0[((size_t)d * N + line) * 256 + j * 128 + L] : 0.f;
-      }
-    auto store_h_smem = [&](int j, int l, float v) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(v, hi, lo);
-      const int u = j * 128 + L, kk = u >> 6, col = u & 63;
-      const uint32_t off = (uint32_t)(kk * kHSub + (l >> 3) * 1024 + (l & 7) * 128 + ((((col >> 3) ^ (l & 7))) << 4) +
-                                      (col & 7) * 2);
-      asm volatile("st.shared.b16 [%0], %1;" ::"r"(h_hi + off), "h"(__bfloat16_as_ushort(hi)) : "memory");
-      asm volatile("st.shared.b16 [%0], %1;" ::"r"(h_lo + off), "h"(__bfloat16_as_ushort(lo)) : "memory");
-    };
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int l = 0; l < NL; ++l) store_h_smem(j, l, h[j][l]);
-    fence_proxy_async();
-    tc_fence_before();
-    mbar_arrive(h_ready_bar);
-
-    float rbz[2], rbr[2], rbn[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float* b = rb + (size_t)d * 768 + j * 128 + L;
-      rbz[j] = b[0];
-      rbr[j] = b[256];
-      rbn[j] = b[512];
-    }
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int step = 0; step < T; ++step) {
-      const int t = rev ? (T - 1 - step) : step;
-      mbar_wait(d_full_bar, step & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-#pragma unroll
-        for (int half = 0; half < NL / 16; ++half) {
-          uint32_t az[16], ar[16], an[16];
-          tmem_ld16(lane_base + (uint32_t)((0 * 2 + j) * NL + half * 16), az);
-          tmem_ld16(lane_base + (uint32_t)((1 * 2 + j) * NL + half * 16), ar);
-          tmem_ld16(lane_base + (uint32_t)((2 * 2 + j) * NL + half * 16), an);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int l = half * 16 + q;
-            const int line = line0 + l;
-            if (line < N) {
-              const float* xg = xw + (((size_t)t * N + line) * D + d) * 768 + j * 128 + L;
-              const float xz = xg[0], xr = xg[256], xn = xg[512];
-              const float z = sigmoidf_(xz + __uint_as_float(az[q]) + rbz[j]);
-              const float r = sigmoidf_(xr + __uint_as_float(ar[q]) + rbr[j]);
-              const float nn_ = tanhf(xn + r * (__uint_as_float(an[q]) + rbn[j]));
-              const float hn = (1.f - z) * nn_ + z * h[j][l];
-              h[j][l] = hn;
-              Y[(((size_t)t * D + d) * N + line) * 256 + j * 128 + L] = hn;
-              store_h_smem(j, l, hn);
-            }
-          }
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(h_ready_bar);
-    }
-    if (Yh != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int l = 0; l < NL; ++l)
-          if (line0 + l < N) Yh[((size_t)d * N + line0 + l) * 256 + j * 128 + L] = h[j][l];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
-}
-
-
-// ------------------------------------------------------------------------------------------
 // Cluster-resident recurrent kernel.  A cluster of 8 CTAs owns one tile of <= 32 lines of one
 // direction for all timesteps.  CTA rank r keeps the R rows of hidden units [32r, 32r+32) (3 gates
-// x 32 rows, split bf16) resident in shared memory as the MMA A operand, so nothing is streamed per
+// x 32 rows, split bf16) resident in TENSOR MEMORY as the MMA A operand, so nothing is streamed per
 // step; after each step every CTA writes its 32-unit slice of h_t (split bf16, MMA B-operand layout)
 // into the shared memory of all 8 CTAs (DSMEM) and signals their mbarriers.
 // Lines are described individually (ragged): own length, own row strides for xw and Y.
 // ------------------------------------------------------------------------------------------
 
+constexpr int NL = 32;                               // lines per cluster tile (= MMA N)
+constexpr int kHSub = NL * 128;                      // one 64-wide K sub-tile of h (bytes)
+constexpr int kHPlane = 4 * kHSub;                   // h plane (hi or lo): [NL][256] bf16
+
 constexpr int kCl = 8;                                 // CTAs per cluster
-constexpr int kAPlane = 4 * 128 * 128;                 // R slice plane: 4 K-subtiles x [128 rows x 128 B] = 64 KB
 constexpr int kHBuf = 2 * kHPlane;                     // one h buffer (hi + lo) = 32 KB
 constexpr int kExBytes = 3 * NL * 32 * 4;              // gate pre-activation exchange [3][NL][32] f32
 constexpr int kGateWarps = 16;                         // 4 line groups x 4 TMEM lane quarters
@@ -371,7 +187,6 @@ gru_cluster_kernel(const __nv_bfloat16* __restrict__ r_hi_g, const __nv_bfloat16
   const uint32_t ex = hbuf0 + 2 * kHBuf;
   const uint32_t stage = ex + kExBytes;
   const uint32_t bar_base = stage + kStageBf;
-  const uint32_t r_full_bar = bar_base;
   const uint32_t d_full_bar = bar_base + 8;
   const uint32_t h_ready_bar0 = bar_base + 16;         // [2]
   const uint32_t tmem_slot = bar_base + 32;
@@ -664,36 +479,13 @@ void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* 
     uint64_t bd[2] = {(uint64_t)I, (uint64_t)Ntot};
     CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
     CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    static bool attr = false;
-    if (!attr) {
-      OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-      attr = true;
-    }
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     dim3 grid((unsigned)ceil_div(M, 128), (unsigned)(Ntot / 128));
     gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)M, Ntot, I);
     count_launch();
   }
   // (3) recurrence
-  static const bool use_stream_kernel = std::getenv("OCRS_B200_GRU_STREAM") != nullptr;
-  uint64_t rd[2] = {(uint64_t)H, (uint64_t)D * 3 * H};
-  uint64_t rs[1] = {(uint64_t)H * 2};
-  if (use_stream_kernel) {
-    uint32_t box[2] = {64, 128};
-    CUtensorMap tr_hi = make_map(w.r_hi.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    CUtensorMap tr_lo = make_map(w.r_lo.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    static bool attr = false;
-    if (!attr) {
-      OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecSmem));
-      attr = true;
-    }
-    dim3 grid((unsigned)ceil_div(N, NL), (unsigned)D);
-    gru_rec_tc_kernel<<<grid, 192, kRecSmem, st>>>(tr_hi, tr_lo, xw, w.rb.as<float>(), h0, Y, Yh, T, N, D, reverse[0],
-                                                   D > 1 ? reverse[1] : 0);
-    count_launch();
-  } else {
-    uint32_t box[2] = {64, 32};
-    CUtensorMap tr_hi = make_map(w.r_hi.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    CUtensorMap tr_lo = make_map(w.r_lo.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  {
     const int n_tiles = (int)ceil_div(N, NL);
     std::vector<SeqLine> desc((size_t)n_tiles * NL);
     for (int i = 0; i < n_tiles * NL; ++i) {
@@ -707,11 +499,7 @@ void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* 
     }
     auto* d_desc = static_cast<SeqLine*>(alloc(desc.size() * sizeof(SeqLine)));
     OCRS_CUDA_CHECK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(SeqLine), cudaMemcpyHostToDevice, st));
-    static bool attr = false;
-    if (!attr) {
-      OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
-      attr = true;
-    }
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
     dim3 grid((unsigned)(n_tiles * kCl), (unsigned)D);
     gru_cluster_kernel<<<grid, kClThreads, kClSmem, st>>>(w.r_hi.as<__nv_bfloat16>(), w.r_lo.as<__nv_bfloat16>(), xw, w.rb.as<float>(), h0, Y, Yh, d_desc, N, D,
                                                           (int64_t)N * H, reverse[0], D > 1 ? reverse[1] : 0, nullptr);
@@ -740,20 +528,11 @@ void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, cons
     uint64_t bd[2] = {(uint64_t)I, (uint64_t)Ntot};
     CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
     CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    static bool attr = false;
-    if (!attr) {
-      OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-      attr = true;
-    }
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     dim3 grid((unsigned)ceil_div(rows, 128), (unsigned)(Ntot / 128));
     gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)rows, Ntot, I);
     count_launch();
   }
-  uint64_t rd[2] = {(uint64_t)H, (uint64_t)D * 3 * H};
-  uint64_t rs[1] = {(uint64_t)H * 2};
-  uint32_t box[2] = {64, 32};
-  CUtensorMap tr_hi = make_map(w.r_hi.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap tr_lo = make_map(w.r_lo.ptr, 2, rd, rs, box, CU_TENSOR_MAP_SWIZZLE_128B);
   const int n_tiles = (int)ceil_div(n_lines, NL);
   std::vector<SeqLine> desc((size_t)n_tiles * NL);
   for (int i = 0; i < n_tiles * NL; ++i) {
@@ -762,11 +541,7 @@ void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, cons
   }
   auto* d_desc = static_cast<SeqLine*>(alloc(desc.size() * sizeof(SeqLine)));
   OCRS_CUDA_CHECK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(SeqLine), cudaMemcpyHostToDevice, st));
-  static bool attr2 = false;
-  if (!attr2) {
-    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
-    attr2 = true;
-  }
+  OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
   dim3 grid((unsigned)(n_tiles * kCl), (unsigned)D);
   static const bool dbg_on = std::getenv("OCRS_B200_GRU_DEBUG") != nullptr;
   long long* d_dbg = nullptr;

@@ -149,31 +149,6 @@ __device__ void uf_union(int32_t* L, int a, int b) {
 
 __global__ void ccl_frame_init_kernel(int32_t* L, int64_t n) { L[n] = (int32_t)n; }
 
-__global__ void ccl_init_kernel(int32_t* L, int64_t n) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= n) L[i] = (int32_t)i;  // includes the virtual frame node n
-}
-
-__global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int32_t* L, int H, int W) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y;
-  if (x >= W) return;
-  int p = y * W + x;
-  uint8_t v = mask[p];
-  if (v) {
-    if (x > 0 && mask[p - 1]) uf_union(L, p, p - 1);
-    if (y > 0) {
-      if (mask[p - W]) uf_union(L, p, p - W);
-      if (x > 0 && mask[p - W - 1]) uf_union(L, p, p - W - 1);
-      if (x + 1 < W && mask[p - W + 1]) uf_union(L, p, p - W + 1);
-    }
-  } else {
-    if (x > 0 && !mask[p - 1]) uf_union(L, p, p - 1);
-    if (y > 0 && !mask[p - W]) uf_union(L, p, p - W);
-    if (x == 0 || y == 0 || x == W - 1 || y == H - 1) uf_union(L, p, H * W);
-  }
-}
-
 // ---- two-level labelling: tile-local union-find in shared memory, then unions across tile borders ----
 constexpr int kTile = 32;
 
