@@ -351,6 +351,7 @@ def run_gpu(args):
 
     # ---- per-kernel roofline: profile one more pass with CUDA events around every operator ----
     eng.set_profiling(True)
+    eng.stats(reset=True)  # word / line counts below are those of the profiled passes only
     barrier()
     res = None
     for _ in range(max(1, min(3, args.steps))):
