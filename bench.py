@@ -389,8 +389,8 @@ def run_gpu(args):
                         "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
                         "note": "achieved = fp32-equivalent conv/GEMM FLOPs (2*MACs) per launch / CUDA-event time; the "
                                 "kernel issues 3 fp16 MMAs per product term (split operands), so its own ceiling is "
-                                "peak/3; limited by shared-memory bandwidth (MMA operand reads + TMA fill), tensor pipe "
-                                "51% active under ncu (profiles/r01b_ncu_summary.md)"}
+                                "peak/3; tensor pipe 51% active under ncu: the MMA thread waits 25% of its time for the "
+                                "accumulator promotion and spends 20% in issue overhead (profiles/r01b_ncu_summary.md)"}
             tr = measured_traffic(dom_name)
             if tr is not None:
                 roofline["traffic"] = tr["dram_bytes_per_algorithmic_byte"] * roofline["algorithmic_bytes_per_launch"]
