@@ -8,8 +8,10 @@
 //   B_hi, B_lo : [COUT][KC] fp16 from the [COUT][9*Cin] weight matrix
 // into 128B- (KC = 64) or 64B- (KC = 32) swizzled shared memory; one elected thread issues
 //   HH += A_hi*B_hi ; X += A_hi*B_lo ; X += A_lo*B_hi       (tcgen05.mma kind::f16, fp32 accumulate in TMEM)
-// and four warps promote HH to registers every 128 K-elements, then add X, bias, ReLU, optional
-// max-pool, split to fp16 hi/lo and store NHWC (see the kernel comment for the numerics).
+// and eight warps (two per TMEM lane quadrant, half of the output channels each) promote HH to
+// registers every 128 K-elements, then add X, bias, ReLU, optional max-pool, split to fp16 hi/lo and
+// store NHWC (see the kernel comment for the numerics).  Eight rather than four because the MMA
+// thread was measured waiting 25 % of its time for the promotion (experiments/README.md).
 #include "conv_tc.h"
 
 #include "tc_host.h"
@@ -65,7 +67,7 @@ struct Cfg {
 };
 
 constexpr int kTW = 16, kTH = 8;   // pixel tile: 8 rows x 16 columns = 128 TMEM lanes, lane = th*16 + tw
-constexpr int kConvThreads = 192;  // warps 0-3: promotion + epilogue, warp 4: TMA, warp 5: MMA
+constexpr int kConvThreads = 320;  // warps 0-7: promotion + epilogue, warp 8: TMA, warp 9: MMA
 
 // Promotion + epilogue role of warps 0-3 (TMEM lanes 32*warp .. +31), shared by both conv kernels.
 // Tile = 128 pixels, TWD columns wide (lane = th*TWD + tw); `aux` holds the barriers
@@ -73,7 +75,7 @@ constexpr int kConvThreads = 192;  // warps 0-3: promotion + epilogue, warp 4: T
 // (TMEM -> registers, fp32 round-to-nearest), add the cross-term accumulator, then bias, ReLU,
 // optional 2x2 / 2x1 / 1x2 max-pool through warp shuffles, fp16 split, NHWC store.
 template <int COUT, int TWD>
-__device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, int warp, int lane, int n_tiles,
+__device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, int warp8, int lane, int n_tiles,
                                               int tiles_w, int tiles_h, int TH, int ngroups, int H, int W, int relu,
                                               int ph, int pw, float promo_scale, const float* __restrict__ bias,
                                               act_t* __restrict__ out_hi, act_t* __restrict__ out_lo,
@@ -82,8 +84,12 @@ __device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, 
   auto hh_empty = [&](int b) { return aux + 8u * (2 + b); };
   auto x_full = [&](int b) { return aux + 8u * (4 + b); };
   auto x_empty = [&](int b) { return aux + 8u * (6 + b); };
+  // eight warps: warp8 & 3 = TMEM lane quadrant (a warp may only touch lanes 32*(warp % 4)..+31),
+  // warp8 >> 2 = which half of the output channels; each thread keeps COUT / 2 partial sums
   constexpr int kRowsPerWarp = 32 / TWD;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  constexpr int CH = COUT / 2;
+  const int warp = warp8 & 3, hsel = warp8 >> 2;
+  const uint32_t lane_base = ((uint32_t)(warp * 32) << 16) + (uint32_t)(hsel * CH);
   const int th = warp * kRowsPerWarp + lane / TWD, tw = lane % TWD;
   const int OH = H / ph, OW = W / pw;
   uint32_t gc = 0, ti = 0;
@@ -93,15 +99,15 @@ __device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, 
     t /= tiles_w;
     const int h0 = (t % tiles_h) * TH;
     const int n = t / tiles_h;
-    float acc[COUT];
+    float acc[CH];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int c = 0; c < CH; ++c) acc[c] = 0.f;
     for (int g = 0; g < ngroups; ++g, ++gc) {
       const uint32_t b = gc & 1;
       mbar_wait(hh_full(b), (gc >> 1) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 32) {
+      for (int c0 = 0; c0 < CH; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_base + b * COUT + (uint32_t)c0, r);
 #pragma unroll
@@ -115,7 +121,7 @@ __device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, 
     mbar_wait(x_full(tp), (ti >> 1) & 1);
     tc_fence_after();
 #pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 32) {
+    for (int c0 = 0; c0 < CH; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + lane_base + 2 * COUT + tp * COUT + (uint32_t)c0, r);
 #pragma unroll
@@ -130,12 +136,12 @@ __device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, 
     const bool writer = (ph == 1 || (lane & TWD) == 0) && (pw == 1 || (lane & 1) == 0) && oh < OH && ow < OW;
     const size_t opix = ((size_t)n * OH + oh) * OW + ow;
 #pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 8) {
+    for (int c0 = 0; c0 < CH; c0 += 8) {
       uint32_t hp[4], lp[4];
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
-        float v0 = acc[c0 + j] + __ldg(bias + c0 + j);
-        float v1 = acc[c0 + j + 1] + __ldg(bias + c0 + j + 1);
+        float v0 = acc[c0 + j] + __ldg(bias + hsel * CH + c0 + j);
+        float v1 = acc[c0 + j + 1] + __ldg(bias + hsel * CH + c0 + j + 1);
         if (relu) {
           v0 = fmaxf(v0, 0.f);
           v1 = fmaxf(v1, 0.f);
@@ -151,8 +157,8 @@ __device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, 
         split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
       }
       if (writer) {
-        *reinterpret_cast<uint4*>(out_hi + opix * COUT + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        *reinterpret_cast<uint4*>(out_lo + opix * COUT + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(out_lo + opix * COUT + hsel * CH + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
       }
     }
   }
@@ -197,13 +203,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(hh_full(b), 1);
-      mbar_init(hh_empty(b), 4);
+      mbar_init(hh_empty(b), 8);
       mbar_init(x_full(b), 1);
-      mbar_init(x_empty(b), 4);
+      mbar_init(x_empty(b), 8);
     }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == 8) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -214,7 +220,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   const int nkb = 9 * chunks;
   const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       uint32_t it = 0;
@@ -239,7 +245,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       // c_format F32 (bit 4), a/b format F16 (0 at bits 7, 10), N >> 3 at 17, M >> 4 at 24
@@ -262,12 +268,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
             mbar_wait(full_bar(s), par);
             tc_fence_after();
             const uint32_t st = base + s * C::kStageBytes;
-            const uint32_t a_hi = st, a_lo = st + C::kABytes, b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
+            // one descriptor per stage; the other operands and the K steps are byte offsets >> 4 added to its
+            // 14-bit start-address field (shared memory ends below 256 KB, so the adds never carry out of it)
+            const uint64_t d0 = make_desc<KC>(st);
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
-              const uint32_t koff = k * 32;  // 16 fp16 = 32 bytes along K inside the swizzle atom
-              const uint64_t da_hi = make_desc<KC>(a_hi + koff), da_lo = make_desc<KC>(a_lo + koff);
-              const uint64_t db_hi = make_desc<KC>(b_hi + koff), db_lo = make_desc<KC>(b_lo + koff);
+              const uint64_t da_hi = d0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABytes >> 4);
+              const uint64_t db_hi = da_hi + (uint64_t)((2 * C::kABytes) >> 4), db_lo = db_hi + (uint64_t)(C::kBBytes >> 4);
               umma_bf16(d_hh, da_hi, db_hi, idesc, (kb != kb0 || k) ? 1u : 0u);
               umma_bf16(d_x, da_hi, db_lo, idesc, (kb | k) ? 1u : 0u);
               umma_bf16(d_x, da_lo, db_hi, idesc, 1u);
@@ -286,7 +293,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == 8) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------
