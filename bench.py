@@ -171,40 +171,72 @@ def make_batch(rank: int):
 # =============================================================================================
 # reference arm: the reference's CPU path (oracle port; rten cannot be built here -- no Rust)
 # =============================================================================================
-def run_reference(args):
+# The CPU port is single-threaded Python around torch-CPU networks; pages are independent, so the
+# host cores are used the way the GPU arm uses the GPU: one worker process per page of the batch,
+# torch threads split between the workers.
+_ORACLE = None
+
+
+def _oracle_worker_init(det, rec, threads):
+    global _ORACLE
     import torch
+    torch.set_num_threads(max(1, threads))
+    from oracle.engine import OcrEngine as OEngine, OcrEngineParams as OParams
+    from oracle.onnx_eval import OnnxModel
+    _ORACLE = OEngine(OParams(detection_model=OnnxModel(det), recognition_model=OnnxModel(rec)))
+
+
+def _oracle_worker_page(page):
+    return _ORACLE.get_text(_ORACLE.prepare_input(page, "hwc"))
+
+
+class OraclePool:
+    """`workers` processes, each holding the oracle engine (models loaded once)."""
+
+    def __init__(self, det, rec):
+        import multiprocessing as mp
+        self.cores = min(os.cpu_count() or 1, CPU_THREADS)
+        self.workers = max(1, min(BATCH, self.cores))
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(self.workers, initializer=_oracle_worker_init,
+                             initargs=(det, rec, self.cores // self.workers))
+        self.pool.map(_oracle_worker_page, [np.zeros((64, 64, 3), np.uint8)] * self.workers)  # imports, model load
+
+    def run_batch(self, pages):
+        return self.pool.map(_oracle_worker_page, list(pages), chunksize=1)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.engine import OcrEngine as OEngine, OcrEngineParams as OParams
-    from oracle.onnx_eval import OnnxModel
     from tools.models import ensure_models
-    cores = min(os.cpu_count() or 1, CPU_THREADS)
-    torch.set_num_threads(cores)
     det, rec = ensure_models()
-    ora = OEngine(OParams(detection_model=OnnxModel(det), recognition_model=OnnxModel(rec)))
     pages = make_batch(0)
-
-    def one_page(i):
-        img = ora.prepare_input(pages[i % BATCH], "hwc")
-        return ora.get_text(img)
-
-    for i in range(args.warmup):
-        one_page(i)
+    pool = OraclePool(det, rec)
+    for _ in range(args.warmup):
+        pool.run_batch(pages)
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        one_page(i)
+    for _ in range(args.steps):
+        pool.run_batch(pages)
     dt = time.perf_counter() - t0
-    value = args.steps / dt
+    pool.close()
+    value = BATCH * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": "1 page of the 8-page batch (bounded sample)",
+        "config": {"workload": WORKLOAD, "step": f"one {BATCH}-page batch, one page per worker process",
                    "weights": "models/*.onnx (synthetic stand-ins; the reference's weights are not available offline)"},
-        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} pages of the batch, oracle port (torch-CPU fp32 nets + python/numpy "
-                                   "post-processing); NOT rten -- no Rust toolchain or weights in this environment"},
+        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": pool.cores, "kind": "port",
+                         "sample": f"{args.steps} batches of {BATCH} pages over {pool.workers} worker processes x "
+                                   f"{max(1, pool.cores // pool.workers)} torch threads, oracle port (torch-CPU fp32 nets + "
+                                   "python/numpy post-processing); NOT rten -- no Rust toolchain or weights in this "
+                                   "environment"},
         "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -404,22 +436,33 @@ def run_gpu(args):
     # ---- CPU baseline: oracle port on a bounded sample (rank 0, N = 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle.engine import OcrEngine as OEngine, OcrEngineParams as OParams
-        from oracle.onnx_eval import OnnxModel
-        cores = min(os.cpu_count() or 1, CPU_THREADS)
-        torch.set_num_threads(cores)
-        ora = OEngine(OParams(detection_model=OnnxModel(det), recognition_model=OnnxModel(rec)))
-        n_sample = 2
-        t0 = time.perf_counter()
-        ref_text = []
-        for i in range(n_sample):
-            ref_text.append(ora.get_text(ora.prepare_input(pages[i], "hwc")))
-        dt = time.perf_counter() - t0
-        got = [res[i] for i in range(n_sample)]
-        cpu = {"value": n_sample / dt, "unit": "pages/s", "cores": cores, "kind": "port",
-               "sample": f"first {n_sample} pages of the batch through the oracle port (torch-CPU fp32 nets + "
-                         "python/numpy post-processing; NOT rten)",
-               "text_identical_to_gpu": got == ref_text}
+        try:
+            pool = OraclePool(det, rec)
+            n_rep = 2
+            t0 = time.perf_counter()
+            for _ in range(n_rep):
+                ref_text = pool.run_batch(pages)
+            dt = time.perf_counter() - t0
+            pool.close()
+            cpu = {"value": n_rep * BATCH / dt, "unit": "pages/s", "cores": pool.cores, "kind": "port",
+                   "sample": f"{n_rep} x the {BATCH}-page batch over {pool.workers} worker processes x "
+                             f"{max(1, pool.cores // pool.workers)} torch threads, oracle port (torch-CPU fp32 nets + "
+                             "python/numpy post-processing; NOT rten)",
+                   "text_identical_to_gpu": [res[i] for i in range(BATCH)] == list(ref_text)}
+        except Exception as ex:  # noqa: BLE001  (worker processes unavailable: time two pages in this process)
+            from oracle.engine import OcrEngine as OEngine, OcrEngineParams as OParams
+            from oracle.onnx_eval import OnnxModel
+            cores = min(os.cpu_count() or 1, CPU_THREADS)
+            torch.set_num_threads(cores)
+            ora = OEngine(OParams(detection_model=OnnxModel(det), recognition_model=OnnxModel(rec)))
+            n_sample = 2
+            t0 = time.perf_counter()
+            ref_text = [ora.get_text(ora.prepare_input(pages[i], "hwc")) for i in range(n_sample)]
+            dt = time.perf_counter() - t0
+            cpu = {"value": n_sample / dt, "unit": "pages/s", "cores": cores, "kind": "port",
+                   "sample": f"first {n_sample} pages of the batch, sequentially, through the oracle port (worker pool failed: "
+                             f"{type(ex).__name__}); NOT rten",
+                   "text_identical_to_gpu": [res[i] for i in range(n_sample)] == ref_text}
 
     line = {
         "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
