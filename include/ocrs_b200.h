@@ -110,6 +110,13 @@ int ocrs_b200_model_input_shape(const ocrs_b200_model* m, int64_t dims[8], int* 
  * *out is malloc'ed by the library: release with ocrs_b200_free. */
 int ocrs_b200_model_run(const ocrs_b200_model* m, const float* in, const int64_t* in_shape, int in_ndim, float** out,
                         int64_t out_shape[8], int* out_ndim);
+/* Parses a model file WITHOUT touching a GPU (host code) and describes it as JSON:
+ * {"format","opset","inputs":[{"name","dims"}],"outputs":[...],"nodes":n,"ops":{op:count},
+ *  "unsupported_ops":[...],"initializers":n,"initializer_bytes":n}; dims: -1 = symbolic.  What
+ * `rten::Model::load` would reject (ocrs-cli/src/models.rs:105) is reported here as
+ * OCRS_B200_ERR_MODEL_LOAD with a message; a malformed file never crashes the caller.
+ * *json is malloc'ed, NUL terminated. */
+int ocrs_b200_model_inspect(const uint8_t* bytes, size_t len, char** json);
 /* FLOPs executed by the last run on this handle (2*MACs of Conv/ConvTranspose/MatMul/GRU). */
 double ocrs_b200_model_last_flops(const ocrs_b200_model* m);
 void ocrs_b200_model_destroy(ocrs_b200_model* m);

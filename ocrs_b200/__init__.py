@@ -6,6 +6,6 @@ host-side mirror of the reference API (`engine.py`).  Importing it loads
 from .engine import (  # noqa: F401
     DEFAULT_ALPHABET, DecodeMethod, DimOrder, ImageSource, ImageSourceError, Model, OcrEngine, OcrEngineParams,
     OcrInput, Rect, RotatedRect, TextChar, TextItem, TextLine, TextWord, device_count, find_text_lines,
-    format_json_output, format_text_output, kernel_launch_count,
+    format_json_output, format_text_output, inspect_model, kernel_launch_count,
 )
 from ._lib import OcrsError, LIB_PATH  # noqa: F401

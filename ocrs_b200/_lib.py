@@ -68,6 +68,7 @@ SIGNATURES = {
     "ocrs_b200_model_input_shape": (C.c_int, [C.c_void_p, P(C.c_int64), P(C.c_int)]),
     "ocrs_b200_model_run": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_int64), C.c_int, P(P(C.c_float)),
                                       P(C.c_int64), P(C.c_int)]),
+    "ocrs_b200_model_inspect": (C.c_int, [C.c_void_p, C.c_size_t, P(C.c_void_p)]),
     "ocrs_b200_model_last_flops": (C.c_double, [C.c_void_p]),
     "ocrs_b200_model_destroy": (None, [C.c_void_p]),
     "ocrs_b200_engine_create": (C.c_int, [P(EngineParamsC), P(C.c_void_p)]),

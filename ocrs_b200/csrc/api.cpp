@@ -5,11 +5,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <mutex>
 
 #include "engine.h"
 #include "executor.h"
 #include "layout.h"
+#include "onnx_reader.h"
 #include "text_output.h"
 
 using namespace ocrs;
@@ -149,6 +151,82 @@ int ocrs_b200_model_input_shape(const ocrs_b200_model* m, int64_t dims[8], int* 
     OCRS_CHECK(s.size() <= 8, kInternal, "input rank > 8");
     *ndim = (int)s.size();
     for (size_t i = 0; i < s.size(); ++i) dims[i] = s[i];
+  });
+}
+
+int ocrs_b200_model_inspect(const uint8_t* bytes, size_t len, char** json) {
+  return guard([&] {
+    OCRS_CHECK(bytes && json, kInvalidArg, "null argument");
+    OCRS_CHECK(!onnx::looks_like_rten(bytes, len), kModelLoad,
+               ".rten containers are not supported (FlatBuffers schema unavailable offline); export the model as .onnx");
+    onnx::Graph g = onnx::parse_model(bytes, len);
+    // JSON string; names come from an untrusted file: bytes that are not well-formed UTF-8 become U+FFFD
+    auto esc = [](const std::string& in) {
+      std::string o = "\"";
+      const size_t n = in.size();
+      for (size_t i = 0; i < n;) {
+        const unsigned char ch = (unsigned char)in[i];
+        if (ch < 0x80) {
+          if (ch == '"' || ch == '\\') { o.push_back('\\'); o.push_back((char)ch); }
+          else if (ch < 0x20) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", ch); o += b; }
+          else o.push_back((char)ch);
+          ++i;
+          continue;
+        }
+        int len = ch >= 0xF0 && ch <= 0xF4 ? 4 : ch >= 0xE0 ? 3 : ch >= 0xC2 && ch < 0xE0 ? 2 : 0;
+        bool ok = len > 0 && i + (size_t)len <= n;
+        for (int k = 1; ok && k < len; ++k) ok = ((unsigned char)in[i + k] & 0xC0) == 0x80;
+        if (ok && len == 3) {
+          const unsigned char c1 = (unsigned char)in[i + 1];
+          ok = !(ch == 0xE0 && c1 < 0xA0) && !(ch == 0xED && c1 >= 0xA0);  // overlong, surrogates
+        }
+        if (ok && len == 4) {
+          const unsigned char c1 = (unsigned char)in[i + 1];
+          ok = !(ch == 0xF0 && c1 < 0x90) && !(ch == 0xF4 && c1 >= 0x90);
+        }
+        if (ok) {
+          o.append(in, i, (size_t)len);
+          i += (size_t)len;
+        } else {
+          o += "\\ufffd";
+          ++i;
+        }
+      }
+      return o + "\"";
+    };
+    auto values = [&](const std::vector<onnx::ValueInfo>& vs) {
+      std::string o = "[";
+      for (size_t i = 0; i < vs.size(); ++i) {
+        o += std::string(i ? "," : "") + "{\"name\":" + esc(vs[i].name) + ",\"dims\":[";
+        for (size_t d = 0; d < vs[i].dims.size(); ++d) o += std::string(d ? "," : "") + std::to_string(vs[i].dims[d]);
+        o += "]}";
+      }
+      return o + "]";
+    };
+    std::map<std::string, int> ops;
+    for (const auto& n : g.nodes) ops[n.op] += 1;
+    size_t init_bytes = 0;
+    for (const auto& kv : g.initializers) init_bytes += kv.second.raw.size();
+    std::string o = "{\"format\":\"onnx\",\"opset\":" + std::to_string(g.opset) + ",\"inputs\":" + values(g.inputs) +
+                    ",\"outputs\":" + values(g.outputs) + ",\"nodes\":" + std::to_string(g.nodes.size()) + ",\"ops\":{";
+    bool first = true;
+    for (const auto& kv : ops) {
+      o += std::string(first ? "" : ",") + esc(kv.first) + ":" + std::to_string(kv.second);
+      first = false;
+    }
+    o += "},\"unsupported_ops\":[";
+    first = true;
+    for (const auto& kv : ops)
+      if (!supported_ops().count(kv.first)) {
+        o += std::string(first ? "" : ",") + esc(kv.first);
+        first = false;
+      }
+    o += "],\"initializers\":" + std::to_string(g.initializers.size()) + ",\"initializer_bytes\":" +
+         std::to_string(init_bytes) + "}";
+    char* out = cmalloc<char>(o.size() + 1);
+    std::memcpy(out, o.data(), o.size());
+    out[o.size()] = 0;
+    *json = out;
   });
 }
 

@@ -76,6 +76,14 @@ Storage::~Storage() {
   }
 }
 
+const std::set<std::string>& supported_ops() {
+  static const std::set<std::string> kSupported = {
+      "Add", "AveragePool", "Cast", "Concat", "ConstantOfShape", "Conv", "ConvTranspose", "GRU", "Gather",
+      "LogSoftmax", "MatMul", "MaxPool", "Pad", "Relu", "Reshape", "Shape", "Sigmoid", "Slice", "Transpose",
+      "Unsqueeze", "Squeeze", "Identity", "Constant", "Tanh"};
+  return kSupported;
+}
+
 void configure_device_pool(int device) {
   cudaMemPool_t pool;
   OCRS_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -210,12 +218,8 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
   OCRS_CHECK(!g.inputs[0].dims.empty(), kModelLoad, "model does not specify expected input shape");  // model.rs:28
   m->input_shape_ = g.inputs[0].dims;
 
-  static const std::set<std::string> kSupported = {
-      "Add", "AveragePool", "Cast", "Concat", "ConstantOfShape", "Conv", "ConvTranspose", "GRU", "Gather",
-      "LogSoftmax", "MatMul", "MaxPool", "Pad", "Relu", "Reshape", "Shape", "Sigmoid", "Slice", "Transpose",
-      "Unsqueeze", "Squeeze", "Identity", "Constant", "Tanh"};
   for (const auto& n : g.nodes)
-    OCRS_CHECK(kSupported.count(n.op), kModelLoad, "unsupported ONNX operator: " + n.op);
+    OCRS_CHECK(supported_ops().count(n.op), kModelLoad, "unsupported ONNX operator: " + n.op);
 
   auto impl = std::make_unique<Impl>();
   const int nn_ = (int)g.nodes.size();

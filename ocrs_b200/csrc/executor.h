@@ -9,6 +9,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -45,6 +46,10 @@ struct ModelCost {
   double flops = 0;        // 2 * MACs of Conv / ConvTranspose / MatMul / GRU for the last run
   double min_bytes = 0;    // input + output + weights
 };
+
+// ONNX operators the executor implements (the 20 of ocrs/src/wasm_api.rs:35-56 plus Squeeze, Identity,
+// Constant, Tanh).  Host-side; used by Model::load and by ocrs_b200_model_inspect.
+const std::set<std::string>& supported_ops();
 
 class Model {
  public:

@@ -512,6 +512,18 @@ def kernel_launch_count() -> int:
     return int(lib.ocrs_b200_kernel_launch_count())
 
 
+def inspect_model(model) -> dict:
+    """Parses an `.onnx` file (path or bytes) on the host -- no GPU involved -- and returns its inputs,
+    outputs, operator histogram and the operators the executor does not implement.  Raises OcrsError
+    (`OCRS_B200_ERR_MODEL_LOAD`) for malformed files and `.rten` containers."""
+    import json
+    data = _model_bytes(model)
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    out = C.c_void_p()
+    check(lib.ocrs_b200_model_inspect(C.cast(buf, C.c_void_p), len(data), C.byref(out)))
+    return json.loads(_take_string(out))
+
+
 def find_text_lines(words: Sequence[RotatedRect]) -> List[List[RotatedRect]]:
     """layout_analysis.rs:158 through the C ABI (host code; needs no GPU)."""
     arr = _rects_to_c(words)
