@@ -81,3 +81,33 @@ def test_random_pages_bit_exact(seed, rotated):
     rng = np.random.default_rng(100 + seed)
     words = _random_page(rng, n_rows=int(rng.integers(3, 14)), rotated=rotated)
     _check(words)
+
+
+def test_find_text_lines_survives_degenerate_rects():
+    """NaN / inf / zero-sized / zero-axis / far-away rects: the host layout code returns (or reports an
+    error) without crashing or looping; every input rect appears at most once in the output."""
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        n = int(rng.integers(0, 60))
+        rects = []
+        for _ in range(n):
+            v = list(rng.normal(0, 300, 2)) + list(rng.normal(0, 1, 2)) + list(np.abs(rng.normal(30, 40, 2)))
+            mode = int(rng.integers(0, 12))
+            if mode == 0:
+                v[int(rng.integers(0, 6))] = float("nan")
+            elif mode == 1:
+                v[int(rng.integers(0, 6))] = float("inf")
+            elif mode == 2:
+                v[4] = 0.0
+            elif mode == 3:
+                v[5] = -5.0
+            elif mode == 4:
+                v[2] = v[3] = 0.0
+            elif mode == 5:
+                v[0] = 1e30
+            rects.append(ob.RotatedRect(*[float(x) for x in v]))
+        try:
+            lines = ob.find_text_lines(rects)
+        except ob.OcrsError:
+            continue
+        assert sum(len(l) for l in lines) <= n
