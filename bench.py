@@ -6,8 +6,8 @@
 
 Workload (BASELINE.json configs[2]): full pipeline on a batch of 8 synthetic 1024x768 RGB pages per
 GPU.  One "step" = one pass of the whole hot path over that batch.  Rank r of N processes its own
-8 pages (weak scaling); with N > 1 the recognised text of every rank is gathered to rank 0 over NCCL
-inside the timed region.  Prints ONE JSON line on rank 0.
+8 pages (weak scaling); with N > 1 the recognised text of every rank (all steps of a timed region) is gathered to
+rank 0 over NCCL once per timed region, inside it.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -27,7 +27,6 @@ if ROOT not in sys.path:
 
 PAGE_H, PAGE_W, BATCH = 768, 1024, 8
 METRIC = "pages/sec end-to-end (detect+recognise)"
-CPU_THREADS = 32  # torch-CPU threads of the oracle port (more only adds contention on these small ops)
 WORKLOAD = "full pipeline (detect+line-group+recognise+CTC), batch=8 1024x768 synthetic pages per GPU"
 
 
@@ -172,9 +171,11 @@ def make_batch(rank: int):
 # reference arm: the reference's CPU path (oracle port; rten cannot be built here -- no Rust)
 # =============================================================================================
 # The CPU port is single-threaded Python around torch-CPU networks; pages are independent, so the
-# host cores are used the way the GPU arm uses the GPU: one worker process per page of the batch,
-# torch threads split between the workers.
+# host cores are used the way the GPU arm uses the GPUs: worker processes, one page each at a time,
+# torch threads split between the workers.  To occupy ALL host cores a CPU "step" processes the 8-page
+# batch `replicas` times (pages spread over all workers); pages/s counts every processed page.
 _ORACLE = None
+THREADS_PER_WORKER = 4   # torch-CPU intra-op threads per worker (these small convolutions stop scaling beyond that)
 
 
 def _oracle_worker_init(det, rec, threads):
@@ -187,23 +188,55 @@ def _oracle_worker_init(det, rec, threads):
 
 
 def _oracle_worker_page(page):
-    return _ORACLE.get_text(_ORACLE.prepare_input(page, "hwc"))
+    timers = {}
+    t0 = time.perf_counter()
+    img = _ORACLE.prepare_input(page, "hwc")
+    timers["prepare_image"] = time.perf_counter() - t0
+    text = _ORACLE.get_text(img, timers)
+    return text, timers
 
 
 class OraclePool:
-    """`workers` processes, each holding the oracle engine (models loaded once)."""
+    """Worker processes, each holding the oracle engine (models loaded once)."""
 
-    def __init__(self, det, rec):
+    def __init__(self, det, rec, max_cores=None):
         import multiprocessing as mp
-        self.cores = min(os.cpu_count() or 1, CPU_THREADS)
-        self.workers = max(1, min(BATCH, self.cores))
+        self.cores = os.cpu_count() or 1
+        try:
+            self.cores = len(os.sched_getaffinity(0))
+        except Exception:  # noqa: BLE001
+            pass
+        if max_cores:
+            self.cores = min(self.cores, max_cores)
+        self.threads = max(1, min(THREADS_PER_WORKER, self.cores))
+        self.workers = max(1, self.cores // self.threads)
+        self.replicas = max(1, -(-self.workers // BATCH))  # ceil: every worker has a page per step
         ctx = mp.get_context("spawn")
-        self.pool = ctx.Pool(self.workers, initializer=_oracle_worker_init,
-                             initargs=(det, rec, self.cores // self.workers))
+        self.pool = ctx.Pool(self.workers, initializer=_oracle_worker_init, initargs=(det, rec, self.threads))
         self.pool.map(_oracle_worker_page, [np.zeros((64, 64, 3), np.uint8)] * self.workers)  # imports, model load
+        self.stage_s = {}
 
-    def run_batch(self, pages):
-        return self.pool.map(_oracle_worker_page, list(pages), chunksize=1)
+    def run_batch(self, pages, replicas=None):
+        """Returns the texts of the FIRST replica; every replica is processed (and timed by the caller)."""
+        r = self.replicas if replicas is None else replicas
+        out = self.pool.map(_oracle_worker_page, list(pages) * r, chunksize=1)
+        for _, tm in out:
+            for k, v in tm.items():
+                self.stage_s[k] = self.stage_s.get(k, 0.0) + v
+        return [t for t, _ in out[:len(pages)]]
+
+    def stage_share(self):
+        """Share of the summed per-page CPU time per stage (detect_pad_resize_net includes detection_net)."""
+        d = dict(self.stage_s)
+        if "detect_pad_resize_net" in d and "detection_net" in d:
+            d["detect_pad_resize"] = d.pop("detect_pad_resize_net") - d["detection_net"]
+        tot = sum(d.values()) or 1.0
+        return {k: round(v / tot, 4) for k, v in sorted(d.items(), key=lambda kv: -kv[1])}
+
+    def describe(self):
+        return (f"{self.workers} worker processes x {self.threads} torch threads = {self.workers * self.threads} of "
+                f"{self.cores} host cores; oracle port (torch-CPU fp32 nets + python/numpy post-processing); NOT rten -- "
+                "no Rust toolchain or weights in this environment")
 
     def close(self):
         self.pool.close()
@@ -220,23 +253,26 @@ def run_reference(args):
     pool = OraclePool(det, rec)
     for _ in range(args.warmup):
         pool.run_batch(pages)
+    pool.stage_s = {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
         pool.run_batch(pages)
     dt = time.perf_counter() - t0
+    share = pool.stage_share()
     pool.close()
-    value = BATCH * args.steps / dt
+    n_pages = BATCH * pool.replicas * args.steps
+    value = n_pages / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": f"one {BATCH}-page batch, one page per worker process",
+        "config": {"workload": WORKLOAD,
+                   "step": f"the {BATCH}-page batch x {pool.replicas} replicas = {BATCH * pool.replicas} pages per step, one page per "
+                           "worker process at a time",
                    "weights": "models/*.onnx (synthetic stand-ins; the reference's weights are not available offline)"},
-        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": pool.cores, "kind": "port",
-                         "sample": f"{args.steps} batches of {BATCH} pages over {pool.workers} worker processes x "
-                                   f"{max(1, pool.cores // pool.workers)} torch threads, oracle port (torch-CPU fp32 nets + "
-                                   "python/numpy post-processing); NOT rten -- no Rust toolchain or weights in this "
-                                   "environment"},
+        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": pool.workers * pool.threads, "kind": "port",
+                         "sample": f"{args.steps} steps of {BATCH * pool.replicas} pages; " + pool.describe(),
+                         "stage_share_of_cpu_time": share},
         "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -246,6 +282,8 @@ def run_reference(args):
 # B200 arm
 # =============================================================================================
 def run_gpu(args):
+    import hashlib
+
     import torch
     import torch.distributed as dist
 
@@ -259,19 +297,22 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import ocrs_b200 as ob
-    from ocrs_b200.dist import gather_texts
+    from ocrs_b200.dist import gather_texts, pack_texts
     from tools.models import ensure_models
 
     det, rec = ensure_models()
-    eng = ob.OcrEngine(ob.OcrEngineParams(detection_model=det, recognition_model=rec, device=local))
-    # `--in-flight 2`: a second engine instance (own streams and buffers) on the same GPU lets the host
-    # phases of one batch (layout analysis, result assembly) overlap the kernels of the other
-    engines = [eng] + [ob.OcrEngine(ob.OcrEngineParams(detection_model=det, recognition_model=rec, device=local))
-                       for _ in range(max(1, args.in_flight) - 1)]
+    # ONE library object per rank: the pool owns `in_flight` worker threads / engines on this rank's GPU and
+    # overlaps the host phases of one batch (layout analysis, result assembly) with the kernels of another
+    in_flight = max(1, args.in_flight)
+    pool = ob.OcrPool(ob.OcrEngineParams(detection_model=det, recognition_model=rec), devices=[local], in_flight=in_flight)
+    engines = [pool.engine(0, k) for k in range(in_flight)]
+    eng = engines[0]
     pages = make_batch(rank)
     # host copies in pinned memory (e2e) and device copies (kernel-only `value`)
     pinned = [torch.from_numpy(p).pin_memory() for p in pages]
+    sources = [ob.ImageSource(t.numpy(), ob.DimOrder.Hwc) for t in pinned]
     resident = [t.cuda(local) for t in pinned]
+    resident_ptrs = [t.data_ptr() for t in resident]
     torch.cuda.synchronize()
 
     def barrier():
@@ -279,118 +320,140 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather_text(results):
-        """NCCL gather of the recognised text to rank 0 (two-phase: lengths, then padded bytes)."""
-        if world > 1:
-            gather_texts(results, device=f"cuda:{local}")
+    def submit_resident():
+        return pool.submit_device(resident_ptrs, 0, ob.DimOrder.Hwc, PAGE_H, PAGE_W, 3)
 
-    def step_resident(e=None):
-        e = e or eng
-        inputs = [e.prepare_input_device(t.data_ptr(), 0, ob.DimOrder.Hwc, PAGE_H, PAGE_W, 3) for t in resident]
-        return e.ocr_batch_text(inputs)
-
-    def step_e2e(e=None):
-        e = e or eng
-        inputs = [e.prepare_input(ob.ImageSource(t.numpy(), ob.DimOrder.Hwc)) for t in pinned]
-        return e.ocr_batch_text(inputs)
+    def submit_e2e():
+        return pool.submit(sources)
 
     step_done = []  # completion time of every step (diagnostic: largest gap is reported)
 
-    def run_steps(fn, steps):
-        """Runs `steps` batches, at most len(engines) in flight (one host thread per engine); the text
-        of every finished batch is gathered to rank 0."""
-        if len(engines) == 1:
-            for _ in range(steps):
-                gather_text(fn(eng))
-                step_done.append(time.perf_counter())
-            return
-        import queue
-        todo = queue.Queue()
-        for i in range(steps):
-            todo.put(i)
-        done = queue.Queue()
-        errs = []
-
-        def worker(e):
-            try:
-                while True:
-                    try:
-                        todo.get_nowait()
-                    except queue.Empty:
-                        return
-                    done.put(fn(e))
-            except Exception as ex:  # noqa: BLE001
-                errs.append(ex)
-                done.put(None)
-
-        ts = [threading.Thread(target=worker, args=(e,)) for e in engines]
-        [t.start() for t in ts]
+    def run_steps(submit, steps):
+        """`steps` batches through the pool, in_flight + 1 outstanding; returns the texts of every step.
+        With N > 1 the texts of ALL steps are gathered to rank 0 ONCE, at the end (NCCL, inside the timed
+        region) -- no per-step host rendezvous between the ranks."""
+        from collections import deque
+        outstanding = deque()
+        texts = []
         for _ in range(steps):
-            res = done.get()
+            outstanding.append(submit())
+            while len(outstanding) > in_flight + 1:
+                texts.append(pool.wait_text(outstanding.popleft()))
+                step_done.append(time.perf_counter())
+        while outstanding:
+            texts.append(pool.wait_text(outstanding.popleft()))
             step_done.append(time.perf_counter())
-            if res is None:
-                break
-            gather_text(res)  # collectives stay on the main thread, in completion order
-        [t.join() for t in ts]
-        if errs:
-            raise errs[0]
+        gathered = None
+        if world > 1:
+            gathered = gather_texts([t for step in texts for t in step], device=f"cuda:{local}")
+        return texts, gathered
 
-    gaps = []  # per timed() call: largest interval between two step completions, ms
+    gaps = []
 
-    def timed(fn, steps):
+    def timed(submit, steps):
+        """One timed region of exactly `steps` steps: barrier + synchronize on both sides, CUDA events on every
+        worker engine's stream and the host clock around it; the larger of the two, max over ranks."""
         barrier()
         launches0 = ob.kernel_launch_count()
         tb0 = [e.transfer_bytes() for e in engines]
-        eng.timer_start()
+        for e in engines:
+            e.timer_start()
         t0 = time.perf_counter()
         del step_done[:]
         step_done.append(t0)
-        run_steps(fn, steps)
+        texts, gathered = run_steps(submit, steps)
         gaps.append(max(b - a for a, b in zip(step_done, step_done[1:])) * 1e3 if len(step_done) > 1 else 0.0)
-        for e2 in engines[1:]:
-            e2.timer_start()  # (orders a marker behind everything enqueued on that engine's stream)
-            e2.timer_stop()
-        ms = eng.timer_stop()
+        ms = max(e.timer_stop() for e in engines)  # (records behind everything enqueued on that engine's stream)
         wall = (time.perf_counter() - t0) * 1e3
-        ms = max(ms, wall) if len(engines) > 1 else ms  # several streams: the host clock brackets them all
+        ms = max(ms, wall)
         barrier()
         tb1 = [e.transfer_bytes() for e in engines]
-        h2d0 = sum(t[0] for t in tb0); d2h0 = sum(t[1] for t in tb0)
-        h2d1 = sum(t[0] for t in tb1); d2h1 = sum(t[1] for t in tb1)
+        h2d = (sum(t[0] for t in tb1) - sum(t[0] for t in tb0)) / steps
+        d2h = (sum(t[1] for t in tb1) - sum(t[1] for t in tb0)) / steps
         t = torch.tensor([ms, wall], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), ob.kernel_launch_count() - launches0, (h2d1 - h2d0) / steps, (d2h1 - d2h0) / steps
+        return {"ms": float(t[0]), "wall": float(t[1]), "launches": ob.kernel_launch_count() - launches0, "h2d": h2d,
+                "d2h": d2h, "texts": texts, "gathered": gathered}
+
+    def repeated(submit, steps, min_seconds):
+        """Repeats the K-step timed region until it has covered `min_seconds` (at least 3 regions, at most 25);
+        the MEDIAN region is reported, so `steps` and `ms_per_step` stay those of one region."""
+        regs = [timed(submit, steps)]
+        n_more = int(min(24, max(2, np.ceil(min_seconds * 1e3 / max(regs[0]["ms"], 1e-3)) - 1)))
+        if world > 1:  # every rank must run the same number of regions
+            t = torch.tensor([n_more], dtype=torch.int64, device=f"cuda:{local}")
+            dist.broadcast(t, 0)
+            n_more = int(t.item())
+        for _ in range(n_more):
+            regs.append(timed(submit, steps))
+        order = sorted(range(len(regs)), key=lambda i: regs[i]["ms"])
+        med = regs[order[len(order) // 2]]
+        return med, [round(r["ms"], 3) for r in regs]
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.prepare()  # attach the NVML client before the warm-up, not inside the timed region
-    # warm-up runs the whole step, including the gather (the first NCCL collective builds the
-    # communicator, ~100 ms, and must not land in the timed region)
-    for e in engines:
-        for _ in range(args.warmup):
-            gather_text(step_resident(e))
-        for _ in range(max(1, args.warmup // 2)):
-            gather_text(step_e2e(e))
+    # warm-up runs the whole step on every worker, including the gather (the first NCCL collective builds
+    # the communicator, ~100 ms, and must not land in the timed region)
+    run_steps(submit_resident, max(args.warmup, 1) * in_flight)
+    run_steps(submit_e2e, max(1, args.warmup // 2) * in_flight)
 
     if rank == 0:
         sampler.start()
-    eng.profile(reset=True)  # clear host-section timers
-    ms, wall, launches, _, _ = timed(step_resident, args.steps)
-    host_real = {k: round(v["ms"] / args.steps, 3) for k, v in eng.profile(reset=True).items() if k.startswith("host/")}
-    ms_e2e, wall_e2e, _, h2d, d2h = timed(step_e2e, args.steps)
+    for e in engines:
+        e.profile(reset=True)  # clear host-section timers
+    res_r, reps_r = repeated(submit_resident, args.steps, args.min_seconds)
+    host_real = {}
+    for e in engines:
+        for k, v in e.profile(reset=True).items():
+            if k.startswith("host/"):
+                host_real[k] = host_real.get(k, 0.0) + v["ms"]
+    host_real = {k: round(v / (args.steps * len(reps_r)), 3) for k, v in host_real.items()}
+    res_e, reps_e = repeated(submit_e2e, args.steps, args.min_seconds)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- parity of what was timed (outside the timed region) ----
+    # (1) every step of the timed regions produced the same text; (2) N > 1: the text rank 0 gathered over
+    # NCCL is byte-identical to what each rank produced; each rank checks one of its own pages against the
+    # CPU oracle (N = 1 checks all 8 pages in the cpu_baseline leg below)
+    my_texts = res_e["texts"][0]
+    steps_identical = all(t == my_texts for t in res_e["texts"]) and all(t == my_texts for t in res_r["texts"])
+    parity = {"all_steps_identical": bool(steps_identical)}
+    if world > 1:
+        digest = hashlib.sha256(pack_texts([t for step in res_e["texts"] for t in step])).digest()
+        mine = torch.tensor(list(digest), dtype=torch.uint8, device=f"cuda:{local}")
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        from oracle.engine import OcrEngine as OEngine, OcrEngineParams as OParams
+        from oracle.onnx_eval import OnnxModel
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(world, 1) // 2))
+        ora = OEngine(OParams(detection_model=OnnxModel(det), recognition_model=OnnxModel(rec)))
+        page_ok = ora.get_text(ora.prepare_input(pages[0], "hwc")) == my_texts[0]
+        ok = torch.tensor([1 if (page_ok and steps_identical) else 0], dtype=torch.int32, device=f"cuda:{local}")
+        oks = [torch.zeros_like(ok) for _ in range(world)]
+        dist.all_gather(oks, ok)
+        if rank == 0:
+            per = len(my_texts) * args.steps
+            got = [hashlib.sha256(pack_texts(res_e["gathered"][r][:per])).digest() for r in range(world)]
+            parity["gathered_text_matches_rank_text"] = [bytes(allh[r].cpu().tolist()) == got[r] for r in range(world)]
+            parity["rank_page0_identical_to_cpu_oracle"] = [bool(int(o.item())) for o in oks]
+            parity["pages_gathered"] = sum(len(g) for g in res_e["gathered"])
+
     # ---- per-kernel roofline: profile one more pass with CUDA events around every operator ----
+    n_prof = max(1, min(3, args.steps))
     eng.set_profiling(True)
     eng.stats(reset=True)  # word / line counts below are those of the profiled passes only
     barrier()
+    peng_inputs = None
     res = None
-    for _ in range(max(1, min(3, args.steps))):
-        res = step_resident(eng)
+    for _ in range(n_prof):
+        peng_inputs = [eng.prepare_input_device(p, 0, ob.DimOrder.Hwc, PAGE_H, PAGE_W, 3) for p in resident_ptrs]
+        res = eng.ocr_batch_text(peng_inputs)
     prof = eng.profile(reset=True)
     eng.set_profiling(False)
     stats = eng.stats(reset=True)
+    del peng_inputs
 
     if rank != 0:
         if world > 1:
@@ -399,15 +462,16 @@ def run_gpu(args):
 
     peaks = measured_peaks()
     total_pages = BATCH * world
+    ms, ms_e2e = res_r["ms"], res_e["ms"]
     value = total_pages * args.steps / (ms / 1e3)
     e2e_value = total_pages * args.steps / (ms_e2e / 1e3)
 
     # dominant kernel = the profiled operator class with the largest share of device time
     ops = {k: v for k, v in prof.items()
            if not k.startswith("stage/") and not k.startswith("host/") and not k.endswith("(total)")}
-    host_ms = {k: round(v["ms"] / max(1, min(3, args.steps)), 3) for k, v in prof.items() if k.startswith("host/")}
+    host_ms = {k: round(v["ms"] / n_prof, 3) for k, v in prof.items() if k.startswith("host/")}
     dom_name, dom = max(ops.items(), key=lambda kv: kv[1]["ms"]) if ops else ("none", None)
-    stage_ms = {k: round(v["ms"] / max(1, min(3, args.steps)), 3) for k, v in prof.items() if k.startswith("stage/")}
+    stage_ms = {k: round(v["ms"] / n_prof, 3) for k, v in prof.items() if k.startswith("stage/")}
     roofline = None
     if dom is not None and dom["launches"] > 0:
         sec_per_launch = dom["ms"] / 1e3 / dom["launches"]
@@ -417,12 +481,10 @@ def run_gpu(args):
                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
                         "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside the step)",
                         "share_of_step": dom["ms"] / max(sum(v["ms"] for v in ops.values()), 1e-9),
-                        "launches_per_step": dom["launches"] / max(1, min(3, args.steps)),
+                        "launches_per_step": dom["launches"] / n_prof,
                         "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
-                        "note": "achieved = fp32-equivalent conv/GEMM FLOPs (2*MACs) per launch / CUDA-event time; the "
-                                "kernel issues 3 fp16 MMAs per product term (split operands), so its own ceiling is "
-                                "peak/3; tensor pipe 51% active under ncu: the MMA thread waits 25% of its time for the "
-                                "accumulator promotion and spends 20% in issue overhead (profiles/r01b_ncu_summary.md)"}
+                        "note": "achieved = fp32-equivalent conv/GEMM FLOPs (2*MACs) per launch / CUDA-event time; split "
+                                "operands: three fp16 MMAs per product term, so the kernel's own ceiling is peak/3"}
             tr = measured_traffic(dom_name)
             if tr is not None:
                 roofline["traffic"] = tr["dram_bytes_per_algorithmic_byte"] * roofline["algorithmic_bytes_per_launch"]
@@ -436,49 +498,40 @@ def run_gpu(args):
     # ---- CPU baseline: oracle port on a bounded sample (rank 0, N = 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        try:
-            pool = OraclePool(det, rec)
-            n_rep = 2
-            t0 = time.perf_counter()
-            for _ in range(n_rep):
-                ref_text = pool.run_batch(pages)
-            dt = time.perf_counter() - t0
-            pool.close()
-            cpu = {"value": n_rep * BATCH / dt, "unit": "pages/s", "cores": pool.cores, "kind": "port",
-                   "sample": f"{n_rep} x the {BATCH}-page batch over {pool.workers} worker processes x "
-                             f"{max(1, pool.cores // pool.workers)} torch threads, oracle port (torch-CPU fp32 nets + "
-                             "python/numpy post-processing; NOT rten)",
-                   "text_identical_to_gpu": [res[i] for i in range(BATCH)] == list(ref_text)}
-        except Exception as ex:  # noqa: BLE001  (worker processes unavailable: time two pages in this process)
-            from oracle.engine import OcrEngine as OEngine, OcrEngineParams as OParams
-            from oracle.onnx_eval import OnnxModel
-            cores = min(os.cpu_count() or 1, CPU_THREADS)
-            torch.set_num_threads(cores)
-            ora = OEngine(OParams(detection_model=OnnxModel(det), recognition_model=OnnxModel(rec)))
-            n_sample = 2
-            t0 = time.perf_counter()
-            ref_text = [ora.get_text(ora.prepare_input(pages[i], "hwc")) for i in range(n_sample)]
-            dt = time.perf_counter() - t0
-            cpu = {"value": n_sample / dt, "unit": "pages/s", "cores": cores, "kind": "port",
-                   "sample": f"first {n_sample} pages of the batch, sequentially, through the oracle port (worker pool failed: "
-                             f"{type(ex).__name__}); NOT rten",
-                   "text_identical_to_gpu": [res[i] for i in range(n_sample)] == ref_text}
+        opool = OraclePool(det, rec)
+        n_rep = 2
+        t0 = time.perf_counter()
+        for _ in range(n_rep):
+            ref_text = opool.run_batch(pages)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_rep * BATCH * opool.replicas / dt, "unit": "pages/s", "cores": opool.workers * opool.threads,
+               "kind": "port",
+               "sample": f"{n_rep} steps of {BATCH * opool.replicas} pages (the {BATCH}-page batch x {opool.replicas} replicas); "
+                         + opool.describe(),
+               "stage_share_of_cpu_time": opool.stage_share(),
+               "text_identical_to_gpu": list(my_texts) == list(ref_text) and list(res) == list(ref_text)}
+        opool.close()
 
     line = {
         "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pages_per_gpu": BATCH, "page_hw": [PAGE_H, PAGE_W], "batches_in_flight": len(engines),
+        "config": {"workload": WORKLOAD, "pages_per_gpu": BATCH, "page_hw": [PAGE_H, PAGE_W], "batches_in_flight": in_flight,
+                   "api": "ocrs_b200_pool_submit / ocrs_b200_pool_wait_text (one pool per rank; NCCL gather of all steps' "
+                          "text once per timed region)",
                    "weights": "models/*.onnx", "l2": "inputs per step (18.9 MB u8 + activations >> 126 MB L2 over a step)",
-                   "words_per_page": stats["words"] / max(1, BATCH * max(1, min(3, args.steps))),
-                   "lines_per_page": stats["lines"] / max(1, BATCH * max(1, min(3, args.steps)))},
-        "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                   "timed_regions": len(reps_r), "report": "median region",
+                   "words_per_page": stats["words"] / max(1, BATCH * n_prof),
+                   "lines_per_page": stats["lines"] / max(1, BATCH * n_prof)},
+        "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": res_e["h2d"], "d2h_bytes_per_step": res_e["d2h"],
+                "ms_per_step": ms_e2e / args.steps, "region_ms": reps_e},
+        "gpu_launches": res_r["launches"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "region_ms": reps_r,
         "stage_ms_per_step": stage_ms, "host_ms_per_step": host_real, "host_ms_per_step_serial_profile": host_ms,
-        "wall_ms_per_step": wall / args.steps,
-        "max_step_gap_ms": {"value": round(gaps[0], 2), "e2e": round(gaps[1], 2)} if len(gaps) >= 2 else None,
-        "op_ms_per_step": {k: round(v["ms"] / max(1, min(3, args.steps)), 3) for k, v in ops.items()},
+        "wall_ms_per_step": res_r["wall"] / args.steps,
+        "max_step_gap_ms": {"value": round(gaps[0], 2), "e2e": round(gaps[-1], 2)} if len(gaps) >= 2 else None,
+        "op_ms_per_step": {k: round(v["ms"] / n_prof, 3) for k, v in ops.items()},
+        "pool": pool.describe().strip().split("\n"),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -492,7 +545,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight per GPU (engine instances)")
+    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight per GPU (pool workers / engines)")
+    ap.add_argument("--min-seconds", type=float, default=2.0,
+                    help="each arm repeats its K-step timed region until it has covered this long; the median region is reported")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

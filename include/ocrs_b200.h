@@ -190,6 +190,49 @@ int ocrs_b200_engine_ocr_batch_text(ocrs_b200_engine* e, const ocrs_b200_input* 
 int ocrs_b200_engine_detect_words_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
                                         ocrs_b200_rotated_rect** rects, size_t** offsets);
 
+/* ---- engine pool: pipelining and multi-GPU fan-out inside the library ---------------------------
+ * The reference runs get_text page by page on the calling thread (ocrs/src/lib.rs:290-300,
+ * ocrs-cli/src/main.rs:438-446).  A pool owns, per device, `in_flight` worker threads with one engine
+ * each; batches of pages are submitted asynchronously and collected by ticket, so the host phases of
+ * one batch (layout analysis, result assembly) overlap the kernels of another, and all GPUs of a box
+ * are fed from one process (SURVEY.md section 8b "device_ids[]", section 8e).  Workers are pinned to
+ * the CPUs of their GPU's NUMA node. */
+typedef struct ocrs_b200_pool ocrs_b200_pool;
+
+/* ImageSource (preprocess.rs:61-124).  `pixels` is borrowed until the batch's ticket has been waited
+ * for.  on_device != 0: `pixels` is device memory of one of the pool's GPUs (the batch runs there). */
+typedef struct ocrs_b200_page {
+  const void* pixels;
+  int32_t dtype, order; /* OCRS_B200_DTYPE_*, OCRS_B200_ORDER_* */
+  int32_t height, width, channels;
+  int32_t on_device;
+} ocrs_b200_page;
+
+typedef struct ocrs_b200_pool_params {
+  ocrs_b200_engine_params engine; /* models, decode method, alphabet ...; `device` is ignored */
+  const int32_t* device_ids;      /* NULL = every visible device */
+  int32_t n_devices;
+  int32_t in_flight;              /* batches in flight (worker threads, engines) per device; 0 = 2 */
+  int32_t pin_numa;               /* 0 = default (pin), 1 = pin, -1 = do not pin */
+  int32_t layout_threads;         /* host threads per worker for layout analysis; 0 = 4 */
+} ocrs_b200_pool_params;
+
+int ocrs_b200_pool_create(const ocrs_b200_pool_params* params, ocrs_b200_pool** out);
+void ocrs_b200_pool_destroy(ocrs_b200_pool* p); /* finishes queued batches first */
+/* Enqueues one batch (detect -> layout -> recognise of every page); never blocks on the GPU. */
+int ocrs_b200_pool_submit(ocrs_b200_pool* p, const ocrs_b200_page* pages, size_t n_pages, uint64_t* ticket);
+/* Blocks until the batch is done.  results / texts: caller arrays of n_pages entries, filled with
+ * malloc'ed objects (ocrs_b200_text_result_free / ocrs_b200_free).  A ticket is consumed by its wait. */
+int ocrs_b200_pool_wait(ocrs_b200_pool* p, uint64_t ticket, ocrs_b200_text_result** results, size_t n_pages);
+int ocrs_b200_pool_wait_text(ocrs_b200_pool* p, uint64_t ticket, char** texts, size_t n_pages);
+int ocrs_b200_pool_done(ocrs_b200_pool* p, uint64_t ticket, int* done);
+int ocrs_b200_pool_shape(const ocrs_b200_pool* p, int* n_devices, int* in_flight);
+/* Worker engine `slot` of device index `dev_index` as an engine handle (statistics / profiling hooks);
+ * release with ocrs_b200_engine_destroy. */
+int ocrs_b200_pool_engine(ocrs_b200_pool* p, int dev_index, int slot, ocrs_b200_engine** out);
+/* Human-readable worker placement (device, PCI bus id, NUMA node, CPUs); *text is malloc'ed. */
+int ocrs_b200_pool_describe(ocrs_b200_pool* p, char** text);
+
 /* Counters accumulated since the last reset: [0] detection FLOPs, [1] recognition FLOPs,
  * [2] words, [3] lines, [4] CTC timesteps, [5] recognition batches. */
 int ocrs_b200_engine_stats(ocrs_b200_engine* e, double out[8], int reset);

@@ -56,6 +56,16 @@ class EngineParamsC(C.Structure):
                 ("alphabet_utf8", C.c_char_p), ("allowed_chars_utf8", C.c_char_p), ("device", C.c_int32)]
 
 
+class PageC(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("dtype", C.c_int32), ("order", C.c_int32), ("height", C.c_int32),
+                ("width", C.c_int32), ("channels", C.c_int32), ("on_device", C.c_int32)]
+
+
+class PoolParamsC(C.Structure):
+    _fields_ = [("engine", EngineParamsC), ("device_ids", C.POINTER(C.c_int32)), ("n_devices", C.c_int32),
+                ("in_flight", C.c_int32), ("pin_numa", C.c_int32), ("layout_threads", C.c_int32)]
+
+
 # every symbol include/ocrs_b200.h declares: (restype, argtypes)
 P = C.POINTER
 SIGNATURES = {
@@ -110,6 +120,15 @@ SIGNATURES = {
     "ocrs_b200_engine_timer_stop": (C.c_int, [C.c_void_p, P(C.c_float)]),
     "ocrs_b200_engine_transfer_bytes": (C.c_int, [C.c_void_p, P(C.c_int64)]),
     "ocrs_b200_kernel_launch_count": (C.c_int64, []),
+    "ocrs_b200_pool_create": (C.c_int, [P(PoolParamsC), P(C.c_void_p)]),
+    "ocrs_b200_pool_destroy": (None, [C.c_void_p]),
+    "ocrs_b200_pool_submit": (C.c_int, [C.c_void_p, P(PageC), C.c_size_t, P(C.c_uint64)]),
+    "ocrs_b200_pool_wait": (C.c_int, [C.c_void_p, C.c_uint64, P(P(TextResultC)), C.c_size_t]),
+    "ocrs_b200_pool_wait_text": (C.c_int, [C.c_void_p, C.c_uint64, P(C.c_void_p), C.c_size_t]),
+    "ocrs_b200_pool_done": (C.c_int, [C.c_void_p, C.c_uint64, P(C.c_int)]),
+    "ocrs_b200_pool_shape": (C.c_int, [C.c_void_p, P(C.c_int), P(C.c_int)]),
+    "ocrs_b200_pool_engine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, P(C.c_void_p)]),
+    "ocrs_b200_pool_describe": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
 }
 
 

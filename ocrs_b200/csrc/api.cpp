@@ -12,6 +12,7 @@
 #include "executor.h"
 #include "layout.h"
 #include "onnx_reader.h"
+#include "pool.h"
 #include "text_output.h"
 
 using namespace ocrs;
@@ -85,6 +86,46 @@ std::vector<geom::RotatedRect> to_rects(const ocrs_b200_rotated_rect* p, size_t 
   return v;
 }
 }  // namespace
+
+namespace {
+char* join_text(const std::vector<TextLine>& lines) {  // OcrEngine::get_text (lib.rs:290-300)
+  std::string text;
+  bool first = true;
+  for (const auto& l : lines) {
+    if (!l.present) continue;
+    if (!first) text.push_back('\n');
+    first = false;
+    std::vector<uint32_t> cps;
+    cps.reserve(l.chars.size());
+    for (const auto& c : l.chars) cps.push_back(c.ch);
+    text += codepoints_to_utf8(cps);
+  }
+  char* out = cmalloc<char>(text.size() + 1);
+  std::memcpy(out, text.c_str(), text.size() + 1);
+  return out;
+}
+
+EngineParams to_engine_params(const ocrs_b200_engine_params* p) {
+  EngineParams ep;
+  ep.detection_model = p->detection_model;
+  ep.detection_model_len = p->detection_model_len;
+  ep.recognition_model = p->recognition_model;
+  ep.recognition_model_len = p->recognition_model_len;
+  ep.debug = p->debug != 0;
+  OCRS_CHECK(p->decode_method == OCRS_B200_DECODE_GREEDY || p->decode_method == OCRS_B200_DECODE_BEAM, kInvalidArg,
+             "unknown decode method");
+  ep.decode_method = p->decode_method == OCRS_B200_DECODE_BEAM ? DecodeMethod::kBeamSearch : DecodeMethod::kGreedy;
+  ep.beam_width = p->beam_width;
+  if (p->alphabet_utf8) { ep.has_alphabet = true; ep.alphabet_utf8 = p->alphabet_utf8; }
+  if (p->allowed_chars_utf8) { ep.has_allowed_chars = true; ep.allowed_chars_utf8 = p->allowed_chars_utf8; }
+  ep.device = p->device;
+  return ep;
+}
+}  // namespace
+
+struct ocrs_b200_pool {
+  std::unique_ptr<Pool> pool;
+};
 
 struct ocrs_b200_model {
   std::unique_ptr<Model> model;
@@ -253,12 +294,13 @@ int ocrs_b200_model_run(const ocrs_b200_model* cm, const float* in, const int64_
       x.data = reinterpret_cast<float*>(x.storage->ptr);
       OCRS_CUDA_CHECK(cudaMemcpyAsync(x.data, in, (size_t)n * 4, cudaMemcpyHostToDevice, st));
       ModelCost cost;
+      const int tc_tok = m->model->tc_token();
       DTensor y = m->model->run(x, st, &cost);
       OCRS_CHECK(y.shape.size() <= 8, kWrongOutput, "output rank > 8");
       float* host = cmalloc<float>((size_t)y.numel());
       cudaError_t e = cudaMemcpyAsync(host, y.data, (size_t)y.numel() * 4, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e == cudaSuccess && m->model->take_tc_overflow()) {
+      if (e == cudaSuccess && m->model->take_tc_overflow(tc_tok)) {
         // split-fp16 range overflow: the model now runs its convolutions in fp32; repeat the call
         y = m->model->run(x, st, &cost);
         e = cudaMemcpyAsync(host, y.data, (size_t)y.numel() * 4, cudaMemcpyDeviceToHost, st);
@@ -298,19 +340,7 @@ int ocrs_b200_engine_create(const ocrs_b200_engine_params* p, ocrs_b200_engine**
     OCRS_CHECK(p && out, kInvalidArg, "null argument");
     *out = nullptr;
     require_device();
-    EngineParams ep;
-    ep.detection_model = p->detection_model;
-    ep.detection_model_len = p->detection_model_len;
-    ep.recognition_model = p->recognition_model;
-    ep.recognition_model_len = p->recognition_model_len;
-    ep.debug = p->debug != 0;
-    OCRS_CHECK(p->decode_method == OCRS_B200_DECODE_GREEDY || p->decode_method == OCRS_B200_DECODE_BEAM, kInvalidArg,
-               "unknown decode method");
-    ep.decode_method = p->decode_method == OCRS_B200_DECODE_BEAM ? DecodeMethod::kBeamSearch : DecodeMethod::kGreedy;
-    ep.beam_width = p->beam_width;
-    if (p->alphabet_utf8) { ep.has_alphabet = true; ep.alphabet_utf8 = p->alphabet_utf8; }
-    if (p->allowed_chars_utf8) { ep.has_allowed_chars = true; ep.allowed_chars_utf8 = p->allowed_chars_utf8; }
-    ep.device = p->device;
+    EngineParams ep = to_engine_params(p);
     auto* e = new ocrs_b200_engine();
     try {
       e->engine = std::make_shared<Engine>(ep);
@@ -603,21 +633,110 @@ int ocrs_b200_engine_ocr_batch_text(ocrs_b200_engine* e, const ocrs_b200_input* 
       texts[i] = nullptr;
     }
     auto r = e->engine->ocr_pages(pages);
-    for (size_t i = 0; i < n_pages; ++i) {
-      std::string text;
-      bool first = true;
-      for (const auto& l : r[i]) {
-        if (!l.present) continue;
-        if (!first) text.push_back('\n');
-        first = false;
-        std::vector<uint32_t> cps;
-        cps.reserve(l.chars.size());
-        for (const auto& c : l.chars) cps.push_back(c.ch);
-        text += codepoints_to_utf8(cps);
-      }
-      texts[i] = cmalloc<char>(text.size() + 1);
-      std::memcpy(texts[i], text.c_str(), text.size() + 1);
+    for (size_t i = 0; i < n_pages; ++i) texts[i] = join_text(r[i]);
+  });
+}
+
+// ---- engine pool ---------------------------------------------------------------------------------
+int ocrs_b200_pool_create(const ocrs_b200_pool_params* p, ocrs_b200_pool** out) {
+  return guard([&] {
+    OCRS_CHECK(p && out, kInvalidArg, "null argument");
+    *out = nullptr;
+    require_device();
+    PoolParams pp;
+    pp.engine = to_engine_params(&p->engine);
+    OCRS_CHECK(p->n_devices >= 0 && (p->device_ids != nullptr || p->n_devices == 0), kInvalidArg, "bad device list");
+    for (int i = 0; i < p->n_devices; ++i) pp.devices.push_back(p->device_ids[i]);
+    if (p->in_flight != 0) pp.in_flight = p->in_flight;
+    pp.pin_numa = p->pin_numa >= 0;
+    if (p->layout_threads != 0) pp.layout_threads = p->layout_threads;
+    auto* h = new ocrs_b200_pool();
+    try {
+      h->pool = std::make_unique<Pool>(pp);
+    } catch (...) {
+      delete h;
+      throw;
     }
+    *out = h;
+  });
+}
+
+void ocrs_b200_pool_destroy(ocrs_b200_pool* p) {
+  guard([&] { delete p; });
+}
+
+int ocrs_b200_pool_submit(ocrs_b200_pool* p, const ocrs_b200_page* pages, size_t n_pages, uint64_t* ticket) {
+  return guard([&] {
+    OCRS_CHECK(p && ticket && (pages || n_pages == 0), kInvalidArg, "null argument");
+    std::vector<PoolPage> v(n_pages);
+    for (size_t i = 0; i < n_pages; ++i) {
+      const ocrs_b200_page& s = pages[i];
+      // ImageSource validation (preprocess.rs:81-123) happens up front so that a bad page fails the submit
+      OCRS_CHECK(s.pixels != nullptr, kInvalidArg, "pixels is null");
+      OCRS_CHECK(s.dtype == 0 || s.dtype == 1, kInvalidArg, "dtype must be 0 (u8) or 1 (f32)");
+      OCRS_CHECK(s.order == 0 || s.order == 1, kInvalidArg, "order must be 0 (HWC) or 1 (CHW)");
+      OCRS_CHECK(s.height >= 0 && s.width >= 0, kInvalidArg, "negative image size");
+      OCRS_CHECK(s.channels == 1 || s.channels == 3 || s.channels == 4, kUnsupportedChannelCount,
+                 "channel count is not 1, 3 or 4");
+      v[i].pixels = s.pixels; v[i].dtype = s.dtype; v[i].order = s.order;
+      v[i].H = s.height; v[i].W = s.width; v[i].C = s.channels; v[i].on_device = s.on_device != 0;
+    }
+    *ticket = p->pool->submit(v.data(), v.size());
+  });
+}
+
+int ocrs_b200_pool_wait(ocrs_b200_pool* p, uint64_t ticket, ocrs_b200_text_result** results, size_t n_pages) {
+  return guard([&] {
+    OCRS_CHECK(p && (results || n_pages == 0), kInvalidArg, "null argument");
+    for (size_t i = 0; i < n_pages; ++i) results[i] = nullptr;
+    auto r = p->pool->wait(ticket);
+    OCRS_CHECK(r.size() == n_pages, kInvalidArg, "n_pages does not match the submitted batch");
+    for (size_t i = 0; i < n_pages; ++i) results[i] = make_text_result(r[i]);
+  });
+}
+
+int ocrs_b200_pool_wait_text(ocrs_b200_pool* p, uint64_t ticket, char** texts, size_t n_pages) {
+  return guard([&] {
+    OCRS_CHECK(p && (texts || n_pages == 0), kInvalidArg, "null argument");
+    for (size_t i = 0; i < n_pages; ++i) texts[i] = nullptr;
+    auto r = p->pool->wait(ticket);
+    OCRS_CHECK(r.size() == n_pages, kInvalidArg, "n_pages does not match the submitted batch");
+    for (size_t i = 0; i < n_pages; ++i) texts[i] = join_text(r[i]);
+  });
+}
+
+int ocrs_b200_pool_done(ocrs_b200_pool* p, uint64_t ticket, int* done) {
+  return guard([&] {
+    OCRS_CHECK(p && done, kInvalidArg, "null argument");
+    *done = p->pool->done(ticket) ? 1 : 0;
+  });
+}
+
+int ocrs_b200_pool_shape(const ocrs_b200_pool* p, int* n_devices, int* in_flight) {
+  return guard([&] {
+    OCRS_CHECK(p && n_devices && in_flight, kInvalidArg, "null argument");
+    *n_devices = p->pool->n_devices();
+    *in_flight = p->pool->in_flight();
+  });
+}
+
+int ocrs_b200_pool_engine(ocrs_b200_pool* p, int dev_index, int slot, ocrs_b200_engine** out) {
+  return guard([&] {
+    OCRS_CHECK(p && out, kInvalidArg, "null argument");
+    *out = nullptr;
+    auto eng = p->pool->engine(dev_index, slot);
+    auto* e = new ocrs_b200_engine();
+    e->engine = std::move(eng);
+    *out = e;
+  });
+}
+
+int ocrs_b200_pool_describe(ocrs_b200_pool* p, char** text) {
+  return guard([&] {
+    OCRS_CHECK(p && text, kInvalidArg, "null argument");
+    std::string s = p->pool->numa_report();
+    *text = cmalloc<char>(s.size() + 1);
+    std::memcpy(*text, s.c_str(), s.size() + 1);
   });
 }
 

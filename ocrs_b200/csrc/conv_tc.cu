@@ -60,108 +60,31 @@ struct Cfg {
   static constexpr int kABytes = 128 * KC * 2;
   static constexpr int kBBytes = COUT * KC * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStages = (kStageBytes * 4 + 2048 <= 200 * 1024) ? 4 : 3;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kGroupKb = 128 / KC;      // k-blocks per promotion group (128 K-elements)
+  static constexpr int kBarBytes = 512;          // mbarriers + TMEM slot + scheduler ring
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarBytes;
   static constexpr int kTmemCols = 4 * COUT;     // HH[2] | X[2]
+  static_assert(kStages > kGroupKb, "a promotion group must fit in the stage ring with room to prefetch");
 };
 
 constexpr int kTW = 16, kTH = 8;   // pixel tile: 8 rows x 16 columns = 128 TMEM lanes, lane = th*16 + tw
-constexpr int kConvThreads = 320;  // warps 0-7: promotion + epilogue, warp 8: TMA, warp 9: MMA
+constexpr int kConvThreads = 320;  // warps 0-7: promotion + epilogue, warp 8: TMA + tile scheduler, warp 9: MMA
+constexpr int kSched = 4;          // depth of the tile ring between the scheduler and the other roles
 
-// Promotion + epilogue role of warps 0-3 (TMEM lanes 32*warp .. +31), shared by both conv kernels.
-// Tile = 128 pixels, TWD columns wide (lane = th*TWD + tw); `aux` holds the barriers
-// hh_full[2] | hh_empty[2] | x_full[2] | x_empty[2].  Per tile: add every promoted hi*hi partial
-// (TMEM -> registers, fp32 round-to-nearest), add the cross-term accumulator, then bias, ReLU,
-// optional 2x2 / 2x1 / 1x2 max-pool through warp shuffles, fp16 split, NHWC store.
-template <int COUT, int TWD>
-__device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, int warp8, int lane, int n_tiles,
-                                              int tiles_w, int tiles_h, int TH, int ngroups, int H, int W, int relu,
-                                              int ph, int pw, float promo_scale, const float* __restrict__ bias,
-                                              act_t* __restrict__ out_hi, act_t* __restrict__ out_lo,
-                                              int* __restrict__ ovf) {
-  auto hh_full = [&](int b) { return aux + 8u * b; };
-  auto hh_empty = [&](int b) { return aux + 8u * (2 + b); };
-  auto x_full = [&](int b) { return aux + 8u * (4 + b); };
-  auto x_empty = [&](int b) { return aux + 8u * (6 + b); };
-  // eight warps: warp8 & 3 = TMEM lane quadrant (a warp may only touch lanes 32*(warp % 4)..+31),
-  // warp8 >> 2 = which half of the output channels; each thread keeps COUT / 2 partial sums
-  constexpr int kRowsPerWarp = 32 / TWD;
-  constexpr int CH = COUT / 2;
-  const int warp = warp8 & 3, hsel = warp8 >> 2;
-  const uint32_t lane_base = ((uint32_t)(warp * 32) << 16) + (uint32_t)(hsel * CH);
-  const int th = warp * kRowsPerWarp + lane / TWD, tw = lane % TWD;
-  const int OH = H / ph, OW = W / pw;
-  uint32_t gc = 0, ti = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-    int t = tile;
-    const int w0 = (t % tiles_w) * TWD;
-    t /= tiles_w;
-    const int h0 = (t % tiles_h) * TH;
-    const int n = t / tiles_h;
-    float acc[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) acc[c] = 0.f;
-    for (int g = 0; g < ngroups; ++g, ++gc) {
-      const uint32_t b = gc & 1;
-      mbar_wait(hh_full(b), (gc >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < CH; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_base + b * COUT + (uint32_t)c0, r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(__uint_as_float(r[j]), promo_scale, acc[c0 + j]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(hh_empty(b));
-    }
-    const uint32_t tp = ti & 1;
-    mbar_wait(x_full(tp), (ti >> 1) & 1);
-    tc_fence_after();
-#pragma unroll
-    for (int c0 = 0; c0 < CH; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + lane_base + 2 * COUT + tp * COUT + (uint32_t)c0, r);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(x_empty(tp));
+// One entry of the tile ring (written by the scheduler thread, read by the MMA thread and the
+// eight promotion warps): which tile, and what the epilogue needs to know about its group.
+struct TileEntry {
+  int32_t g, n, h0, w0;       // group (-1 = no more tiles), image, tile origin
+  int32_t H, W, OH, OW;       // input / pooled output dims of the group
+  int64_t out_off;            // first output pixel of the group
+  int64_t pad;
+};
+static_assert(sizeof(TileEntry) == 48, "TileEntry layout");
 
-    const int h = h0 + th, w = w0 + tw;
-    const int oh = h / ph, ow = w / pw;
-    const bool writer = (ph == 1 || (lane & TWD) == 0) && (pw == 1 || (lane & 1) == 0) && oh < OH && ow < OW;
-    const size_t opix = ((size_t)n * OH + oh) * OW + ow;
-#pragma unroll
-    for (int c0 = 0; c0 < CH; c0 += 8) {
-      uint32_t hp[4], lp[4];
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        float v0 = acc[c0 + j] + __ldg(bias + hsel * CH + c0 + j);
-        float v1 = acc[c0 + j + 1] + __ldg(bias + hsel * CH + c0 + j + 1);
-        if (relu) {
-          v0 = fmaxf(v0, 0.f);
-          v1 = fmaxf(v1, 0.f);
-        }
-        if (ph == 2) {
-          v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, TWD));
-          v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, TWD));
-        }
-        if (pw == 2) {
-          v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
-          v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
-        }
-        split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
-      }
-      if (writer) {
-        *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        *reinterpret_cast<uint4*>(out_lo + opix * COUT + hsel * CH + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-      }
-    }
-  }
+__device__ __forceinline__ void fence_tensormap_acquire(const void* p) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(p) : "memory");
 }
 
 // Numerics.  tcgen05.mma truncates its fp32 accumulator toward zero after every instruction
@@ -173,15 +96,32 @@ __device__ __forceinline__ void epilogue_role(uint32_t tmem_base, uint32_t aux, 
 //     cores) every 128 K-elements, double-buffered in TMEM so the tensor pipe never waits.
 // The same warps then run the epilogue (bias, ReLU, optional 2x2 / 2x1 max-pool through warp
 // shuffles, split to fp16 hi/lo, NHWC store) while the MMA warp is already on the next tile.
+//
+// Work distribution.  ONE launch covers every width group of a layer ("ragged"): the groups are
+// separate NHWC tensors, each with its own pair of TMA tensor maps (hi, lo) in a device array, and
+// the persistent CTAs draw 8x16-pixel tiles from a global counter (dynamic scheduling: a CTA that
+// starts late -- its SM was busy with another kernel -- simply takes fewer tiles).  The scheduler is
+// the TMA thread; it publishes each tile through a small shared-memory ring.
+//
+// Issue order inside a promotion group (128 K-elements = kGroupKb k-blocks): first ALL hi*hi MMAs of
+// the group, commit -> the promotion warps start draining that accumulator while the tensor pipe
+// works through the group's 2x as many cross-term MMAs.  The arithmetic (order of accumulation into
+// either accumulator) is the same as issuing them interleaved.
+//
+// dbg (optional, OCRS_B200_CONV_DEBUG=1): per-launch sums over all CTAs of the MMA thread's phases
+// [0] tiles, [1] k-blocks, [2] wait tile ring, [3] wait x_empty, [4] wait hh_empty, [5] wait operands
+// (HH phase), [6] issue HH, [7] issue X + commits, [8] total cycles in the tile loop.
 template <int KC, int COUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
-                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                  const float* __restrict__ bias, act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, int N, int H,
-                  int W, int Cin, int relu, int ph, int pw, float promo_scale, int* __restrict__ ovf) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                  const CUtensorMap* __restrict__ maps, const RaggedDesc* __restrict__ groups, int n_groups,
+                  int n_tiles, int* __restrict__ counter, const float* __restrict__ bias, act_t* __restrict__ out_hi,
+                  act_t* __restrict__ out_lo, int Cin, int relu, int ph, int pw, float promo_scale,
+                  int* __restrict__ ovf, unsigned long long* __restrict__ dbg) {
   using C = Cfg<KC, COUT>;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t base = (smem0 + 1023u) & ~1023u;
   const uint32_t bar_base = base + C::kStages * C::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
@@ -190,11 +130,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   auto hh_empty = [&](int b) { return aux + 8u * (2 + b); };
   auto x_full = [&](int b) { return aux + 8u * (4 + b); };
   auto x_empty = [&](int b) { return aux + 8u * (6 + b); };
-  const uint32_t tmem_slot = aux + 8u * 8;
+  auto sched_full = [&](int s) { return aux + 8u * (8 + s); };
+  auto sched_empty = [&](int s) { return aux + 8u * (8 + kSched + s); };
+  const uint32_t tmem_slot = aux + 8u * (8 + 2 * kSched);
+  const uint32_t ring = tmem_slot + 16u;  // kSched x TileEntry (16-byte aligned)
+  static_assert(8 * (2 * 8 + 8 + 2 * kSched) + 16 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
+  TileEntry* ring_p = reinterpret_cast<TileEntry*>(smem_raw + (ring - smem0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_w = (W + kTW - 1) / kTW, tiles_h = (H + kTH - 1) / kTH;
-  const int n_tiles = N * tiles_h * tiles_w;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -207,6 +150,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       mbar_init(x_full(b), 1);
       mbar_init(x_empty(b), 8);
     }
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(sched_full(s), 1);
+      mbar_init(sched_empty(s), 9);  // MMA thread + 8 promotion warps
+    }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -218,31 +165,60 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
 
   const int chunks = Cin / KC;
   const int nkb = 9 * chunks;
-  const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
 
   if (warp == 8) {
     if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int w0 = (t % tiles_w) * kTW;
-        t /= tiles_w;
-        const int h0 = (t % tiles_h) * kTH;
-        const int n = t / tiles_h;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % C::kStages;
-          const uint32_t par = (it / C::kStages) & 1;
-          mbar_wait(empty_bar(s), par ^ 1);
-          const uint32_t st = base + s * C::kStageBytes;
-          mbar_expect_tx(full_bar(s), C::kStageBytes);
+      // ---------------- tile scheduler + TMA producer ----------------
+      uint32_t stage = 0, par = 0;
+      int cur_g = 0, last_map_g = -1;
+      RaggedDesc gd = groups[0];
+      int t = atomicAdd(counter, 1);
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        mbar_wait(sched_empty(slot), ((ti / kSched) & 1) ^ 1);
+        TileEntry e;
+        e.g = -1;
+        e.n = e.h0 = e.w0 = e.H = e.W = e.OH = e.OW = 0;
+        e.out_off = 0;
+        e.pad = 0;
+        if (t < n_tiles) {
+          while (cur_g + 1 < n_groups && __ldg(&groups[cur_g + 1].first) <= t) {
+            ++cur_g;
+            gd = groups[cur_g];
+          }
+          int l = t - gd.first;
+          e.g = cur_g;
+          e.w0 = (l % gd.tiles_w) * kTW;
+          l /= gd.tiles_w;
+          e.h0 = (l % gd.tiles_h) * kTH;
+          e.n = l / gd.tiles_h;
+          e.H = gd.H; e.W = gd.W; e.OH = gd.OH; e.OW = gd.OW;
+          e.out_off = gd.out_off;
+        }
+        ring_p[slot] = e;
+        mbar_arrive(sched_full(slot));  // release: the entry is visible to whoever sees the phase flip
+        if (e.g < 0) break;
+        const int t_next = atomicAdd(counter, 1);  // in flight while this tile's loads are issued
+        const CUtensorMap* m_hi = maps + 2 * e.g;
+        const CUtensorMap* m_lo = m_hi + 1;
+        if (e.g != last_map_g) {
+          fence_tensormap_acquire(m_hi);
+          fence_tensormap_acquire(m_lo);
+          last_map_g = e.g;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(stage), par ^ 1);
+          const uint32_t st = base + stage * C::kStageBytes;
+          mbar_expect_tx(full_bar(stage), C::kStageBytes);
           const int tap = kb / chunks, c0 = (kb - tap * chunks) * KC;
           const int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d(st, &tm_x_hi, c0, w0 + kw - 1, h0 + kh - 1, n, full_bar(s));
-          tma_load_4d(st + C::kABytes, &tm_x_lo, c0, w0 + kw - 1, h0 + kh - 1, n, full_bar(s));
-          tma_load_2d(st + 2 * C::kABytes, &tm_w_hi, tap * Cin + c0, 0, full_bar(s));
-          tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tm_w_lo, tap * Cin + c0, 0, full_bar(s));
+          tma_load_4d(st, m_hi, c0, e.w0 + kw - 1, e.h0 + kh - 1, e.n, full_bar(stage));
+          tma_load_4d(st + C::kABytes, m_lo, c0, e.w0 + kw - 1, e.h0 + kh - 1, e.n, full_bar(stage));
+          tma_load_2d(st + 2 * C::kABytes, &tm_w_hi, tap * Cin + c0, 0, full_bar(stage));
+          tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tm_w_lo, tap * Cin + c0, 0, full_bar(stage));
+          if (++stage == C::kStages) { stage = 0; par ^= 1; }
         }
+        t = t_next;
       }
     }
   } else if (warp == 9) {
@@ -250,45 +226,188 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       // ---------------- MMA issuer ----------------
       // c_format F32 (bit 4), a/b format F16 (0 at bits 7, 10), N >> 3 at 17, M >> 4 at 24
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
-      uint32_t it = 0, gc = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      uint32_t stage = 0, par = 0, gc = 0;
+      unsigned long long c_sched = 0, c_xe = 0, c_hhe = 0, c_full = 0, c_hh = 0, c_x = 0, n_tiles_done = 0;
+      const bool timing = dbg != nullptr;
+      const long long t_begin = timing ? clock64() : 0;
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        long long c0 = timing ? clock64() : 0;
+        mbar_wait(sched_full(slot), (ti / kSched) & 1);
+        int g;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(g) : "r"(ring + slot * (uint32_t)sizeof(TileEntry)) : "memory");
+        mbar_arrive(sched_empty(slot));
+        if (g < 0) break;
         const uint32_t tp = ti & 1;
         const uint32_t d_x = tmem_base + 2 * COUT + tp * COUT;
+        long long c1 = timing ? clock64() : 0;
         mbar_wait(x_empty(tp), ((ti >> 1) & 1) ^ 1);
-        int kb = 0;
-        for (int g = 0; g < ngroups; ++g, ++gc) {
+        long long c2 = timing ? clock64() : 0;
+        c_sched += (unsigned long long)(c1 - c0);
+        c_xe += (unsigned long long)(c2 - c1);
+        for (int kb = 0; kb < nkb; ++gc) {
           const uint32_t b = gc & 1;
           const uint32_t d_hh = tmem_base + b * COUT;
+          const int nk = min(C::kGroupKb, nkb - kb);
+          long long g0 = timing ? clock64() : 0;
           mbar_wait(hh_empty(b), ((gc >> 1) & 1) ^ 1);
           tc_fence_after();
-          const int kb_end = min(kb + C::kGroupKb, nkb);
-          for (int kb0 = kb; kb < kb_end; ++kb, ++it) {
-            const int s = it % C::kStages;
-            const uint32_t par = (it / C::kStages) & 1;
-            mbar_wait(full_bar(s), par);
+          long long g1 = timing ? clock64() : 0;
+          c_hhe += (unsigned long long)(g1 - g0);
+          // ---- hi*hi MMAs of the whole group ----
+          uint32_t s = stage, p = par;
+          for (int j = 0; j < nk; ++j) {
+            long long w0 = timing ? clock64() : 0;
+            mbar_wait(full_bar(s), p);
             tc_fence_after();
-            const uint32_t st = base + s * C::kStageBytes;
+            if (timing) c_full += (unsigned long long)(clock64() - w0);
             // one descriptor per stage; the other operands and the K steps are byte offsets >> 4 added to its
             // 14-bit start-address field (shared memory ends below 256 KB, so the adds never carry out of it)
-            const uint64_t d0 = make_desc<KC>(st);
+            const uint64_t d0 = make_desc<KC>(base + s * C::kStageBytes);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              const uint64_t da_hi = d0 + (uint64_t)(2 * k);
+              const uint64_t db_hi = da_hi + (uint64_t)((2 * C::kABytes) >> 4);
+              umma_bf16(d_hh, da_hi, db_hi, idesc, (j | k) ? 1u : 0u);
+            }
+            if (++s == C::kStages) { s = 0; p ^= 1; }
+          }
+          umma_commit(hh_full(b));
+          long long g2 = timing ? clock64() : 0;
+          // ---- cross terms of the group; each k-block's stage is released behind its last MMA ----
+          s = stage;
+          for (int j = 0; j < nk; ++j) {
+            const uint64_t d0 = make_desc<KC>(base + s * C::kStageBytes);
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
               const uint64_t da_hi = d0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABytes >> 4);
               const uint64_t db_hi = da_hi + (uint64_t)((2 * C::kABytes) >> 4), db_lo = db_hi + (uint64_t)(C::kBBytes >> 4);
-              umma_bf16(d_hh, da_hi, db_hi, idesc, (kb != kb0 || k) ? 1u : 0u);
-              umma_bf16(d_x, da_hi, db_lo, idesc, (kb | k) ? 1u : 0u);
+              umma_bf16(d_x, da_hi, db_lo, idesc, (kb | j | k) ? 1u : 0u);
               umma_bf16(d_x, da_lo, db_hi, idesc, 1u);
             }
             umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+            if (++s == C::kStages) s = 0;
           }
-          umma_commit(hh_full(b));
+          if (timing) {
+            const long long g3 = clock64();
+            c_hh += (unsigned long long)(g2 - g1);
+            c_x += (unsigned long long)(g3 - g2);
+          }
+          stage = s;
+          par = p;
+          kb += nk;
         }
         umma_commit(x_full(tp));
+        ++n_tiles_done;
+      }
+      if (timing) {
+        atomicAdd(dbg + 0, n_tiles_done);
+        atomicAdd(dbg + 1, n_tiles_done * (unsigned long long)nkb);
+        atomicAdd(dbg + 2, c_sched);
+        atomicAdd(dbg + 3, c_xe);
+        atomicAdd(dbg + 4, c_hhe);
+        atomicAdd(dbg + 5, c_full);
+        atomicAdd(dbg + 6, c_hh - c_full);
+        atomicAdd(dbg + 7, c_x);
+        atomicAdd(dbg + 8, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(dbg + 9, 1ull);
       }
     }
   } else {
-    epilogue_role<COUT, kTW>(tmem_base, aux, warp, lane, n_tiles, tiles_w, tiles_h, kTH, ngroups, H, W, relu, ph, pw,
-                             promo_scale, bias, out_hi, out_lo, ovf);
+    // ---------------- promotion + epilogue: warps 0-7 ----------------
+    // warp & 3 = TMEM lane quadrant (a warp may only touch lanes 32*(warp % 4)..+31), warp >> 2 = which
+    // half of the output channels; each thread keeps COUT / 2 partial sums.
+    constexpr int kRowsPerWarp = 32 / kTW;
+    constexpr int CH = COUT / 2;
+    const int wq = warp & 3, hsel = warp >> 2;
+    const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + (uint32_t)(hsel * CH);
+    const int th = wq * kRowsPerWarp + lane / kTW, tw = lane % kTW;
+    const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
+    uint32_t gc = 0;
+    for (uint32_t ti = 0;; ++ti) {
+      const uint32_t slot = ti & (kSched - 1);
+      mbar_wait(sched_full(slot), (ti / kSched) & 1);
+      const TileEntry e = ring_p[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sched_empty(slot));
+      if (e.g < 0) break;
+      float acc[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+      for (int g = 0; g < ngroups; ++g, ++gc) {
+        const uint32_t b = gc & 1;
+        mbar_wait(hh_full(b), (gc >> 1) & 1);
+        tc_fence_after();
+        if constexpr (CH == 64) {
+          // both TMEM loads of the group in flight before the single wait
+          uint32_t r0[32], r1[32];
+          tmem_ld32_issue(tmem_base + lane_base + b * COUT, r0);
+          tmem_ld32_issue(tmem_base + lane_base + b * COUT + 32u, r1);
+          tmem_wait_ld();
+          reg_fence32(r0);
+          reg_fence32(r1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(r0[j]), promo_scale, acc[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[32 + j] = fmaf(__uint_as_float(r1[j]), promo_scale, acc[32 + j]);
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < CH; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + b * COUT + (uint32_t)c0, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(__uint_as_float(r[j]), promo_scale, acc[c0 + j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hh_empty(b));
+      }
+      const uint32_t tp = ti & 1;
+      mbar_wait(x_full(tp), (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < CH; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + 2 * COUT + tp * COUT + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_empty(tp));
+
+      const int h = e.h0 + th, w = e.w0 + tw;
+      const int oh = h / ph, ow = w / pw;
+      const bool writer = (ph == 1 || (lane & kTW) == 0) && (pw == 1 || (lane & 1) == 0) && oh < e.OH && ow < e.OW;
+      const size_t opix = (size_t)e.out_off + ((size_t)e.n * e.OH + oh) * e.OW + ow;
+#pragma unroll
+      for (int c0 = 0; c0 < CH; c0 += 8) {
+        uint32_t hp[4], lp[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          float v0 = acc[c0 + j] + __ldg(bias + hsel * CH + c0 + j);
+          float v1 = acc[c0 + j + 1] + __ldg(bias + hsel * CH + c0 + j + 1);
+          if (relu) {
+            v0 = fmaxf(v0, 0.f);
+            v1 = fmaxf(v1, 0.f);
+          }
+          if (ph == 2) {
+            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, kTW));
+            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, kTW));
+          }
+          if (pw == 2) {
+            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
+            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
+          }
+          split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
+        }
+        if (writer) {
+          *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(out_lo + opix * COUT + hsel * CH + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        }
+      }
+    }
   }
   __syncwarp();
   tc_fence_before();
@@ -340,20 +459,35 @@ __global__ void nhwc_split_to_nchw_kernel(const act_t* __restrict__ hi, const ac
   }
 }
 
+__device__ __forceinline__ int find_group(const RaggedDesc* __restrict__ g, int n, int key) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&g[mid].first) <= key) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ragged over width groups: block -> group by `first`; one thread per (n, w, 8-channel group): mean over
+// h, written at row out_off + w*N + n of the packed [rows, C] feature matrix
 __global__ void nhwc_split_avg_to_seq_kernel(const act_t* __restrict__ hi, const act_t* __restrict__ lo,
-                                             float* __restrict__ y, int N, int C, int H, int W) {
-  // one thread per (n, w, 8-channel group): mean over h, written at [w][n][c]
-  const int groups = C / 8;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)N * W * groups) return;
-  const int g = (int)(idx % groups);
-  const int w = (int)((idx / groups) % W);
-  const int n = (int)(idx / ((int64_t)groups * W));
+                                             float* __restrict__ y, int C, const RaggedDesc* __restrict__ groups,
+                                             int n_groups) {
+  const int gi = find_group(groups, n_groups, blockIdx.x);
+  const RaggedDesc d = groups[gi];
+  const int N = d.N, H = d.H, W = d.W;
+  const int cg = C / 8;
+  const int64_t idx = (int64_t)(blockIdx.x - d.first) * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * W * cg) return;
+  const int g = (int)(idx % cg);
+  const int w = (int)((idx / cg) % W);
+  const int n = (int)(idx / ((int64_t)cg * W));
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (int h = 0; h < H; ++h) {
-    const int64_t pix = ((int64_t)n * H + h) * W + w;
+    const int64_t pix = d.in_off + ((int64_t)n * H + h) * W + w;
     const uint4 vh = *reinterpret_cast<const uint4*>(hi + pix * C + g * 8);
     const uint4 vl = *reinterpret_cast<const uint4*>(lo + pix * C + g * 8);
     const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
@@ -364,7 +498,7 @@ __global__ void nhwc_split_avg_to_seq_kernel(const act_t* __restrict__ hi, const
     }
   }
   const float inv = (float)H;
-  float4* dst = reinterpret_cast<float4*>(y + ((int64_t)w * N + n) * C + g * 8);
+  float4* dst = reinterpret_cast<float4*>(y + (d.out_off + (int64_t)w * N + n) * C + g * 8);
   dst[0] = make_float4(acc[0] / inv, acc[1] / inv, acc[2] / inv, acc[3] / inv);
   dst[1] = make_float4(acc[4] / inv, acc[5] / inv, acc[6] / inv, acc[7] / inv);
 }
@@ -411,19 +545,24 @@ __global__ void maxpool_nhwc_split_kernel(const act_t* __restrict__ x_hi, const 
   *reinterpret_cast<uint4*>(y_lo + opix * C + g * 8) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
 }
 
-// one thread = one pooled output pixel, all Cout channels (weights broadcast from shared memory)
+// one thread = one pooled output pixel, all Cout channels (weights broadcast from shared memory);
+// ragged over width groups (block -> group by `first`)
 template <int COUT>
 __global__ void __launch_bounds__(128)
 stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
-            act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, int N, int H, int W, int* __restrict__ ovf) {
+            act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, const RaggedDesc* __restrict__ groups, int n_groups,
+            int* __restrict__ ovf) {
   __shared__ float sw[COUT * 9 + COUT];
   for (int i = threadIdx.x; i < COUT * 10; i += blockDim.x) sw[i] = i < COUT * 9 ? wgt[i] : bias[i - COUT * 9];
   __syncthreads();
+  const int gi = find_group(groups, n_groups, blockIdx.x);
+  const RaggedDesc d = groups[gi];
+  const int H = d.H, W = d.W;
   const int OH = H / 2, OW = W / 2;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)N * OH * OW) return;
+  const int64_t idx = (int64_t)(blockIdx.x - d.first) * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)d.N * OH * OW) return;
   const int ow = (int)(idx % OW), oh = (int)((idx / OW) % OH), n = (int)(idx / ((int64_t)OW * OH));
-  const float* xi = x + (int64_t)n * H * W;
+  const float* xi = x + d.in_off + (int64_t)n * H * W;
   float p[4][4];  // input patch rows 2oh-1 .. 2oh+2, cols 2ow-1 .. 2ow+2 (zero padded)
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -434,8 +573,8 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const fl
       p[r][c] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xi + (int64_t)ih * W + iw) : 0.f;
     }
   }
-  act_t* oh_ptr = out_hi + idx * COUT;
-  act_t* ol_ptr = out_lo + idx * COUT;
+  act_t* oh_ptr = out_hi + (d.out_off + idx) * COUT;
+  act_t* ol_ptr = out_lo + (d.out_off + idx) * COUT;
 #pragma unroll 1
   for (int c8 = 0; c8 < COUT; c8 += 8) {
     uint32_t ph[4], pl[4];
@@ -496,17 +635,17 @@ float promo_scale() {
   return s;
 }
 
+bool conv_debug() {
+  static const bool on = std::getenv("OCRS_B200_CONV_DEBUG") != nullptr;
+  return on;
+}
+
 template <int KC, int COUT>
-void launch_conv(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, act_t* y_hi,
-                 act_t* y_lo, int N, int H, int W, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
+void launch_conv(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
+                 const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
   using C = Cfg<KC, COUT>;
   const int Cin = w.Cin;
   const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-  uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-  uint32_t xb[4] = {(uint32_t)KC, (uint32_t)kTW, (uint32_t)kTH, 1};
-  CUtensorMap tm_x_hi = make_map(x_hi, 4, xd, xs, xb, swz);
-  CUtensorMap tm_x_lo = make_map(x_lo, 4, xd, xs, xb, swz);
   uint64_t wd[2] = {(uint64_t)9 * Cin, (uint64_t)COUT};
   uint64_t ws[1] = {(uint64_t)9 * Cin * 2};
   uint32_t wb[2] = {(uint32_t)KC, (uint32_t)COUT};
@@ -514,16 +653,31 @@ void launch_conv(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, a
   CUtensorMap tm_w_lo = make_map(w.w_lo.ptr, 2, wd, ws, wb, swz);
   OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::kSmemBytes));  // per-device attribute, cheap to repeat
-  const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
-  // launched as clusters of 2 (no cluster-level protocol: the CTAs are independent).  The pair is
-  // placed on the two SMs of one TPC and walks neighbouring tiles in near lock step; measured 4-7 %
-  // faster per layer than the same grid without the cluster attribute.
-  const int grid = std::max(2, std::min((tiles + 1) / 2 * 2, sm_count() / 2 * 2));
-  conv3x3_tc_kernel<KC, COUT><<<grid, kConvThreads, C::kSmemBytes, st>>>(tm_x_hi, tm_x_lo, tm_w_hi, tm_w_lo,
-                                                                           w.bias.as<float>(), y_hi, y_lo, N, H, W, Cin,
-                                                                           relu, ph, pw, promo_scale(), ovf);
+  // persistent CTAs, launched as clusters of 2 (no cluster-level protocol: the CTAs are independent; the
+  // pair sits on the two SMs of one TPC, measured 4-7 % faster per layer than without the attribute)
+  const int grid = std::max(2, std::min((n_tiles + 1) / 2 * 2, sm_count() / 2 * 2));
+  unsigned long long* d_dbg = nullptr;
+  if (conv_debug()) {
+    OCRS_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_dbg), 16 * sizeof(unsigned long long), st));
+    OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 16 * sizeof(unsigned long long), st));
+  }
+  conv3x3_tc_kernel<KC, COUT><<<grid, kConvThreads, C::kSmemBytes, st>>>(
+      tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles, d_counter, w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph, pw,
+      promo_scale(), ovf, d_dbg);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
+  if (d_dbg) {
+    unsigned long long h[16];
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OCRS_CUDA_CHECK(cudaFreeAsync(d_dbg, st));
+    const double kb = (double)std::max<unsigned long long>(h[1], 1), ctas = (double)std::max<unsigned long long>(h[9], 1);
+    fprintf(stderr,
+            "[conv dbg] Cin %d Cout %d pool %dx%d: %llu tiles, %d groups, %.0f CTAs | per k-block (cycles): ring %.0f, x_empty %.0f, "
+            "hh_empty %.0f, operands %.0f, issue HH %.0f, issue X %.0f | loop total %.0f (per CTA %.0f cycles)\n",
+            Cin, COUT, ph, pw, h[0], n_groups, ctas, h[2] / kb, h[3] / kb, h[4] / kb, h[5] / kb, h[6] / kb, h[7] / kb, h[8] / kb,
+            h[8] / ctas);
+  }
 }
 
 }  // namespace
@@ -565,15 +719,36 @@ std::unique_ptr<StemWeights> prepare_stem(const float* w, const float* b, int Co
   return s;
 }
 
+void stem_ragged(const float* x, const StemWeights& w, act_t* y_hi, act_t* y_lo, const RaggedDesc* d_groups, int n_groups,
+                 int n_blocks, int* ovf, cudaStream_t st) {
+  if (n_blocks == 0) return;
+  if (w.Cout == 32)
+    stem_kernel<32><<<(unsigned)n_blocks, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, d_groups, n_groups, ovf);
+  else
+    stem_kernel<64><<<(unsigned)n_blocks, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, d_groups, n_groups, ovf);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+namespace {
+// stream-ordered upload of a small host blob (pageable source: the runtime stages it before returning)
+void* upload_async(const void* host, size_t bytes, cudaStream_t st) {
+  void* d = nullptr;
+  OCRS_CUDA_CHECK(cudaMallocAsync(&d, bytes, st));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st));
+  return d;
+}
+}  // namespace
+
 void stem_conv_relu_pool2(const float* x, const StemWeights& w, act_t* y_hi, act_t* y_lo, int N, int H,
                           int W, int* ovf, cudaStream_t st) {
   int64_t total = (int64_t)N * (H / 2) * (W / 2);
   if (!total) return;
-  unsigned grid = (unsigned)ceil_div(total, 128);
-  if (w.Cout == 32) stem_kernel<32><<<grid, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, N, H, W, ovf);
-  else stem_kernel<64><<<grid, 128, 0, st>>>(x, w.w.as<float>(), w.bias.as<float>(), y_hi, y_lo, N, H, W, ovf);
-  count_launch();
-  OCRS_CUDA_CHECK(cudaGetLastError());
+  RaggedDesc d{};
+  d.N = N; d.H = H; d.W = W; d.OH = H / 2; d.OW = W / 2;
+  auto* dd = static_cast<RaggedDesc*>(upload_async(&d, sizeof(d), st));
+  stem_ragged(x, w, y_hi, y_lo, dd, 1, (int)ceil_div(total, 128), ovf, st);
+  OCRS_CUDA_CHECK(cudaFreeAsync(dd, st));
 }
 
 std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, int Cin, int Cout) {
@@ -605,16 +780,48 @@ std::unique_ptr<ConvWeightsTC> prepare_weights(const float* w, const float* b, i
   return out;
 }
 
+int conv_tiles(int N, int H, int W) { return N * (int)ceil_div(H, kTH) * (int)ceil_div(W, kTW); }
+
+void conv_fill_tiles(RaggedDesc* d) {
+  d->tiles_w = (int)ceil_div(d->W, kTW);
+  d->tiles_h = (int)ceil_div(d->H, kTH);
+}
+
+void make_act_maps(const act_t* hi, const act_t* lo, int N, int H, int W, int Cin, CUtensorMap out[2]) {
+  const int KC = (Cin % 64 == 0) ? 64 : 32;
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  uint32_t xb[4] = {(uint32_t)KC, (uint32_t)kTW, (uint32_t)kTH, 1};
+  out[0] = make_map(hi, 4, xd, xs, xb, swz);
+  out[1] = make_map(lo, 4, xd, xs, xb, swz);
+}
+
+void conv3x3_ragged(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
+                    const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
+  if (n_tiles == 0 || n_groups == 0) return;
+  OCRS_CHECK((ph == 1 || ph == 2) && (pw == 1 || pw == 2), kInternal, "conv3x3 (tensor core): fused pool must be 1 or 2");
+  const bool k64 = (w.Cin % 64 == 0);
+  if (k64 && w.Cout == 128) launch_conv<64, 128>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+  else if (k64 && w.Cout == 64) launch_conv<64, 64>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+  else if (!k64 && w.Cout == 128) launch_conv<32, 128>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+  else if (!k64 && w.Cout == 64) launch_conv<32, 64>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+  else throw Error(kInternal, "conv3x3 (tensor core): unsupported channel configuration");
+}
+
 void conv3x3(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, act_t* y_hi,
              act_t* y_lo, int N, int H, int W, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
   if (N == 0 || H == 0 || W == 0) return;
-  OCRS_CHECK((ph == 1 || ph == 2) && (pw == 1 || pw == 2), kInternal, "conv3x3 (tensor core): fused pool must be 1 or 2");
-  const bool k64 = (w.Cin % 64 == 0);
-  if (k64 && w.Cout == 128) launch_conv<64, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ph, pw, ovf, st);
-  else if (k64 && w.Cout == 64) launch_conv<64, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ph, pw, ovf, st);
-  else if (!k64 && w.Cout == 128) launch_conv<32, 128>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ph, pw, ovf, st);
-  else if (!k64 && w.Cout == 64) launch_conv<32, 64>(x_hi, x_lo, w, y_hi, y_lo, N, H, W, relu, ph, pw, ovf, st);
-  else throw Error(kInternal, "conv3x3 (tensor core): unsupported channel configuration");
+  // one-group ragged launch: [maps hi, lo | desc | counter] in one stream-ordered blob
+  struct Blob { CUtensorMap maps[2]; RaggedDesc d; int counter; int pad[3]; } blob;
+  make_act_maps(x_hi, x_lo, N, H, W, w.Cin, blob.maps);
+  blob.d = RaggedDesc{};
+  blob.d.N = N; blob.d.H = H; blob.d.W = W; blob.d.OH = H / ph; blob.d.OW = W / pw;
+  conv_fill_tiles(&blob.d);
+  blob.counter = 0;
+  auto* dev = static_cast<Blob*>(upload_async(&blob, sizeof(blob), st));
+  conv3x3_ragged(dev->maps, &dev->d, 1, conv_tiles(N, H, W), &dev->counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+  OCRS_CUDA_CHECK(cudaFreeAsync(dev, st));
 }
 
 void nchw_to_nhwc_split(const float* x, act_t* hi, act_t* lo, int N, int C, int H, int W, int* ovf,
@@ -637,13 +844,23 @@ void nhwc_split_to_nchw(const act_t* hi, const act_t* lo, float* y, int N, int C
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
-void nhwc_split_avg_to_seq(const act_t* hi, const act_t* lo, float* y, int N, int C, int H, int W, cudaStream_t st) {
+void avg_to_seq_ragged(const act_t* hi, const act_t* lo, float* y, int C, const RaggedDesc* d_groups, int n_groups,
+                       int n_blocks, cudaStream_t st) {
   OCRS_CHECK(C % 8 == 0, kInternal, "nhwc_split_avg_to_seq: C must be a multiple of 8");
-  int64_t total = (int64_t)N * W * (C / 8);
-  if (!total) return;
-  nhwc_split_avg_to_seq_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(hi, lo, y, N, C, H, W);
+  if (n_blocks == 0) return;
+  nhwc_split_avg_to_seq_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(hi, lo, y, C, d_groups, n_groups);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void nhwc_split_avg_to_seq(const act_t* hi, const act_t* lo, float* y, int N, int C, int H, int W, cudaStream_t st) {
+  int64_t total = (int64_t)N * W * (C / 8);
+  if (!total) return;
+  RaggedDesc d{};
+  d.N = N; d.H = H; d.W = W; d.OH = 1; d.OW = W;
+  auto* dd = static_cast<RaggedDesc*>(upload_async(&d, sizeof(d), st));
+  avg_to_seq_ragged(hi, lo, y, C, dd, 1, (int)ceil_div(total, 256), st);
+  OCRS_CUDA_CHECK(cudaFreeAsync(dd, st));
 }
 
 void maxpool_nhwc_split(const act_t* x_hi, const act_t* x_lo, act_t* y_hi,

@@ -10,6 +10,7 @@
 // Replaces rten's Conv operator kernels (reached through `Model::run`, ocrs/src/model.rs:33-40)
 // for the layers where `group == 1`, kernel 3x3, stride 1, pad 1 and C_in is a multiple of 32.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -59,6 +60,34 @@ bool stem_supported(int Cin, int Cout, int R, int S, int stride_h, int stride_w,
 std::unique_ptr<StemWeights> prepare_stem(const float* w, const float* b, int Cout);
 void stem_conv_relu_pool2(const float* x, const StemWeights& w, act_t* y_hi, act_t* y_lo, int N, int H,
                           int W, int* ovf, cudaStream_t st);
+
+// ---- ragged execution over width groups ---------------------------------------------------------
+// The recognition batch is a set of width groups (recognition.rs:431-459), each its own NHWC tensor.
+// One launch per layer covers all of them: every group has one RaggedDesc per layer (device array,
+// ordered by `first`) and, for the tensor-core layers, a pair of TMA tensor maps (hi, lo planes).
+struct RaggedDesc {
+  int32_t N, H, W;           // input dims of this layer for the group
+  int32_t OH, OW;            // output dims (after the fused pool)
+  int32_t tiles_w, tiles_h;  // conv: 8x16-pixel tiles per image
+  int32_t first;             // first tile (conv) / first thread block (stem, tail) of the group in the launch
+  int64_t in_off;            // stem: first f32 element of the group's [N,1,H,W] input; tail: first input pixel
+  int64_t out_off;           // first output pixel (NHWC) of the group; tail: first row of the packed [rows, C] output
+};
+static_assert(sizeof(RaggedDesc) == 48, "RaggedDesc layout");
+
+int conv_tiles(int N, int H, int W);      // tiles of one group in a conv launch
+void conv_fill_tiles(RaggedDesc* d);      // sets tiles_w / tiles_h from H / W
+// TMA tensor maps {hi, lo} of a group's NHWC input [N,H,W,Cin] (host side; copy them to the device array).
+void make_act_maps(const act_t* hi, const act_t* lo, int N, int H, int W, int Cin, CUtensorMap out[2]);
+// d_maps: device [2 * n_groups]; d_counter: device int, zero before the launch (tile scheduler).
+void conv3x3_ragged(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
+                    const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st);
+// blocks of 128 threads, one thread per pooled output pixel: n_blocks = sum over groups of ceil(N*OH*OW / 128)
+void stem_ragged(const float* x, const StemWeights& w, act_t* y_hi, act_t* y_lo, const RaggedDesc* d_groups, int n_groups,
+                 int n_blocks, int* ovf, cudaStream_t st);
+// blocks of 256 threads, one thread per (n, w, 8 channels): n_blocks = sum over groups of ceil(N*W*C/8 / 256)
+void avg_to_seq_ragged(const act_t* hi, const act_t* lo, float* y, int C, const RaggedDesc* d_groups, int n_groups,
+                       int n_blocks, cudaStream_t st);
 
 // Layout / precision converters and the pooling used between tensor-core layers.
 void nchw_to_nhwc_split(const float* x, act_t* hi, act_t* lo, int N, int C, int H, int W, int* ovf,

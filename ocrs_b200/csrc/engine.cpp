@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <exception>
 #include <map>
@@ -66,6 +67,7 @@ struct Engine::HostTimer {
   HostTimer(Engine* eng, const char* n) : e(eng), name(n), t0(std::chrono::steady_clock::now()) {}
   ~HostTimer() {
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> lk(e->host_mu_);  // timers run inside and outside mu_ (ocr_pages): own lock
     auto& slot = e->host_ms_[name];
     slot.first += ms;
     slot.second += 1;
@@ -198,6 +200,7 @@ std::string Engine::profile_json(bool reset) {
     j += buf;
     first = false;
   }
+  std::lock_guard<std::mutex> hlk(host_mu_);
   for (const auto& kv : host_ms_) {
     char buf[256];
     snprintf(buf, sizeof(buf), "%s\"host/%s\": {\"ms\": %.6f, \"calls\": %lld, \"launches\": 0, \"flops\": 0, \"bytes\": 0}",
@@ -302,7 +305,12 @@ std::vector<float> Engine::detect_text_pixels(const OcrInput& in) {
   det_in_.reserve((size_t)in_h * in_w * 4);
   img::resize_padded(in.grey(), H, W, H + pad_bottom, W + pad_right, img::kBlackValue, det_in_.as<float>(),
                      in_h, in_w, 1, 0, 0, st_);
+  int tok = det_->tc_token();
   DTensor out = det_->run(wrap_tensor(det_in_.as<float>(), {1, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_);
+  if (tok) {  // tensor-core chains in the detection model: check the fp16 range flag, rerun in fp32 if raised
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+    if (det_->take_tc_overflow(tok)) out = det_->run(wrap_tensor(det_in_.as<float>(), {1, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_);
+  }
   OCRS_CHECK(out.shape.size() == 4 && out.numel() == (int64_t)in_h * in_w, kWrongOutput,
              "detection output must be [1,1,H,W]");
   PageScratch& s = scratch_for(0, H, W);
@@ -318,6 +326,15 @@ std::vector<float> Engine::detect_text_pixels(const OcrInput& in) {
 std::vector<std::vector<RotatedRect>> Engine::detect_words(const std::vector<const OcrInput*>& pages) {
   OCRS_CHECK(det_ != nullptr, kModelNotLoaded, "Detection model not loaded");  // lib.rs:197
   std::lock_guard<std::mutex> lk(mu_);
+  const int tok = det_->tc_token();
+  auto result = detect_words_locked(pages);
+  // a detection model with tensor-core-eligible convolutions whose activations left the fp16 range: the
+  // model has switched itself to the fp32 kernels, repeat the call once (as recognize_text does)
+  if (det_->take_tc_overflow(tok)) result = detect_words_locked(pages);
+  return result;
+}
+
+std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vector<const OcrInput*>& pages) {
   OCRS_CUDA_CHECK(cudaSetDevice(device_));
   const int N = (int)pages.size();
   std::vector<std::vector<RotatedRect>> result((size_t)N);
@@ -427,10 +444,11 @@ std::vector<std::vector<TextLine>> Engine::recognize_text(
   OCRS_CHECK(rec_ != nullptr, kModelNotLoaded, "Recognition model not loaded");  // lib.rs:254
   OCRS_CHECK(pages.size() == lines_per_page.size(), kInvalidArg, "pages / lines size mismatch");
   std::lock_guard<std::mutex> lk(mu_);
+  const int tok = rec_->tc_token();
   auto result = recognize_text_locked(pages, lines_per_page);
   // split-fp16 range overflow in the tensor-core convolutions: the model has switched itself to
   // the fp32 kernels, repeat the call once
-  if (rec_->take_tc_overflow()) result = recognize_text_locked(pages, lines_per_page);
+  if (rec_->take_tc_overflow(tok)) result = recognize_text_locked(pages, lines_per_page);
   return result;
 }
 
@@ -618,9 +636,55 @@ std::vector<std::vector<TextLine>> Engine::recognize_text_locked(
     OCRS_CHECK((size_t)rec_->seq_head_classes() == n_classes, kWrongOutput,
                "output column count (" + std::to_string(rec_->seq_head_classes()) + ") does not match alphabet size (" +
                    std::to_string(n_classes) + ")");
+    const int Cf = rec_->seq_head_channels();
+    if (rec_->has_packed_prefix(rec_h)) {
+      // ---- ragged path: every layer of the conv prefix runs once over all width groups; the packed
+      // sequence head follows.  Passes bound the activation memory of huge calls (normally one pass). ----
+      size_t ci = 0;
+      while (ci < chunks.size()) {
+        size_t ce = ci;
+        int64_t bytes = 0;
+        std::vector<Model::PrefixGroup> pg;
+        while (ce < chunks.size()) {
+          const Chunk& c = chunks[ce];
+          const int64_t b = (int64_t)32 * rec_h * c.gw * 4 * c.count;
+          if (!pg.empty() && bytes + b > kMaxActBytes) break;
+          bytes += b;
+          Model::PrefixGroup g;
+          g.x_base = rec_batch_.as<float>();
+          g.x_off = descs[c.first].dst_off;
+          g.N = c.count;
+          g.W = c.gw;
+          pg.push_back(g);
+          ++ce;
+        }
+        std::vector<Model::PackedGroup> groups;
+        ModelCost cost;
+        int tkr = prof_.begin("stage/rec_prefix", st_);
+        DTensor x = rec_->run_prefix_packed(pg, rec_h, st_, &groups, &cost, &prof_, "rec/");
+        prof_.end(tkr, st_, cost.flops, 0);
+        stats_.rec_flops += cost.flops;
+        stats_.rec_batches += 1;
+        OCRS_CHECK(x.shape.size() == 2 && x.shape[1] == Cf, kWrongOutput, "recognition feature rows must be [rows, C]");
+        const int64_t rows = x.shape[0];
+        ModelCost hcost;
+        int tkh = prof_.begin("stage/rec_seq_head", st_);
+        DTensor logits = rec_->run_seq_head(x.data, rows, groups, st_, &hcost, &prof_, "rec/");
+        prof_.end(tkh, st_, hcost.flops, 0);
+        stats_.rec_flops += hcost.flops;
+        std::vector<img::CtcLine> cl;
+        for (size_t k = ci; k < ce; ++k) {
+          chunks[k].T = groups[k - ci].T;
+          chunk_lines(chunks[k], groups[k - ci].row_off, &cl);
+        }
+        decode_lines(logits.data, rows, std::move(cl));
+        feats.push_back(std::move(x));       // alive until the final synchronisation below
+        feats.push_back(std::move(logits));
+        ci = ce;
+      }
+    } else {
     std::vector<Model::PackedGroup> groups;
     int64_t rows = 0;
-    const int Cf = rec_->seq_head_channels();
     // the per-group conv prefixes are independent and individually too small to fill 148 SMs:
     // spread them over side streams, join before the packed head
     const int n_aux = prof_.enabled ? 1 : (int)std::min<size_t>(chunks.size(), 6);
@@ -662,6 +726,7 @@ std::vector<std::vector<TextLine>> Engine::recognize_text_locked(
     cl.reserve((size_t)n_lines);
     for (size_t g = 0; g < chunks.size(); ++g) chunk_lines(chunks[g], groups[g].row_off, &cl);
     decode_lines(logits.data, rows, std::move(cl));
+    }
   } else {
     for (auto& c : chunks) {
       float* in_ptr = rec_batch_.as<float>() + descs[c.first].dst_off;
@@ -772,19 +837,23 @@ std::vector<std::vector<TextLine>> Engine::ocr_pages(const std::vector<const Ocr
   auto words = detect_words(pages);
   std::vector<std::vector<std::vector<RotatedRect>>> lines(pages.size());
   {
-    // layout analysis is pure host code and independent per page: one thread per page
+    // layout analysis is pure host code and independent per page: a few threads share the pages
     HostTimer ht(this, "find_text_lines");
-    if (pages.size() <= 1) {
+    const size_t nt = std::min<size_t>(pages.size(), (size_t)std::max(1, layout_threads_));
+    if (nt <= 1) {
       for (size_t p = 0; p < pages.size(); ++p) lines[p] = layout::find_text_lines(words[p]);
     } else {
       std::vector<std::thread> pool;
       std::vector<std::exception_ptr> errs(pages.size());
-      for (size_t p = 0; p < pages.size(); ++p)
-        pool.emplace_back([&, p] {
-          try {
-            lines[p] = layout::find_text_lines(words[p]);
-          } catch (...) {
-            errs[p] = std::current_exception();
+      std::atomic<size_t> next{0};
+      for (size_t t = 0; t < nt; ++t)
+        pool.emplace_back([&] {
+          for (size_t p = next.fetch_add(1); p < pages.size(); p = next.fetch_add(1)) {
+            try {
+              lines[p] = layout::find_text_lines(words[p]);
+            } catch (...) {
+              errs[p] = std::current_exception();
+            }
           }
         });
       for (auto& t : pool) t.join();

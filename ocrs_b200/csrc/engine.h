@@ -82,6 +82,7 @@ class Engine {
   std::vector<std::vector<TextLine>> recognize_text(
       const std::vector<const OcrInput*>& pages,
       const std::vector<std::vector<std::vector<geom::RotatedRect>>>& lines_per_page);
+  std::vector<std::vector<geom::RotatedRect>> detect_words_locked(const std::vector<const OcrInput*>& pages);  // caller holds mu_
   std::vector<std::vector<TextLine>> recognize_text_locked(
       const std::vector<const OcrInput*>& pages,
       const std::vector<std::vector<std::vector<geom::RotatedRect>>>& lines_per_page);  // caller holds mu_
@@ -104,6 +105,8 @@ class Engine {
   Stats stats() const { return stats_; }
   void reset_stats() { stats_ = Stats(); }
   void synchronize();
+  // host threads used by ocr_pages for layout analysis (pages of a batch in parallel); default 8
+  void set_layout_threads(int n) { layout_threads_ = n < 1 ? 1 : n; }
 
   // CUDA-event profiling of stages and of every operator of the two networks
   void set_profiling(bool on);
@@ -142,7 +145,9 @@ class Engine {
   cudaEvent_t ev_fork_ = nullptr;
   void ensure_aux(int n);
   int64_t d2h_bytes_ = 0, h2d_bytes_ = 0;
+  int layout_threads_ = 8;
   std::map<std::string, std::pair<double, int64_t>> host_ms_;  // host-side section timers (ms, calls)
+  std::mutex host_mu_;                                         // guards host_ms_ only
   struct HostTimer;
 };
 

@@ -200,6 +200,7 @@ struct Model::Impl {
   std::map<int, HeadFuse> head_fuse; // per ConvTranspose node: fused 1x1 conv + sigmoid
   bool tc_enabled = false;
   std::atomic<bool> tc_conv_on{true};  // cleared for good after an fp16 range overflow
+  std::mutex ovf_mu;                    // serialises the flag read / switch-off in take_tc_overflow
   DeviceBuffer tc_ovf;                  // int32 flag written by the split-fp16 kernels
 };
 
@@ -642,10 +643,13 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
   };
 
   std::vector<char> dyn_skip(g.nodes.size(), 0);  // nodes absorbed by a run-time fusion of this run
+  // one decision for the whole graph walk: another thread's overflow may switch the chains off while this
+  // run is in flight (the run then finishes on the tensor cores and is caught by take_tc_overflow(token))
+  const bool tc_on = impl->tc_conv_on.load(std::memory_order_acquire);
   for (int ni = 0; ni < (int)g.nodes.size(); ++ni) {
-    if (skip_[ni] || dyn_skip[ni] || (impl->tc_member[ni] && impl->tc_conv_on.load(std::memory_order_relaxed))) continue;
+    if (skip_[ni] || dyn_skip[ni] || (impl->tc_member[ni] && tc_on)) continue;
     const Node& n = g.nodes[ni];
-    auto chain_it = impl->tc_conv_on.load(std::memory_order_relaxed) ? impl->tc_chains.find(ni) : impl->tc_chains.end();
+    auto chain_it = tc_on ? impl->tc_chains.find(ni) : impl->tc_chains.end();
     if (chain_it != impl->tc_chains.end()) {
       int* ovf = impl->tc_ovf.as<int>();
       // ---- Conv3x3(+ReLU)(+MaxPool) chain on the tensor cores (NHWC split-fp16) ----
@@ -1234,13 +1238,23 @@ bool Model::has_seq_head() const { return impl_->head.present; }
 int Model::seq_head_channels() const { return impl_->head.C; }
 int Model::seq_head_classes() const { return impl_->head.classes; }
 
-bool Model::take_tc_overflow() const {
+int Model::tc_token() const {
+  const Impl* impl = impl_.get();
+  return (impl->tc_enabled && impl->tc_ovf.ptr && impl->tc_conv_on.load(std::memory_order_acquire)) ? 1 : 0;
+}
+
+bool Model::take_tc_overflow(int token) const {
   Impl* impl = impl_.get();
-  if (!impl->tc_enabled || !impl->tc_ovf.ptr || !impl->tc_conv_on.load()) return false;
+  if (token == 0) return false;  // the run started on the fp32 kernels: nothing to check
+  // the run started with the tensor-core chains on.  If another run has switched them off in the meantime,
+  // this run's output may be saturated too (the flag it raised may already have been consumed): repeat it.
+  if (!impl->tc_conv_on.load(std::memory_order_acquire)) return true;
+  std::lock_guard<std::mutex> lk(impl->ovf_mu);
+  if (!impl->tc_conv_on.load(std::memory_order_acquire)) return true;
   int flag = 0;
   OCRS_CUDA_CHECK(cudaMemcpy(&flag, impl->tc_ovf.ptr, 4, cudaMemcpyDeviceToHost));
   if (!flag) return false;
-  impl->tc_conv_on.store(false);
+  impl->tc_conv_on.store(false, std::memory_order_release);
   OCRS_CUDA_CHECK(cudaMemset(impl->tc_ovf.ptr, 0, 4));
   return true;
 }
@@ -1249,6 +1263,184 @@ DTensor Model::run_prefix(const DTensor& input, cudaStream_t st, ModelCost* cost
                           const std::string& prof_prefix) const {
   OCRS_CHECK(impl_->head.present, kInternal, "run_prefix: model has no packed sequence head");
   return run(input, st, cost, prof, prof_prefix, &impl_->head.x_name);
+}
+
+// The packed conv prefix: graph input -> [stem + tensor-core conv chain + pooling tail] -> X_seq, i.e. the
+// whole prefix is one TcChain.  Then every layer runs ONCE over all width groups (ragged launches).
+static const TcChain* packed_chain(const Model::Impl* impl, const onnx::Graph& g);
+
+bool Model::has_packed_prefix(int in_h) const {
+  const Impl* impl = impl_.get();
+  if (!impl->head.present || !impl->tc_conv_on.load(std::memory_order_relaxed)) return false;
+  if (std::getenv("OCRS_B200_DISABLE_RAGGED") != nullptr) return false;
+  const TcChain* ch = packed_chain(impl, graph_);
+  if (!ch) return false;
+  int h = in_h / 2;
+  for (const TcUnit& u : ch->units) {
+    if (u.pool_node >= 0 && !((u.ph == 1 || u.ph == 2) && (u.pw == 1 || u.pw == 2))) return false;
+    h /= (u.pool_node >= 0 ? u.ph : 1);
+  }
+  return h == ch->tail.kh && h >= 1;
+}
+
+static const TcChain* packed_chain(const Model::Impl* impl, const onnx::Graph& g) {
+  for (const auto& kv : impl->tc_chains) {
+    const TcChain& ch = kv.second;
+    if (!ch.stem || ch.tail.avg_node < 0 || ch.tail.out_name != impl->head.x_name) continue;
+    if (g.nodes[kv.first].inputs.empty() || g.nodes[kv.first].inputs[0] != g.inputs[0].name) continue;
+    return &ch;
+  }
+  return nullptr;
+}
+
+DTensor Model::run_prefix_packed(const std::vector<PrefixGroup>& groups, int in_h, cudaStream_t st,
+                                 std::vector<PackedGroup>* out_groups, ModelCost* cost, Profiler* prof,
+                                 const std::string& prof_prefix) const {
+  const Impl* impl = impl_.get();
+  const TcChain* chp = packed_chain(impl, graph_);
+  OCRS_CHECK(chp != nullptr && has_packed_prefix(in_h), kInternal, "run_prefix_packed: model has no packed conv prefix");
+  const TcChain& ch = *chp;
+  const int G = (int)groups.size();
+  const int U = (int)ch.units.size();
+  OCRS_CHECK(G > 0, kInvalidArg, "run_prefix_packed: no groups");
+  int* ovf = impl->tc_ovf.as<int>();
+  double flops = 0;
+
+  // ---- plan: per layer and group, dims and pixel offsets (layer 0 = stem, 1..U = convs, U+1 = tail) ----
+  const int L = U + 2;
+  std::vector<tc::RaggedDesc> descs((size_t)L * G);
+  std::vector<int64_t> layer_pix((size_t)U + 1, 0);   // output pixels of the stem and of each conv
+  std::vector<int> layer_c((size_t)U + 1, 0);         // their channel counts
+  std::vector<int> layer_units((size_t)L, 0);         // tiles / blocks per launch
+  std::vector<int> gh((size_t)G), gw((size_t)G);
+  layer_c[0] = ch.stem->Cout;
+  {
+    int64_t pix = 0;
+    int blocks = 0;
+    for (int g = 0; g < G; ++g) {
+      OCRS_CHECK(groups[g].N > 0 && groups[g].W > 0, kInvalidArg, "run_prefix_packed: empty group");
+      tc::RaggedDesc& d = descs[(size_t)g];
+      d = tc::RaggedDesc{};
+      d.N = groups[g].N; d.H = in_h; d.W = groups[g].W; d.OH = in_h / 2; d.OW = groups[g].W / 2;
+      d.first = blocks;
+      d.in_off = groups[g].x_off;
+      d.out_off = pix;
+
+      pix += (int64_t)d.N * d.OH * d.OW;
+      blocks += (int)ceil_div((int64_t)d.N * d.OH * d.OW, 128);
+      gh[g] = d.OH; gw[g] = d.OW;
+      flops += 2.0 * d.N * d.H * d.W * (double)ch.stem->Cout * 9.0;
+    }
+    layer_pix[0] = pix;
+    layer_units[0] = blocks;
+  }
+  std::vector<double> conv_flops((size_t)U, 0), conv_bytes((size_t)U, 0);
+  for (int u = 0; u < U; ++u) {
+    const TcUnit& un = ch.units[(size_t)u];
+    const int fph = un.pool_node >= 0 ? un.ph : 1, fpw = un.pool_node >= 0 ? un.pw : 1;
+    int64_t pix = 0;
+    int tiles = 0;
+    for (int g = 0; g < G; ++g) {
+      tc::RaggedDesc& d = descs[(size_t)(u + 1) * G + g];
+      d = tc::RaggedDesc{};
+      d.N = groups[g].N; d.H = gh[g]; d.W = gw[g]; d.OH = gh[g] / fph; d.OW = gw[g] / fpw;
+      tc::conv_fill_tiles(&d);
+      d.first = tiles;
+      d.in_off = descs[(size_t)u * G + g].out_off;
+      d.out_off = pix;
+      pix += (int64_t)d.N * d.OH * d.OW;
+      tiles += tc::conv_tiles(d.N, d.H, d.W);
+      const double cf = 2.0 * d.N * d.H * d.W * (double)un.w->Cout * un.w->Cin * 9.0;
+      conv_flops[u] += cf;
+      conv_bytes[u] += 4.0 * d.N * ((double)d.H * d.W * un.w->Cin + (double)d.OH * d.OW * un.w->Cout);
+      gh[g] = d.OH; gw[g] = d.OW;
+    }
+    layer_pix[(size_t)u + 1] = pix;
+    layer_c[(size_t)u + 1] = un.w->Cout;
+    layer_units[(size_t)u + 1] = tiles;
+    flops += conv_flops[u];
+  }
+  const int Cf = layer_c[(size_t)U];
+  int64_t rows = 0;
+  out_groups->clear();
+  {
+    int blocks = 0;
+    for (int g = 0; g < G; ++g) {
+      tc::RaggedDesc& d = descs[(size_t)(U + 1) * G + g];
+      d = tc::RaggedDesc{};
+      d.N = groups[g].N; d.H = gh[g]; d.W = gw[g]; d.OH = 1; d.OW = gw[g];
+      OCRS_CHECK(d.H == ch.tail.kh, kInternal, "run_prefix_packed: pooled height does not match the average pool");
+      d.first = blocks;
+      d.in_off = descs[(size_t)U * G + g].out_off;
+      d.out_off = rows;
+      blocks += (int)ceil_div((int64_t)d.N * d.W * (Cf / 8), 256);
+      out_groups->push_back(PackedGroup{d.W, d.N, rows});
+      rows += (int64_t)d.W * d.N;
+    }
+    layer_units[(size_t)U + 1] = blocks;
+  }
+
+  // ---- activations: two ping-pong buffers (hi + lo planes each) ----
+  int64_t cap[2] = {0, 0};
+  for (int l = 0; l <= U; ++l) cap[l & 1] = std::max(cap[l & 1], layer_pix[(size_t)l] * layer_c[(size_t)l]);
+  std::shared_ptr<Storage> buf_hi[2], buf_lo[2];
+  for (int k = 0; k < 2; ++k) {
+    buf_hi[k] = std::make_shared<Storage>((size_t)std::max<int64_t>(cap[k], 8) * 2, st);
+    buf_lo[k] = std::make_shared<Storage>((size_t)std::max<int64_t>(cap[k], 8) * 2, st);
+  }
+  auto hi_of = [&](int l) { return reinterpret_cast<tc::act_t*>(buf_hi[l & 1]->ptr); };
+  auto lo_of = [&](int l) { return reinterpret_cast<tc::act_t*>(buf_lo[l & 1]->ptr); };
+
+  // ---- one device blob: [descs | counters | tensor maps] ----
+  const size_t desc_bytes = round_up((int64_t)(descs.size() * sizeof(tc::RaggedDesc)), 128);
+  const size_t ctr_bytes = round_up((int64_t)U * 4, 128);
+  const size_t map_bytes = (size_t)U * 2 * G * sizeof(CUtensorMap);
+  std::vector<uint8_t> blob(desc_bytes + ctr_bytes + map_bytes, 0);
+  std::memcpy(blob.data(), descs.data(), descs.size() * sizeof(tc::RaggedDesc));
+  auto* hmaps = reinterpret_cast<CUtensorMap*>(blob.data() + desc_bytes + ctr_bytes);
+  for (int u = 0; u < U; ++u) {
+    const int Cin = ch.units[(size_t)u].w->Cin;
+    OCRS_CHECK(Cin == layer_c[(size_t)u], kRunFailed, "Conv: channel mismatch");
+    for (int g = 0; g < G; ++g) {
+      const tc::RaggedDesc& d = descs[(size_t)(u + 1) * G + g];
+      tc::make_act_maps(hi_of(u) + d.in_off * Cin, lo_of(u) + d.in_off * Cin, d.N, d.H, d.W, Cin, hmaps + ((size_t)u * G + g) * 2);
+    }
+  }
+  auto blob_dev = std::make_shared<Storage>(blob.size() + 128, st);
+  uint8_t* dblob = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(blob_dev->ptr) + 127) & ~(uintptr_t)127);
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+  const auto* d_descs = reinterpret_cast<const tc::RaggedDesc*>(dblob);
+  int* d_ctr = reinterpret_cast<int*>(dblob + desc_bytes);
+  const auto* d_maps = reinterpret_cast<const CUtensorMap*>(dblob + desc_bytes + ctr_bytes);
+
+  int ptok = prof ? prof->begin(prof_prefix + "ConvChain(total)", st) : -1;
+  {
+    int tk = prof ? prof->begin(prof_prefix + "stem_kernel", st) : -1;
+    tc::stem_ragged(groups[0].x_base, *ch.stem, hi_of(0), lo_of(0), d_descs, G, layer_units[0], ovf, st);
+    if (prof) prof->end(tk, st, 0, 0);
+  }
+  for (int u = 0; u < U; ++u) {
+    const TcUnit& un = ch.units[(size_t)u];
+    const int fph = un.pool_node >= 0 ? un.ph : 1, fpw = un.pool_node >= 0 ? un.pw : 1;
+    static const bool prof_layers = std::getenv("OCRS_B200_PROF_LAYERS") != nullptr;  // per-layer op names (diagnostics)
+    int ktok = prof ? prof->begin(prof_prefix + "conv3x3_tc_kernel" +
+                                      (prof_layers ? "/" + std::to_string(un.w->Cin) + "->" + std::to_string(un.w->Cout) + "#" + std::to_string(u) : std::string()),
+                                  st)
+                    : -1;
+    tc::conv3x3_ragged(d_maps + (size_t)u * 2 * G, d_descs + (size_t)(u + 1) * G, G, layer_units[(size_t)u + 1], d_ctr + u, *un.w,
+                       hi_of(u + 1), lo_of(u + 1), un.relu, fph, fpw, ovf, st);
+    if (prof) prof->end(ktok, st, conv_flops[u], conv_bytes[u]);
+  }
+  DTensor S = alloc_tensor({rows, (int64_t)Cf}, st);
+  {
+    int tk = prof ? prof->begin(prof_prefix + "AvgPool+Transpose(fused)", st) : -1;
+    tc::avg_to_seq_ragged(hi_of(U), lo_of(U), S.data, Cf, d_descs + (size_t)(U + 1) * G, G, layer_units[(size_t)U + 1], st);
+    if (prof) prof->end(tk, st, 0, 4.0 * (double)rows * Cf * (ch.tail.kh + 1));
+  }
+  if (prof) prof->end(ptok, st, flops);
+  if (cost) { cost->flops = flops; cost->min_bytes = 0; }
+  // buf_*, blob_dev: stream-ordered frees behind the launches above
+  return S;
 }
 
 DTensor Model::run_seq_head(const float* X, int64_t rows, const std::vector<PackedGroup>& groups, cudaStream_t st,

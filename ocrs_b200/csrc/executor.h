@@ -80,23 +80,41 @@ class Model {
   int seq_head_classes() const;
   DTensor run_prefix(const DTensor& input, cudaStream_t st, ModelCost* cost = nullptr, Profiler* prof = nullptr,
                      const std::string& prof_prefix = "") const;
+  // Packed conv prefix: when the graph from its input to X_seq is one tensor-core conv chain (stem conv +
+  // 3x3 convs + pooling tail), every layer runs ONCE over all width groups ("ragged" launches, dynamic
+  // tile scheduling) and the feature rows are written straight into the packed [rows, C] layout.
+  struct PrefixGroup {
+    const float* x_base = nullptr;  // common base pointer of all groups (the recognition batch buffer)
+    int64_t x_off = 0;              // element offset of this group's [N,1,H,W] f32 block
+    int N = 0, W = 0;
+  };
+  bool has_packed_prefix(int in_h) const;
+  // Returns the packed features [rows, C]; `out_groups` receives (T, N, row_off) per group, in order.
+  DTensor run_prefix_packed(const std::vector<PrefixGroup>& groups, int in_h, cudaStream_t st,
+                            std::vector<PackedGroup>* out_groups, ModelCost* cost = nullptr, Profiler* prof = nullptr,
+                            const std::string& prof_prefix = "") const;
   // X: packed [rows, C] f32.  Returns log-probs [rows, classes]; group g occupies rows
   // [row_off, row_off + T*N) in [T, N, classes] order.
   DTensor run_seq_head(const float* X, int64_t rows, const std::vector<PackedGroup>& groups, cudaStream_t st,
                        ModelCost* cost = nullptr, Profiler* prof = nullptr, const std::string& prof_prefix = "") const;
 
   // The tensor-core conv path carries activations as split fp16; a kernel that meets |x| > 65504
-  // raises a device flag.  Call after synchronising the stream(s) a run used: returns true when
-  // the flag was raised, in which case the tensor-core conv chains are switched off for this
-  // model (fp32 CUDA-core kernels from then on) and the caller must repeat the run.
-  bool take_tc_overflow() const;
+  // raises a device flag.  Protocol (safe with concurrent runs on one Model):
+  //     int tok = m.tc_token();  run(...);  synchronise the stream(s);  if (m.take_tc_overflow(tok)) repeat the run;
+  // take_tc_overflow returns true when the run started on the tensor-core chains and either the flag is
+  // raised (the chains are then switched off for this model: fp32 CUDA-core kernels from then on) or
+  // another run has switched them off in the meantime (its check may have consumed this run's flag).
+  int tc_token() const;
+  bool take_tc_overflow(int token) const;
 
   size_t weight_bytes() const { return weight_bytes_; }
   const onnx::Graph& graph() const { return graph_; }
 
+ public:
+  struct Impl;
+
  private:
   Model();
-  struct Impl;
   std::unique_ptr<Impl> impl_;
   onnx::Graph graph_;
   std::vector<int64_t> input_shape_;

@@ -100,7 +100,16 @@ TensorData parse_tensor(Reader r, std::string* name) {
     }
   }
   size_t es = dtype_size(t.dtype);
-  size_t n = (size_t)t.numel();
+  // dims come from an untrusted file: no negative extents, no product that wraps (kernels are sized
+  // from them); 2^40 elements is far beyond any model this engine loads
+  OCRS_CHECK(t.dims.size() <= 8, kModelLoad, "onnx: tensor rank > 8");
+  uint64_t n_checked = 1;
+  for (int64_t d : t.dims) {
+    OCRS_CHECK(d >= 0, kModelLoad, "onnx: negative tensor dimension");
+    OCRS_CHECK(d == 0 || n_checked <= ((uint64_t)1 << 40) / (uint64_t)d, kModelLoad, "onnx: tensor too large");
+    n_checked *= (uint64_t)d;
+  }
+  size_t n = (size_t)n_checked;
   if (!have_raw) {
     t.raw.resize(n * es);
     if (t.dtype == kFloat) {
@@ -275,6 +284,102 @@ std::vector<int64_t> Node::attr_ints(const std::string& k, const std::vector<int
   return a ? a->ints : d;
 }
 
+// Structural validation of an untrusted graph: every supported operator has the input / output arity and
+// the attribute vector lengths that Model::load and Model::run index without further checks.
+void validate_graph(const Graph& g) {
+  auto need = [](const Node& n, size_t min_in, size_t max_in) {
+    OCRS_CHECK(n.inputs.size() >= min_in && n.inputs.size() <= max_in, kModelLoad,
+               "onnx: " + n.op + " node '" + n.name + "' has " + std::to_string(n.inputs.size()) + " inputs");
+    for (size_t i = 0; i < min_in; ++i)
+      OCRS_CHECK(!n.inputs[i].empty(), kModelLoad, "onnx: " + n.op + " node '" + n.name + "' misses a required input");
+  };
+  auto ints_len = [](const Node& n, const char* key, size_t len) {
+    const Attr* a = n.find(key);
+    if (!a) return;
+    OCRS_CHECK(a->kind == Attr::kInts && a->ints.size() == len, kModelLoad,
+               "onnx: " + n.op + " attribute '" + key + "' must hold " + std::to_string(len) + " ints");
+  };
+  OCRS_CHECK(g.nodes.size() <= (size_t)1 << 20, kModelLoad, "onnx: too many nodes");
+  for (const Node& n : g.nodes) {
+    OCRS_CHECK(!n.outputs.empty() && !n.outputs[0].empty(), kModelLoad, "onnx: node '" + n.name + "' (" + n.op + ") has no output");
+    OCRS_CHECK(n.outputs.size() <= 4, kModelLoad, "onnx: node '" + n.name + "' has too many outputs");
+    const std::string& op = n.op;
+    if (op == "Conv" || op == "ConvTranspose") {
+      need(n, 2, 3);
+      ints_len(n, "pads", 4);
+      ints_len(n, "strides", 2);
+      ints_len(n, "dilations", 2);
+      ints_len(n, "kernel_shape", 2);
+      ints_len(n, "output_padding", 2);
+      OCRS_CHECK(n.attr_i("group", 1) >= 1, kModelLoad, "onnx: " + op + " group must be >= 1");
+      for (int64_t v : n.attr_ints("strides", {1, 1})) OCRS_CHECK(v >= 1 && v <= 64, kModelLoad, "onnx: bad stride");
+      for (int64_t v : n.attr_ints("dilations", {1, 1})) OCRS_CHECK(v >= 1 && v <= 64, kModelLoad, "onnx: bad dilation");
+      for (int64_t v : n.attr_ints("pads", {0, 0, 0, 0})) OCRS_CHECK(v >= 0 && v <= 4096, kModelLoad, "onnx: bad pad");
+    } else if (op == "MaxPool" || op == "AveragePool") {
+      need(n, 1, 1);
+      const Attr* ks = n.find("kernel_shape");
+      OCRS_CHECK(ks && ks->kind == Attr::kInts && ks->ints.size() == 2, kModelLoad, "onnx: " + op + " needs a 2-D kernel_shape");
+      for (int64_t v : ks->ints) OCRS_CHECK(v >= 1 && v <= 4096, kModelLoad, "onnx: bad pool kernel");
+      ints_len(n, "pads", 4);
+      ints_len(n, "strides", 2);
+      for (int64_t v : n.attr_ints("strides", {1, 1})) OCRS_CHECK(v >= 1 && v <= 4096, kModelLoad, "onnx: bad stride");
+      for (int64_t v : n.attr_ints("pads", {0, 0, 0, 0})) OCRS_CHECK(v >= 0 && v <= 4096, kModelLoad, "onnx: bad pad");
+    } else if (op == "GRU") {
+      need(n, 3, 6);
+      OCRS_CHECK(n.attr_i("hidden_size", 1) >= 1, kModelLoad, "onnx: GRU hidden_size must be >= 1");
+    } else if (op == "MatMul" || op == "Add" || op == "Gather" || op == "Reshape") {
+      need(n, 2, 2);
+    } else if (op == "Slice") {
+      need(n, 3, 5);
+    } else if (op == "Pad") {
+      need(n, 1, 4);
+    } else if (op == "Concat") {
+      need(n, 1, 1 << 16);
+    } else if (op == "Unsqueeze" || op == "Squeeze") {
+      need(n, 1, 2);
+    } else if (op == "Constant") {
+      need(n, 0, 0);
+    } else if (op == "Relu" || op == "Sigmoid" || op == "Tanh" || op == "LogSoftmax" || op == "Transpose" ||
+               op == "Identity" || op == "Shape" || op == "Cast" || op == "ConstantOfShape") {
+      need(n, 1, 1);
+    }
+    // unknown operators are reported by Model::load / model_inspect with their name
+  }
+  // weights whose shape the loader indexes
+  for (const Node& n : g.nodes) {
+    auto init = [&](size_t i) -> const TensorData* {
+      if (n.inputs.size() <= i || n.inputs[i].empty()) return nullptr;
+      auto it = g.initializers.find(n.inputs[i]);
+      return it == g.initializers.end() ? nullptr : &it->second;
+    };
+    if (n.op == "Conv" || n.op == "ConvTranspose") {
+      if (const TensorData* w = init(1)) {
+        OCRS_CHECK(w->dtype == kFloat && w->dims.size() == 4, kModelLoad, "onnx: " + n.op + " weight must be a 4-D float tensor");
+        for (int64_t d : w->dims) OCRS_CHECK(d >= 1, kModelLoad, "onnx: " + n.op + " weight has an empty dimension");
+        if (const TensorData* b = init(2))
+          OCRS_CHECK(b->dtype == kFloat && b->dims.size() == 1 &&
+                         b->dims[0] == (n.op == "Conv" ? w->dims[0] : w->dims[1] * n.attr_i("group", 1)),
+                     kModelLoad, "onnx: " + n.op + " bias does not match its weight");
+      }
+    } else if (n.op == "GRU") {
+      const TensorData* w = init(1);
+      const TensorData* r = init(2);
+      if (w && r) {
+        OCRS_CHECK(w->dtype == kFloat && r->dtype == kFloat && w->dims.size() == 3 && r->dims.size() == 3, kModelLoad,
+                   "onnx: GRU W / R must be 3-D float tensors");
+        OCRS_CHECK(w->dims[0] >= 1 && w->dims[0] <= 2 && r->dims[0] == w->dims[0] && w->dims[1] % 3 == 0 && w->dims[1] >= 3 &&
+                       r->dims[1] == w->dims[1] && r->dims[2] == w->dims[1] / 3 && w->dims[2] >= 1,
+                   kModelLoad, "onnx: GRU weight shapes are inconsistent");
+        if (const TensorData* b = init(3))
+          OCRS_CHECK(b->dtype == kFloat && b->dims.size() == 2 && b->dims[0] == w->dims[0] && b->dims[1] == 2 * w->dims[1],
+                     kModelLoad, "onnx: GRU bias shape is inconsistent");
+      }
+    } else if (n.op == "MatMul") {
+      if (const TensorData* w = init(1)) OCRS_CHECK(w->dtype == kFloat, kModelLoad, "onnx: MatMul weight must be float");
+    }
+  }
+}
+
 bool looks_like_rten(const uint8_t* b, size_t len) {
   return (len >= 4 && std::memcmp(b, "RTEN", 4) == 0) || (len >= 8 && std::memcmp(b + 4, "RTEN", 4) == 0);
 }
@@ -314,6 +419,7 @@ Graph parse_model(const uint8_t* bytes, size_t len) {
   }
   OCRS_CHECK(have_graph, kModelLoad, "onnx: ModelProto has no graph");
   g.opset = opset;
+  validate_graph(g);
   return g;
 }
 

@@ -62,7 +62,10 @@ struct Graph {
   int64_t opset = 0;
 };
 
-// Throws ocrs::Error(kModelLoad) on malformed input.
+// Throws ocrs::Error(kModelLoad) on malformed input; the returned graph has passed validate_graph().
+// validate_graph: arity of every supported operator, lengths / ranges of the attribute vectors and the
+// weight shapes that Model::load and Model::run index -- an untrusted file cannot drive them out of bounds.
+void validate_graph(const Graph& g);
 Graph parse_model(const uint8_t* bytes, size_t len);
 
 // True if the buffer looks like an rten container ("RTEN" magic).

@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import EngineParamsC, OcrsError, RectC, RotatedRectC, TextResultC, check, lib
+from ._lib import EngineParamsC, OcrsError, PageC, PoolParamsC, RectC, RotatedRectC, TextResultC, check, lib
 
 # lib.rs:34
 DEFAULT_ALPHABET = " 0123456789!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~EABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz"
@@ -334,23 +334,33 @@ class Model:
             self._h = None
 
 
+def _fill_engine_params(p: EngineParamsC, params: "OcrEngineParams"):
+    """Fills the C struct; returns the objects that must stay alive while the struct is in use."""
+    det = _model_bytes(params.detection_model)
+    rec = _model_bytes(params.recognition_model)
+    p.detection_model = C.cast(C.c_char_p(det), C.c_void_p) if det else None
+    p.detection_model_len = len(det) if det else 0
+    p.recognition_model = C.cast(C.c_char_p(rec), C.c_void_p) if rec else None
+    p.recognition_model_len = len(rec) if rec else 0
+    p.debug = int(params.debug)
+    p.decode_method = int(params.decode_method)
+    p.beam_width = int(params.beam_width)
+    p.alphabet_utf8 = params.alphabet.encode("utf-8") if params.alphabet is not None else None
+    p.allowed_chars_utf8 = params.allowed_chars.encode("utf-8") if params.allowed_chars is not None else None
+    p.device = int(params.device)
+    return det, rec
+
+
 class OcrEngine:
     """lib.rs:111-301"""
 
-    def __init__(self, params: OcrEngineParams):
-        self._det = _model_bytes(params.detection_model)
-        self._rec = _model_bytes(params.recognition_model)
+    def __init__(self, params: Optional[OcrEngineParams], _handle=None, _alphabet=None):
+        if _handle is not None:  # a pool's worker engine (OcrPool.engine): same handle type, shared ownership
+            self._h = _handle
+            self.alphabet = _alphabet if _alphabet is not None else DEFAULT_ALPHABET
+            return
         p = EngineParamsC()
-        p.detection_model = C.cast(C.c_char_p(self._det), C.c_void_p) if self._det else None
-        p.detection_model_len = len(self._det) if self._det else 0
-        p.recognition_model = C.cast(C.c_char_p(self._rec), C.c_void_p) if self._rec else None
-        p.recognition_model_len = len(self._rec) if self._rec else 0
-        p.debug = int(params.debug)
-        p.decode_method = int(params.decode_method)
-        p.beam_width = int(params.beam_width)
-        p.alphabet_utf8 = params.alphabet.encode("utf-8") if params.alphabet is not None else None
-        p.allowed_chars_utf8 = params.allowed_chars.encode("utf-8") if params.allowed_chars is not None else None
-        p.device = int(params.device)
+        self._det, self._rec = _fill_engine_params(p, params)
         self._h = C.c_void_p()
         check(lib.ocrs_b200_engine_create(C.byref(p), C.byref(self._h)))
         self.alphabet = params.alphabet if params.alphabet is not None else DEFAULT_ALPHABET
@@ -506,6 +516,105 @@ class OcrEngine:
         buf = (C.c_int64 * 2)()
         check(lib.ocrs_b200_engine_transfer_bytes(self._h, buf))
         return int(buf[0]), int(buf[1])
+
+
+class OcrPool:
+    """Engine pool inside the library (include/ocrs_b200.h, "engine pool"): per device `in_flight` worker
+    threads with one engine each; batches are submitted asynchronously and collected by ticket.
+
+        pool = OcrPool(OcrEngineParams(detection_model=..., recognition_model=...), devices=[0], in_flight=2)
+        t = pool.submit([ImageSource.from_tensor(page, DimOrder.Hwc) for page in pages])
+        texts = pool.wait_text(t)
+    """
+
+    def __init__(self, params: OcrEngineParams, devices: Optional[Sequence[int]] = None, in_flight: int = 2,
+                 pin_numa: bool = True, layout_threads: int = 4):
+        p = PoolParamsC()
+        keep = _fill_engine_params(p.engine, params)
+        ids = None
+        if devices is not None:
+            ids = (C.c_int32 * max(len(devices), 1))(*[int(d) for d in devices])
+            p.device_ids = C.cast(ids, C.POINTER(C.c_int32))
+            p.n_devices = len(devices)
+        p.in_flight = int(in_flight)
+        p.pin_numa = 1 if pin_numa else -1
+        p.layout_threads = int(layout_threads)
+        self._h = C.c_void_p()
+        check(lib.ocrs_b200_pool_create(C.byref(p), C.byref(self._h)))
+        del keep, ids
+        self._alphabet = params.alphabet
+        self._pending = {}  # ticket -> (n_pages, objects kept alive)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.ocrs_b200_pool_destroy(self._h)
+            self._h = None
+
+    @property
+    def shape(self) -> Tuple[int, int]:
+        nd, nf = C.c_int(), C.c_int()
+        check(lib.ocrs_b200_pool_shape(self._h, C.byref(nd), C.byref(nf)))
+        return nd.value, nf.value
+
+    def describe(self) -> str:
+        out = C.c_void_p()
+        check(lib.ocrs_b200_pool_describe(self._h, C.byref(out)))
+        return _take_string(out)
+
+    def engine(self, dev_index: int = 0, slot: int = 0) -> OcrEngine:
+        h = C.c_void_p()
+        check(lib.ocrs_b200_pool_engine(self._h, dev_index, slot, C.byref(h)))
+        return OcrEngine(None, _handle=h, _alphabet=self._alphabet)
+
+    def submit(self, pages: Sequence[ImageSource]) -> int:
+        """Host pages; the arrays are kept alive until the ticket has been waited for."""
+        arr = (PageC * max(len(pages), 1))()
+        for i, img in enumerate(pages):
+            a = img.data
+            if img.order == DimOrder.Hwc:
+                h, w, c = a.shape
+            else:
+                c, h, w = a.shape
+            arr[i] = PageC(a.ctypes.data, 0 if a.dtype == np.uint8 else 1, int(img.order), h, w, c, 0)
+        t = C.c_uint64()
+        check(lib.ocrs_b200_pool_submit(self._h, arr, len(pages), C.byref(t)))
+        self._pending[t.value] = (len(pages), [p.data for p in pages])
+        return t.value
+
+    def submit_device(self, ptrs: Sequence[int], dtype: int, order: DimOrder, h: int, w: int, c: int) -> int:
+        """Pages already resident in the memory of one of the pool's GPUs (device pointers)."""
+        arr = (PageC * max(len(ptrs), 1))()
+        for i, ptr in enumerate(ptrs):
+            arr[i] = PageC(int(ptr), int(dtype), int(order), h, w, c, 1)
+        t = C.c_uint64()
+        check(lib.ocrs_b200_pool_submit(self._h, arr, len(ptrs), C.byref(t)))
+        self._pending[t.value] = (len(ptrs), None)
+        return t.value
+
+    def done(self, ticket: int) -> bool:
+        d = C.c_int()
+        check(lib.ocrs_b200_pool_done(self._h, C.c_uint64(ticket), C.byref(d)))
+        return bool(d.value)
+
+    def wait_text(self, ticket: int) -> List[str]:
+        n, _keep = self._pending.pop(ticket)
+        res = (C.c_void_p * max(n, 1))()
+        check(lib.ocrs_b200_pool_wait_text(self._h, C.c_uint64(ticket), res, n))
+        out = []
+        for i in range(n):
+            out.append(C.string_at(res[i]).decode("utf-8"))
+            lib.ocrs_b200_free(res[i])
+        return out
+
+    def wait(self, ticket: int) -> List[List[Optional[TextLine]]]:
+        n, _keep = self._pending.pop(ticket)
+        res = (C.POINTER(TextResultC) * max(n, 1))()
+        check(lib.ocrs_b200_pool_wait(self._h, C.c_uint64(ticket), res, n))
+        out = []
+        for i in range(n):
+            out.append(_text_result(res[i]))
+            lib.ocrs_b200_text_result_free(res[i])
+        return out
 
 
 def kernel_launch_count() -> int:

@@ -31,6 +31,25 @@ class ModelRunError(RuntimeError):
     """errors.rs:6-12"""
 
 
+class _Stage:
+    """Optional per-stage wall-clock accounting of the CPU path (bench.py's `cpu_baseline.stage_s`):
+    `timers` is a dict name -> seconds, or None."""
+
+    def __init__(self, timers, name):
+        self.timers, self.name = timers, name
+
+    def __enter__(self):
+        if self.timers is not None:
+            import time
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if self.timers is not None:
+            import time
+            self.timers[self.name] = self.timers.get(self.name, 0.0) + time.perf_counter() - self.t0
+        return False
+
+
 def find_connected_component_rects(mask: np.ndarray, expand_dist: float, min_area: float) -> List[RotatedRect]:
     """detection.rs:41-62"""
     out = []
@@ -58,7 +77,7 @@ class TextDetector:
     def threshold(self) -> float:
         return self.text_threshold
 
-    def detect_text_pixels(self, image: np.ndarray) -> np.ndarray:
+    def detect_text_pixels(self, image: np.ndarray, timers=None) -> np.ndarray:
         """detection.rs:131-200.  image f32 [1,H,W] -> prob map f32 [H,W]."""
         _, img_h, img_w = image.shape
         shp = self.input_shape
@@ -72,16 +91,19 @@ class TextDetector:
             x = pad_bottom_right(x, pad_bottom, pad_right, BLACK_VALUE)
         if x.shape[2] != in_h or x.shape[3] != in_w:
             x = resize_bilinear(x, in_h, in_w)
-        mask = self.model.run(np.ascontiguousarray(x, dtype=np.float32))
+        with _Stage(timers, "detection_net"):
+            mask = self.model.run(np.ascontiguousarray(x, dtype=np.float32))
         mask = mask[:, :, : in_h - pad_bottom, : in_w - pad_right]
         mask = resize_bilinear(mask, img_h, img_w)
         return mask.reshape(img_h, img_w)
 
-    def detect_words(self, image: np.ndarray) -> List[RotatedRect]:
+    def detect_words(self, image: np.ndarray, timers=None) -> List[RotatedRect]:
         """detection.rs:104-122"""
-        prob = self.detect_text_pixels(image)
-        binary = threshold_mask(prob, self.text_threshold)
-        return find_connected_component_rects(binary, 3.0, self.min_area)
+        with _Stage(timers, "detect_pad_resize_net"):
+            prob = self.detect_text_pixels(image, timers)
+        with _Stage(timers, "threshold_contours_rects"):
+            binary = threshold_mask(prob, self.text_threshold)
+            return find_connected_component_rects(binary, 3.0, self.min_area)
 
 
 class TextRecognizer:
@@ -135,29 +157,35 @@ class TextRecognizer:
         return prepare_text_line(image, line_polygon(line), rw, h)
 
     def recognize_text_lines(self, image: np.ndarray, lines, alphabet: str, excluded_char_labels=None,
-                             decode_method: str = "greedy", beam_width: int = 100, collect=None):
+                             decode_method: str = "greedy", beam_width: int = 100, collect=None, timers=None):
         """recognition.rs:404-540"""
         h = self.input_height()
         alphabet_len = len(alphabet)
         results: List[LineRecResult] = []
-        for gw, group in self.line_plan(lines):
-            rec_input = prepare_text_line_batch(image, group, h, gw)
-            rec_output = self.run(rec_input)
+        with _Stage(timers, "line_polygons"):
+            plan = self.line_plan(lines)
+        for gw, group in plan:
+            with _Stage(timers, "line_crops"):
+                rec_input = prepare_text_line_batch(image, group, h, gw)
+            with _Stage(timers, "recognition_net"):
+                rec_output = self.run(rec_input)
             if alphabet_len + 1 != rec_output.shape[2]:
                 raise ModelRunError(
                     f"output column count ({rec_output.shape[2]}) does not match alphabet size ({alphabet_len + 1})")
             ctc_input_len = rec_output.shape[1]
-            for gi, line in enumerate(group):
-                seq = filter_excluded_char_labels(rec_output[gi], excluded_char_labels)
-                if decode_method == "greedy":
-                    steps, _ = ctc_decode_greedy(seq)
-                else:
-                    steps, _ = ctc_decode_beam(seq, beam_width)
-                results.append(LineRecResult(line, gw, ctc_input_len, steps))
-                if collect is not None:
-                    collect.append((line.index, gw, rec_input[gi], rec_output[gi]))
+            with _Stage(timers, "ctc_decode"):
+                for gi, line in enumerate(group):
+                    seq = filter_excluded_char_labels(rec_output[gi], excluded_char_labels)
+                    if decode_method == "greedy":
+                        steps, _ = ctc_decode_greedy(seq)
+                    else:
+                        steps, _ = ctc_decode_beam(seq, beam_width)
+                    results.append(LineRecResult(line, gw, ctc_input_len, steps))
+                    if collect is not None:
+                        collect.append((line.index, gw, rec_input[gi], rec_output[gi]))
         results.sort(key=lambda r: r.line.index)
-        return text_lines_from_recognition_results(results, alphabet)
+        with _Stage(timers, "text_assembly"):
+            return text_lines_from_recognition_results(results, alphabet)
 
 
 @dataclass
@@ -189,10 +217,10 @@ class OcrEngine:
         """lib.rs:183-187 -> f32 [1,H,W]"""
         return prepare_image(pixels, order)
 
-    def detect_words(self, image: np.ndarray) -> List[RotatedRect]:
+    def detect_words(self, image: np.ndarray, timers=None) -> List[RotatedRect]:
         if self.detector is None:
             raise RuntimeError("Detection model not loaded")  # lib.rs:197
-        return self.detector.detect_words(image)
+        return self.detector.detect_words(image, timers)
 
     def detect_text_pixels(self, image: np.ndarray) -> np.ndarray:
         if self.detector is None:
@@ -202,11 +230,11 @@ class OcrEngine:
     def find_text_lines(self, image, words: Sequence[RotatedRect]) -> List[List[RotatedRect]]:
         return find_text_lines(words)
 
-    def recognize_text(self, image: np.ndarray, lines, collect=None):
+    def recognize_text(self, image: np.ndarray, lines, collect=None, timers=None):
         if self.recognizer is None:
             raise RuntimeError("Recognition model not loaded")  # lib.rs:254
         return self.recognizer.recognize_text_lines(
-            image, lines, self.alphabet, self.excluded_char_labels, self.decode_method, self.beam_width, collect)
+            image, lines, self.alphabet, self.excluded_char_labels, self.decode_method, self.beam_width, collect, timers)
 
     def prepare_recognition_input(self, image: np.ndarray, line) -> np.ndarray:
         if self.recognizer is None:
@@ -216,11 +244,12 @@ class OcrEngine:
     def detection_threshold(self) -> float:
         return self.detector.threshold() if self.detector is not None else 0.2
 
-    def get_text(self, image: np.ndarray) -> str:
-        """lib.rs:290-300"""
-        words = self.detect_words(image)
-        lines = self.find_text_lines(image, words)
-        texts = self.recognize_text(image, lines)
+    def get_text(self, image: np.ndarray, timers=None) -> str:
+        """lib.rs:290-300.  `timers` (dict or None) accumulates seconds per stage."""
+        words = self.detect_words(image, timers)
+        with _Stage(timers, "find_text_lines"):
+            lines = self.find_text_lines(image, words)
+        texts = self.recognize_text(image, lines, timers=timers)
         return "\n".join(line_text(t) for t in texts if t is not None)
 
 

@@ -60,3 +60,13 @@ def test_no_cpu_fallback():
     with pytest.raises(ob.OcrsError) as ei:
         ob.Model(b"\x08\x08")
     assert ei.value.code == _lib.ERR_NO_DEVICE
+
+
+def test_pool_create_without_device_fails_cleanly():
+    """The pool is a compute entry point: no GPU -> OCRS_B200_ERR_NO_DEVICE, never a fallback."""
+    import ocrs_b200 as ob
+    if ob.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ob.OcrsError) as ei:
+        ob.OcrPool(ob.OcrEngineParams(), devices=[0])
+    assert ei.value.code == -9
