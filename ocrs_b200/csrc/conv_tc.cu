@@ -117,7 +117,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                   const CUtensorMap* __restrict__ maps, const RaggedDesc* __restrict__ groups, int n_groups,
                   int n_tiles, int* __restrict__ counter, const float* __restrict__ bias, act_t* __restrict__ out_hi,
                   act_t* __restrict__ out_lo, int Cin, int relu, int ph, int pw, float promo_scale,
-                  int* __restrict__ ovf, unsigned long long* __restrict__ dbg) {
+                  int* __restrict__ ovf, unsigned long long* __restrict__ dbg, int hh_first) {
   using C = Cfg<KC, COUT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = smem_u32(smem_raw);
@@ -254,8 +254,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
           tc_fence_after();
           long long g1 = timing ? clock64() : 0;
           c_hhe += (unsigned long long)(g1 - g0);
-          // ---- hi*hi MMAs of the whole group ----
           uint32_t s = stage, p = par;
+          long long g2 = g1;
+          if (hh_first) {
+          // ---- hi*hi MMAs of the whole group ----
           for (int j = 0; j < nk; ++j) {
             long long w0 = timing ? clock64() : 0;
             mbar_wait(full_bar(s), p);
@@ -273,7 +275,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             if (++s == C::kStages) { s = 0; p ^= 1; }
           }
           umma_commit(hh_full(b));
-          long long g2 = timing ? clock64() : 0;
+          g2 = timing ? clock64() : 0;
           // ---- cross terms of the group; each k-block's stage is released behind its last MMA ----
           s = stage;
           for (int j = 0; j < nk; ++j) {
@@ -287,6 +289,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             }
             umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
             if (++s == C::kStages) s = 0;
+          }
+          } else {
+          // ---- interleaved: per 16 K-elements hi*hi, hi*lo, lo*hi (consecutive MMAs share an operand) ----
+          for (int j = 0; j < nk; ++j) {
+            long long w0 = timing ? clock64() : 0;
+            mbar_wait(full_bar(s), p);
+            tc_fence_after();
+            if (timing) c_full += (unsigned long long)(clock64() - w0);
+            const uint64_t d0 = make_desc<KC>(base + s * C::kStageBytes);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              const uint64_t da_hi = d0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABytes >> 4);
+              const uint64_t db_hi = da_hi + (uint64_t)((2 * C::kABytes) >> 4), db_lo = db_hi + (uint64_t)(C::kBBytes >> 4);
+              umma_bf16(d_hh, da_hi, db_hi, idesc, (j | k) ? 1u : 0u);
+              umma_bf16(d_x, da_hi, db_lo, idesc, (kb | j | k) ? 1u : 0u);
+              umma_bf16(d_x, da_lo, db_hi, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));
+            if (++s == C::kStages) { s = 0; p ^= 1; }
+          }
+          umma_commit(hh_full(b));
+          g2 = timing ? clock64() : 0;
           }
           if (timing) {
             const long long g3 = clock64();
@@ -635,6 +659,13 @@ float promo_scale() {
   return s;
 }
 
+// MMA issue order inside a promotion group: 0 (default) = interleaved per 16 K-elements, 1 = all hi*hi
+// first (OCRS_B200_CONV_HH_FIRST=1); same arithmetic either way
+bool conv_hh_first() {
+  static const bool on = [] { const char* e = std::getenv("OCRS_B200_CONV_HH_FIRST"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
 bool conv_debug() {
   static const bool on = std::getenv("OCRS_B200_CONV_DEBUG") != nullptr;
   return on;
@@ -663,7 +694,7 @@ void launch_conv(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_gr
   }
   conv3x3_tc_kernel<KC, COUT><<<grid, kConvThreads, C::kSmemBytes, st>>>(
       tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles, d_counter, w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph, pw,
-      promo_scale(), ovf, d_dbg);
+      promo_scale(), ovf, d_dbg, conv_hh_first() ? 1 : 0);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
   if (d_dbg) {

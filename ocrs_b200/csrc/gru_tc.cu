@@ -175,6 +175,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void reg_fence8(uint32_t (&r)[8]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+}
+
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads, 1)
 gru_cluster_kernel(const __nv_bfloat16* __restrict__ r_hi_g, const __nv_bfloat16* __restrict__ r_lo_g,
                    const float* __restrict__ xw, const float* __restrict__ rb, const float* __restrict__ h0,
@@ -422,6 +431,309 @@ gru_cluster_kernel(const __nv_bfloat16* __restrict__ r_hi_g, const __nv_bfloat16
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// v3 of the cluster-resident recurrent kernel.  Same decomposition as above (8 CTAs per tile of <= 32
+// lines, R slice resident in tensor memory), re-cut around what the micro-benchmarks measured
+// (profiles/r02a_ubench_*.log):
+//   * a single thread issues a tcgen05.mma every ~53 cycles whatever its size; four issuing warps get the
+//     48 MMAs of a step through in ~940 cycles instead of ~2550.  Warp w owns the K range of the hidden
+//     units of CTAs 2w and 2w+1 and accumulates into its own TMEM accumulator; the gate warps add the four
+//     partial sums;
+//   * the all-gather of h_t is DSMEM-bandwidth bound (~20 B/clk/SM): it cannot be made cheap, but it can
+//     be overlapped.  h lives in shared memory as 8 mini tiles [32 lines][32 units] (64-byte-swizzled
+//     K-major, hi | lo planes adjacent = 4 KB contiguous per source CTA); every CTA pushes its tile to the
+//     7 peers with ONE cp.async.bulk (shared::cta -> shared::cluster) each, completing on the DESTINATION's
+//     per-slice mbarrier, and the issuing warps start the MMAs of a slice as soon as that slice has landed;
+//   * no fences or remote arrives on the critical path: complete_tx on the peer's barrier is the signal.
+// Protocol per step t (buffer b = t & 1 holds h_{t-1}):  MMA warp w, for s in {2w, 2w+1}: wait
+// slice_bar[b][s] -> 6 MMAs;  commit -> d_full (4 arrivals).  Gate warps: drain + add the 4 accumulators,
+// gate math, write h_t (hi, lo) into their own slice of buffer b^1, fence.proxy.async, barrier; one thread
+// arrives on its own slice barrier and issues the 7 bulk copies.  Buffer b^1 was last read by the MMAs of
+// step t-1, which every peer has finished before it could produce the h_{t-1} this CTA consumed.
+// ------------------------------------------------------------------------------------------
+constexpr int kSliceTile = NL * 64;            // one plane of one slice: [NL][32] bf16, 64-byte rows = 2 KB
+constexpr int kSliceBoth = 2 * kSliceTile;     // hi | lo
+constexpr int kHBuf3 = kCl * kSliceBoth;       // 32 KB
+constexpr int kMmaWarps3 = 4;
+constexpr int kCl3Threads = kGateThreads + 32 * kMmaWarps3;
+constexpr int kCl3Smem = 2 * kHBuf3 + kExBytes + 1024 + 512;
+
+// byte offset of (line l, unit u in [0, 32)) inside a 64-byte-swizzled [NL][32] bf16 tile
+__device__ __forceinline__ uint32_t sw64_off(int l, int u) {
+  return (uint32_t)(l * 64 + ((((u >> 3) ^ (l >> 1)) & 3) << 4) + (u & 7) * 2);
+}
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kCl3Threads, 1)
+gru_cluster3_kernel(const __nv_bfloat16* __restrict__ r_hi_g, const __nv_bfloat16* __restrict__ r_lo_g,
+                    const float* __restrict__ xw, const float* __restrict__ rb, const float* __restrict__ h0,
+                    float* __restrict__ Y, float* __restrict__ Yh, const SeqLine* __restrict__ lines, int n_lines,
+                    int D, int64_t y_dstride, int rev0, int rev1, long long* __restrict__ dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t base = (smem0 + 1023u) & ~1023u;
+  const uint32_t hbuf0 = base;                         // buffer b at hbuf0 + b*kHBuf3; slice s at + s*kSliceBoth: [hi | lo]
+  const uint32_t ex = hbuf0 + 2 * kHBuf3;
+  const uint32_t bar_base = ex + kExBytes;
+  const uint32_t d_full_bar = bar_base;
+  auto slice_bar = [&](int b, int sl) { return bar_base + 16u + 8u * (uint32_t)(b * kCl + sl); };
+  const uint32_t tmem_slot = bar_base + 16u + 8u * 2 * kCl;
+  float* exf = reinterpret_cast<float*>(smem_raw + (ex - smem0));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int tile = blockIdx.x / kCl;
+  const int d = blockIdx.y;
+  const int rev = d == 0 ? rev0 : rev1;
+  const SeqLine* tl = lines + (size_t)tile * NL;
+  const int n_in_tile = min(NL, n_lines - tile * NL);
+  const int steps = tl[0].T;                           // lines are sorted by T descending inside a tile
+
+  if (threadIdx.x == 0) {
+    mbar_init(d_full_bar, kMmaWarps3);
+    for (int b = 0; b < 2; ++b)
+      for (int sl = 0; sl < kCl; ++sl) mbar_init(slice_bar(b, sl), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);  // D_w: cols [32w, 32w+32); A_hi: [128,256); A_lo: [256,384)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // ---- one-time: this CTA's R slice becomes the MMA A operand in TENSOR MEMORY.  TMEM lane = row
+    // (gate g = warp, unit = lane; lanes 96..127 are zero padding), columns = packed bf16 pairs along K.
+    const uint4* src_hi = nullptr;
+    const uint4* src_lo = nullptr;
+    if (warp < 3) {
+      const size_t row = (size_t)d * 768 + (size_t)warp * 256 + (size_t)rank * 32 + lane;
+      src_hi = reinterpret_cast<const uint4*>(r_hi_g + row * 256);
+      src_lo = reinterpret_cast<const uint4*>(r_lo_g + row * 256);
+    }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int plane = 0; plane < 2; ++plane) {
+      const uint4* src = plane == 0 ? src_hi : src_lo;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {  // 4 x 32 columns = 128 words = 256 bf16
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v = src ? __ldg(src + c * 8 + j) : make_uint4(0, 0, 0, 0);
+          r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+        }
+        tmem_st32(lane_base + (uint32_t)(128 + plane * 128 + c * 32), r);
+      }
+    }
+    tmem_wait_st();
+  }
+  if (warp < kGateWarps) {
+    // ---- h_{-1}: every CTA fills its own copy of buffer 0 (all 256 units) ----
+    for (int e = threadIdx.x; e < NL * 256; e += kGateThreads) {
+      const int l = e >> 8, u = e & 255;
+      float v = 0.f;
+      if (h0 != nullptr && l < n_in_tile && tl[l].valid) v = h0[((size_t)d * n_lines + tile * NL + l) * 256 + u];
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      const uint32_t off = hbuf0 + (uint32_t)((u >> 5) * kSliceBoth) + sw64_off(l, u & 31);
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(off), "h"(__bfloat16_as_ushort(hi)) : "memory");
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(off + kSliceTile), "h"(__bfloat16_as_ushort(lo)) : "memory");
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before anyone's bulk copies complete on them
+
+  if (warp >= kGateWarps) {
+    // ---------------- MMA issuers: warp w handles the K range of slices 2w, 2w+1 ----------------
+    const int w = warp - kGateWarps;
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NL >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t d_acc = tmem_base + (uint32_t)(w * NL);
+      tc_fence_after();
+      long long m_issue = 0;
+      for (int step = 0; step < steps; ++step) {
+        const int b = step & 1;
+        const uint32_t hb = hbuf0 + b * kHBuf3;
+        const long long c0 = clock64();
+        // the own slice's barrier is arrived on after this CTA's gate warps have drained the accumulators of
+        // the previous step: every issuing warp waits for it before it overwrites its accumulator (a warp
+        // whose two slices are remote would otherwise depend on the peers' progress only)
+        if (step > 0) mbar_wait_trap(slice_bar(b, (int)rank), ((step - 1) >> 1) & 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int sl = 2 * w + i;
+          if (step > 0) {
+            // remote slices arrive as bulk-copy bytes (arm the transaction count); the own slice as a plain arrive
+            if (sl != (int)rank) mbar_expect_tx(slice_bar(b, sl), kSliceBoth);
+            mbar_wait_trap(slice_bar(b, sl), ((step - 1) >> 1) & 1);
+            tc_fence_after();
+          }
+          const uint64_t db0 = make_desc<32>(hb + sl * kSliceBoth);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t ta_hi = tmem_base + 128u + (uint32_t)((sl * 2 + k) * 8), ta_lo = ta_hi + 128u;
+            const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(kSliceTile >> 4);
+            umma_bf16_ts(d_acc, ta_hi, db_hi, idesc, (i | k) ? 1u : 0u);
+            umma_bf16_ts(d_acc, ta_hi, db_lo, idesc, 1u);
+            umma_bf16_ts(d_acc, ta_lo, db_hi, idesc, 1u);
+          }
+        }
+        umma_commit(d_full_bar);
+        m_issue += clock64() - c0;
+      }
+      if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && w == 0) { dbg[0] = 0; dbg[1] = m_issue; dbg[7] = steps; }
+    }
+  } else {
+    // ---------------- gate math: 16 warps ----------------
+    // phase A: warp (q, g) = (warp / 4, warp % 4), g < 3, drains gate g of lines 8q..8q+7 (TMEM lanes 32g.. = units),
+    //          adding the four K-partial accumulators
+    // phase B: warp w owns lines 2w, 2w+1 for unit = lane of this CTA's slice
+    const int q = warp >> 2, g = warp & 3;
+    const int unit = (int)rank * 32 + lane;
+    const int l0 = 2 * warp;
+    float h[2];
+    int lT[2];
+    int64_t lx[2], lxs[2], ly[2], lys[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int l = l0 + i;
+      const bool ok = l < n_in_tile && tl[l].valid;
+      h[i] = (h0 != nullptr && ok) ? h0[((size_t)d * n_lines + tile * NL + l) * 256 + unit] : 0.f;
+      lT[i] = ok ? tl[l].T : 0;
+      lx[i] = ok ? tl[l].xw_base : 0;
+      lxs[i] = ok ? tl[l].xw_tstride : 0;
+      ly[i] = ok ? tl[l].y_base : 0;
+      lys[i] = ok ? tl[l].y_tstride : 0;
+    }
+    const float rbz = rb[(size_t)d * 768 + unit], rbr = rb[(size_t)d * 768 + 256 + unit], rbn = rb[(size_t)d * 768 + 512 + unit];
+    long long e_wait = 0, e_drain = 0, e_math = 0, e_xchg = 0;
+    for (int step = 0; step < steps; ++step) {
+      const int b = step & 1, nb = b ^ 1;
+      const long long t0 = clock64();
+      // prefetch the input projections of this step (overlaps the MMAs)
+      float xz[2], xr[2], xn[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        xz[i] = xr[i] = xn[i] = 0.f;
+        if (step < lT[i]) {
+          const int t = rev ? (lT[i] - 1 - step) : step;
+          const float* xg = xw + lx[i] + (int64_t)t * lxs[i] + (int64_t)d * 768 + unit;
+          xz[i] = __ldg(xg);
+          xr[i] = __ldg(xg + 256);
+          xn[i] = __ldg(xg + 512);
+        }
+      }
+      mbar_wait_trap(d_full_bar, step & 1);
+      tc_fence_after();
+      const long long t1 = clock64();
+      e_wait += t1 - t0;
+      if (g < 3) {
+        uint32_t a0[8], a1[8], a2[8], a3[8];
+        const uint32_t ta = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * 8);
+        tmem_ld8_issue(ta, a0);
+        tmem_ld8_issue(ta + NL, a1);
+        tmem_ld8_issue(ta + 2 * NL, a2);
+        tmem_ld8_issue(ta + 3 * NL, a3);
+        tmem_wait_ld();
+        reg_fence8(a0); reg_fence8(a1); reg_fence8(a2); reg_fence8(a3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          exf[(g * NL + q * 8 + j) * 32 + lane] =
+              (__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + (__uint_as_float(a2[j]) + __uint_as_float(a3[j]));
+      }
+      tc_fence_before();
+      named_bar_sync(1, kGateThreads);
+      const long long t2 = clock64();
+      e_drain += t2 - t1;
+      {
+        float pz[2], pr[2], pn[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          pz[i] = exf[(0 * NL + l0 + i) * 32 + lane];
+          pr[i] = exf[(1 * NL + l0 + i) * 32 + lane];
+          pn[i] = exf[(2 * NL + l0 + i) * 32 + lane];
+        }
+        const uint32_t own = hbuf0 + nb * kHBuf3 + rank * kSliceBoth;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const bool act = step < lT[i];
+          const float z = fast_sigmoid(xz[i] + pz[i] + rbz);
+          const float r = fast_sigmoid(xr[i] + pr[i] + rbr);
+          const float nn_ = fast_tanh(xn[i] + r * (pn[i] + rbn));
+          const float hn = act ? ((1.f - z) * nn_ + z * h[i]) : h[i];
+          h[i] = hn;
+          if (act) {
+            const int t = rev ? (lT[i] - 1 - step) : step;
+            Y[ly[i] + (int64_t)t * lys[i] + (int64_t)d * y_dstride + unit] = hn;
+          }
+          if (step + 1 < steps) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(hn, hi, lo);
+            const uint32_t off = own + sw64_off(l0 + i, lane);
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(off), "h"(__bfloat16_as_ushort(hi)) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(off + kSliceTile), "h"(__bfloat16_as_ushort(lo)) : "memory");
+          }
+        }
+      }
+      const long long t3 = clock64();
+      e_math += t3 - t2;
+      if (step + 1 < steps) {
+        fence_proxy_async();                 // generic-proxy writes of h_t -> visible to the bulk copies and the MMAs
+        named_bar_sync(1, kGateThreads);
+        if (threadIdx.x < kCl) {
+          const uint32_t own = hbuf0 + nb * kHBuf3 + rank * kSliceBoth;
+          const uint32_t pc = (rank + threadIdx.x) & (kCl - 1);   // thread 0: own CTA; 1..7: the peers, staggered
+          if (pc == rank) {
+            mbar_arrive(slice_bar(nb, (int)rank));
+          } else {
+            asm volatile(
+                "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mapa(own, pc)),
+                "r"(own), "r"((uint32_t)kSliceBoth), "r"(mapa(slice_bar(nb, (int)rank), pc))
+                : "memory");
+          }
+        }
+      }
+      e_xchg += clock64() - t3;
+    }
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      dbg[2] = e_wait; dbg[3] = e_drain; dbg[4] = e_math; dbg[5] = e_xchg; dbg[6] = 0;
+    }
+    if (Yh != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int l = l0 + i;
+        if (l < n_in_tile && tl[l].valid) Yh[((size_t)d * n_lines + tile * NL + l) * 256 + unit] = h[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits while peers' bulk copies may still target its shared memory
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// launch of the recurrent kernel: v3 by default, OCRS_B200_GRU_V2=1 selects the previous kernel
+void launch_recurrence(const GruWeightsTC& w, const float* xw, const float* h0, float* Y, float* Yh, const SeqLine* d_desc,
+                       int n_lines, int n_tiles, int64_t y_dstride, const int* reverse, long long* d_dbg, cudaStream_t st) {
+  static const bool v2 = [] { const char* e = std::getenv("OCRS_B200_GRU_V2"); return e != nullptr && e[0] == '1'; }();
+  dim3 grid((unsigned)(n_tiles * kCl), (unsigned)w.D);
+  if (v2) {
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
+    gru_cluster_kernel<<<grid, kClThreads, kClSmem, st>>>(w.r_hi.as<__nv_bfloat16>(), w.r_lo.as<__nv_bfloat16>(), xw, w.rb.as<float>(),
+                                                          h0, Y, Yh, d_desc, n_lines, w.D, y_dstride, reverse[0],
+                                                          w.D > 1 ? reverse[1] : 0, d_dbg);
+  } else {
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCl3Smem));
+    gru_cluster3_kernel<<<grid, kCl3Threads, kCl3Smem, st>>>(w.r_hi.as<__nv_bfloat16>(), w.r_lo.as<__nv_bfloat16>(), xw,
+                                                             w.rb.as<float>(), h0, Y, Yh, d_desc, n_lines, w.D, y_dstride,
+                                                             reverse[0], w.D > 1 ? reverse[1] : 0, d_dbg);
+  }
+  count_launch();
+}
+
 }  // namespace
 
 bool gru_supported(int D, int H, int I) { return available() && H == 256 && (D == 1 || D == 2) && I % 64 == 0 && I >= 64; }
@@ -499,11 +811,7 @@ void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* 
     }
     auto* d_desc = static_cast<SeqLine*>(alloc(desc.size() * sizeof(SeqLine)));
     OCRS_CUDA_CHECK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(SeqLine), cudaMemcpyHostToDevice, st));
-    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
-    dim3 grid((unsigned)(n_tiles * kCl), (unsigned)D);
-    gru_cluster_kernel<<<grid, kClThreads, kClSmem, st>>>(w.r_hi.as<__nv_bfloat16>(), w.r_lo.as<__nv_bfloat16>(), xw, w.rb.as<float>(), h0, Y, Yh, d_desc, N, D,
-                                                          (int64_t)N * H, reverse[0], D > 1 ? reverse[1] : 0, nullptr);
-    count_launch();
+    launch_recurrence(w, xw, h0, Y, Yh, d_desc, N, n_tiles, (int64_t)N * H, reverse, nullptr, st);
   }
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -541,17 +849,13 @@ void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, cons
   }
   auto* d_desc = static_cast<SeqLine*>(alloc(desc.size() * sizeof(SeqLine)));
   OCRS_CUDA_CHECK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(SeqLine), cudaMemcpyHostToDevice, st));
-  OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmem));
-  dim3 grid((unsigned)(n_tiles * kCl), (unsigned)D);
   static const bool dbg_on = std::getenv("OCRS_B200_GRU_DEBUG") != nullptr;
   long long* d_dbg = nullptr;
   if (dbg_on) {
     d_dbg = static_cast<long long*>(alloc(8 * sizeof(long long)));
     OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 8 * sizeof(long long), st));
   }
-  gru_cluster_kernel<<<grid, kClThreads, kClSmem, st>>>(w.r_hi.as<__nv_bfloat16>(), w.r_lo.as<__nv_bfloat16>(), xw, w.rb.as<float>(), nullptr, Y, nullptr, d_desc, n_lines,
-                                                        D, y_dstride, reverse[0], D > 1 ? reverse[1] : 0, d_dbg);
-  count_launch();
+  launch_recurrence(w, xw, nullptr, Y, nullptr, d_desc, n_lines, n_tiles, y_dstride, reverse, d_dbg, st);
   if (dbg_on) {
     long long hdbg[8];
     OCRS_CUDA_CHECK(cudaMemcpyAsync(hdbg, d_dbg, sizeof(hdbg), cudaMemcpyDeviceToHost, st));
