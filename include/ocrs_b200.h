@@ -190,6 +190,21 @@ int ocrs_b200_engine_ocr_batch_text(ocrs_b200_engine* e, const ocrs_b200_input* 
 int ocrs_b200_engine_detect_words_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
                                         ocrs_b200_rotated_rect** rects, size_t** offsets);
 
+/* ---- debug outputs of ocrs-cli, batched on the device ------------------
+ * `--text-map` / `--text-mask` (ocrs-cli/src/main.rs:423-436: detect_text_pixels, then x > detection_threshold)
+ * for a batch of pages in ONE detection pass.  maps / masks: caller arrays of n_pages entries (either may be
+ * NULL = not wanted), filled with malloc'ed buffers of H_i*W_i floats / bytes (1 = text). */
+int ocrs_b200_engine_detect_text_pixels_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
+                                              float** maps, uint8_t** masks);
+/* `--text-line-images` (main.rs:441-443, write_preprocessed_text_line_images): the recognition inputs
+ * (prepare_recognition_input, lib.rs:268) of ALL lines of a page in one crop launch.  *images is one malloc'ed
+ * buffer; line i is a [*height, (*widths)[i]] row-major image at float offset (*offsets)[i].  *widths and
+ * *offsets are malloc'ed arrays of n_lines entries. */
+int ocrs_b200_engine_prepare_recognition_inputs(ocrs_b200_engine* e, const ocrs_b200_input* in,
+                                                const ocrs_b200_rotated_rect* words, const size_t* line_offsets,
+                                                size_t n_lines, float** images, int* height, int** widths,
+                                                size_t** offsets);
+
 /* ---- engine pool: pipelining and multi-GPU fan-out inside the library ---------------------------
  * The reference runs get_text page by page on the calling thread (ocrs/src/lib.rs:290-300,
  * ocrs-cli/src/main.rs:438-446).  A pool owns, per device, `in_flight` worker threads with one engine

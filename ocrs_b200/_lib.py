@@ -120,6 +120,11 @@ SIGNATURES = {
     "ocrs_b200_engine_timer_stop": (C.c_int, [C.c_void_p, P(C.c_float)]),
     "ocrs_b200_engine_transfer_bytes": (C.c_int, [C.c_void_p, P(C.c_int64)]),
     "ocrs_b200_kernel_launch_count": (C.c_int64, []),
+    "ocrs_b200_engine_detect_text_pixels_batch": (C.c_int, [C.c_void_p, P(C.c_void_p), C.c_size_t, P(C.c_void_p),
+                                                            P(C.c_void_p)]),
+    "ocrs_b200_engine_prepare_recognition_inputs": (C.c_int, [C.c_void_p, C.c_void_p, P(RotatedRectC), P(C.c_size_t),
+                                                              C.c_size_t, P(P(C.c_float)), P(C.c_int), P(P(C.c_int)),
+                                                              P(P(C.c_size_t))]),
     "ocrs_b200_pool_create": (C.c_int, [P(PoolParamsC), P(C.c_void_p)]),
     "ocrs_b200_pool_destroy": (None, [C.c_void_p]),
     "ocrs_b200_pool_submit": (C.c_int, [C.c_void_p, P(PageC), C.c_size_t, P(C.c_uint64)]),

@@ -637,6 +637,57 @@ int ocrs_b200_engine_ocr_batch_text(ocrs_b200_engine* e, const ocrs_b200_input* 
   });
 }
 
+// ---- batched debug outputs -------------------------------------------------------------------------
+int ocrs_b200_engine_detect_text_pixels_batch(ocrs_b200_engine* e, const ocrs_b200_input* const* inputs, size_t n_pages,
+                                              float** maps, uint8_t** masks) {
+  return guard([&] {
+    OCRS_CHECK(e && (inputs || n_pages == 0), kInvalidArg, "null argument");
+    std::vector<const OcrInput*> pages(n_pages);
+    for (size_t i = 0; i < n_pages; ++i) {
+      OCRS_CHECK(inputs[i] != nullptr, kInvalidArg, "null input");
+      pages[i] = inputs[i]->input.get();
+      if (maps) maps[i] = nullptr;
+      if (masks) masks[i] = nullptr;
+    }
+    auto r = e->engine->detect_text_pixels_batch(pages, maps != nullptr, masks != nullptr);
+    for (size_t i = 0; i < n_pages; ++i) {
+      if (maps) {
+        maps[i] = cmalloc<float>(r[i].map.size());
+        std::memcpy(maps[i], r[i].map.data(), r[i].map.size() * 4);
+      }
+      if (masks) {
+        masks[i] = cmalloc<uint8_t>(r[i].mask.size());
+        std::memcpy(masks[i], r[i].mask.data(), r[i].mask.size());
+      }
+    }
+  });
+}
+
+int ocrs_b200_engine_prepare_recognition_inputs(ocrs_b200_engine* e, const ocrs_b200_input* in,
+                                                const ocrs_b200_rotated_rect* words, const size_t* line_offsets,
+                                                size_t n_lines, float** images, int* height, int** widths,
+                                                size_t** offsets) {
+  return guard([&] {
+    OCRS_CHECK(e && in && (line_offsets || n_lines == 0) && images && height && widths && offsets, kInvalidArg, "null argument");
+    std::vector<std::vector<geom::RotatedRect>> lines(n_lines);
+    for (size_t i = 0; i < n_lines; ++i) {
+      OCRS_CHECK(line_offsets[i + 1] >= line_offsets[i], kInvalidArg, "line offsets must be non-decreasing");
+      OCRS_CHECK(words != nullptr || line_offsets[i + 1] == line_offsets[i], kInvalidArg, "words is null");
+      lines[i] = to_rects(words + line_offsets[i], line_offsets[i + 1] - line_offsets[i]);
+    }
+    auto r = e->engine->prepare_recognition_inputs(*in->input, lines);
+    *height = r.height;
+    *images = cmalloc<float>(r.images.size());
+    std::memcpy(*images, r.images.data(), r.images.size() * 4);
+    *widths = cmalloc<int>(n_lines);
+    *offsets = cmalloc<size_t>(n_lines);
+    for (size_t i = 0; i < n_lines; ++i) {
+      (*widths)[i] = r.widths[i];
+      (*offsets)[i] = r.offsets[i];
+    }
+  });
+}
+
 // ---- engine pool ---------------------------------------------------------------------------------
 int ocrs_b200_pool_create(const ocrs_b200_pool_params* p, ocrs_b200_pool** out) {
   return guard([&] {

@@ -66,11 +66,15 @@ struct Cfg {
   static constexpr int kBarBytes = 512;          // mbarriers + TMEM slot + scheduler ring
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarBytes;
   static constexpr int kTmemCols = 4 * COUT;     // HH[2] | X[2]
+  // promotion + epilogue warps: one per (TMEM lane quadrant, 32 output channels) -- 16 for COUT = 128, 8 for 64.
+  // (Eight warps of 64 channels each were measured falling behind the MMAs at every tile boundary: the MMA thread
+  // then waits for an accumulator buffer, profiles/r02b_phase_timers.log.)
+  static constexpr int kEpiWarps = 4 * (COUT / 32);
+  static constexpr int kThreads = 32 * (kEpiWarps + 2);  // + TMA / scheduler warp + MMA warp
   static_assert(kStages > kGroupKb, "a promotion group must fit in the stage ring with room to prefetch");
 };
 
 constexpr int kTW = 16, kTH = 8;   // pixel tile: 8 rows x 16 columns = 128 TMEM lanes, lane = th*16 + tw
-constexpr int kConvThreads = 320;  // warps 0-7: promotion + epilogue, warp 8: TMA + tile scheduler, warp 9: MMA
 constexpr int kSched = 4;          // depth of the tile ring between the scheduler and the other roles
 
 // One entry of the tile ring (written by the scheduler thread, read by the MMA thread and the
@@ -112,7 +116,7 @@ __device__ __forceinline__ void fence_tensormap_acquire(const void* p) {
 // [0] tiles, [1] k-blocks, [2] wait tile ring, [3] wait x_empty, [4] wait hh_empty, [5] wait operands
 // (HH phase), [6] issue HH, [7] issue X + commits, [8] total cycles in the tile loop.
 template <int KC, int COUT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Cfg<KC, COUT>::kThreads), 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                   const CUtensorMap* __restrict__ maps, const RaggedDesc* __restrict__ groups, int n_groups,
                   int n_tiles, int* __restrict__ counter, const float* __restrict__ bias, act_t* __restrict__ out_hi,
@@ -146,17 +150,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(hh_full(b), 1);
-      mbar_init(hh_empty(b), 8);
+      mbar_init(hh_empty(b), C::kEpiWarps);
       mbar_init(x_full(b), 1);
-      mbar_init(x_empty(b), 8);
+      mbar_init(x_empty(b), C::kEpiWarps);
     }
     for (int s = 0; s < kSched; ++s) {
       mbar_init(sched_full(s), 1);
-      mbar_init(sched_empty(s), 9);  // MMA thread + 8 promotion warps
+      mbar_init(sched_empty(s), C::kEpiWarps + 1);  // MMA thread + the promotion warps
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == C::kEpiWarps) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,7 +170,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
   const int chunks = Cin / KC;
   const int nkb = 9 * chunks;
 
-  if (warp == 8) {
+  if (warp == C::kEpiWarps) {
     if (lane == 0) {
       // ---------------- tile scheduler + TMA producer ----------------
       uint32_t stage = 0, par = 0;
@@ -221,7 +225,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         t = t_next;
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == C::kEpiWarps + 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       // c_format F32 (bit 4), a/b format F16 (0 at bits 7, 10), N >> 3 at 17, M >> 4 at 24
@@ -338,19 +342,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
       }
     }
   } else {
-    // ---------------- promotion + epilogue: warps 0-7 ----------------
+    // ---------------- promotion + epilogue: warps 0 .. kEpiWarps-1 ----------------
     // warp & 3 = TMEM lane quadrant (a warp may only touch lanes 32*(warp % 4)..+31), warp >> 2 = which
-    // half of the output channels; each thread keeps COUT / 2 partial sums.
+    // 32 output channels; each thread keeps 32 partial sums.
     constexpr int kRowsPerWarp = 32 / kTW;
-    constexpr int CH = COUT / 2;
+    constexpr int CH = 32;
     const int wq = warp & 3, hsel = warp >> 2;
     const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + (uint32_t)(hsel * CH);
     const int th = wq * kRowsPerWarp + lane / kTW, tw = lane % kTW;
     const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
     uint32_t gc = 0;
+    const bool etime = dbg != nullptr && warp == 0 && lane == 0;
+    unsigned long long e_ring = 0, e_hhf = 0, e_promo = 0, e_xf = 0, e_epi = 0;
     for (uint32_t ti = 0;; ++ti) {
       const uint32_t slot = ti & (kSched - 1);
+      long long q0 = etime ? clock64() : 0;
       mbar_wait(sched_full(slot), (ti / kSched) & 1);
+      if (etime) e_ring += (unsigned long long)(clock64() - q0);
       const TileEntry e = ring_p[slot];
       __syncwarp();
       if (lane == 0) mbar_arrive(sched_empty(slot));
@@ -360,8 +368,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
       for (int c = 0; c < CH; ++c) acc[c] = 0.f;
       for (int g = 0; g < ngroups; ++g, ++gc) {
         const uint32_t b = gc & 1;
+        long long q1 = etime ? clock64() : 0;
         mbar_wait(hh_full(b), (gc >> 1) & 1);
         tc_fence_after();
+        long long q2 = etime ? clock64() : 0;
         if constexpr (CH == 64) {
           // both TMEM loads of the group in flight before the single wait
           uint32_t r0[32], r1[32];
@@ -386,10 +396,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(hh_empty(b));
+        if (etime) {
+          e_hhf += (unsigned long long)(q2 - q1);
+          e_promo += (unsigned long long)(clock64() - q2);
+        }
       }
       const uint32_t tp = ti & 1;
+      long long q3 = etime ? clock64() : 0;
       mbar_wait(x_full(tp), (ti >> 1) & 1);
       tc_fence_after();
+      long long q4 = etime ? clock64() : 0;
 #pragma unroll
       for (int c0 = 0; c0 < CH; c0 += 32) {
         uint32_t r[32];
@@ -408,10 +424,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
 #pragma unroll
       for (int c0 = 0; c0 < CH; c0 += 8) {
         uint32_t hp[4], lp[4];
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0 + 4));
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-          float v0 = acc[c0 + j] + __ldg(bias + hsel * CH + c0 + j);
-          float v1 = acc[c0 + j + 1] + __ldg(bias + hsel * CH + c0 + j + 1);
+          float v0 = acc[c0 + j] + bb[j];
+          float v1 = acc[c0 + j + 1] + bb[j + 1];
           if (relu) {
             v0 = fmaxf(v0, 0.f);
             v1 = fmaxf(v1, 0.f);
@@ -424,7 +443,405 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
             v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
           }
-          split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
+          if (writer) split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
+        }
+        if (writer) {
+          *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(out_lo + opix * COUT + hsel * CH + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        }
+      }
+      if (etime) {
+        e_xf += (unsigned long long)(q4 - q3);
+        e_epi += (unsigned long long)(clock64() - q4);
+      }
+    }
+    if (etime) {
+      atomicAdd(dbg + 10, e_ring);
+      atomicAdd(dbg + 11, e_hhf);
+      atomicAdd(dbg + 12, e_promo);
+      atomicAdd(dbg + 13, e_xf);
+      atomicAdd(dbg + 14, e_epi);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::kEpiWarps) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair form of the kernel for the COUT = 128, KC = 64 layers: two CTAs of a cluster (the two SMs of a
+// TPC) run ONE tcgen05.mma.cta_group::2 of M = 256 per step -- each CTA owns its own 128-pixel tile (A
+// operand, its own TMEM accumulators) and HALF of the weight tile (64 of the 128 output channels); the
+// tensor cores of both SMs read both halves.  Per CTA and k-block the operand traffic drops from 64 KB to
+// 48 KB of TMA writes and from 8 KB to 6 KB of shared-memory reads per MMA, which is what bounds the
+// single-CTA kernel (it sits at the L2 -> SM delivery rate with the tensor pipe ~50 % active).
+// Protocol (rank 0 = leader):
+//   * tiles are drawn in PAIRS from the global counter by the leader's scheduler thread, which writes the
+//     peer's ring entry through DSMEM; a missing second tile is a dummy (TMA zero fill, no stores);
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (expect_tx = 2 stages' bytes);
+//   * only the leader issues MMAs; tcgen05.commit ... multicast::cluster releases the stage in both CTAs
+//     and publishes the accumulators to both CTAs' promotion warps;
+//   * the promotion warps of both CTAs return accumulator buffers on the leader's barriers (remote arrive).
+// The arithmetic per output pixel is that of the single-CTA kernel (same MMA order into the same two
+// accumulators), so the results are bit-identical.
+// ------------------------------------------------------------------------------------------
+template <int COUT>
+struct PairCfg {
+  static constexpr int kKC = 64;
+  static constexpr int kABytes = 128 * kKC * 2;            // one plane of the A tile
+  static constexpr int kBHalf = (COUT / 2) * kKC * 2;      // one plane of this CTA's half of the weights
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBHalf;
+  static constexpr int kStages = 4;
+  static constexpr int kGroupKb = 2;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
+  static constexpr int kTmemCols = 4 * COUT;
+  static constexpr int kEpiWarps = 4 * (COUT / 32);
+  static constexpr int kThreads = 32 * (kEpiWarps + 2);
+};
+
+__device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+// TMA loads whose completion is signalled on `bar_cluster` (a shared::cluster address: the leader's barrier)
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                             uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// bounded cluster-scope wait (young kernel: a protocol bug must trap, not hang the GPU)
+__device__ __forceinline__ void mbar_wait_cluster_trap(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 26); ++i) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+template <int COUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<COUT>::kThreads), 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                    const CUtensorMap* __restrict__ maps, const RaggedDesc* __restrict__ groups, int n_groups, int n_tiles,
+                    int* __restrict__ counter, const float* __restrict__ bias, act_t* __restrict__ out_hi,
+                    act_t* __restrict__ out_lo, int Cin, int relu, int ph, int pw, float promo_scale, int* __restrict__ ovf,
+                    unsigned long long* __restrict__ dbg) {
+  using C = PairCfg<COUT>;
+  constexpr int KC = C::kKC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t base = (smem0 + 1023u) & ~1023u;
+  const uint32_t bar_base = base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };       // the leader's are used
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  const uint32_t aux = bar_base + 8u * (2 * C::kStages);
+  auto hh_full = [&](int b) { return aux + 8u * b; };
+  auto hh_empty = [&](int b) { return aux + 8u * (2 + b); };      // the leader's are used
+  auto x_full = [&](int b) { return aux + 8u * (4 + b); };
+  auto x_empty = [&](int b) { return aux + 8u * (6 + b); };       // the leader's are used
+  auto sched_full = [&](int s) { return aux + 8u * (8 + s); };
+  auto sched_empty = [&](int s) { return aux + 8u * (8 + kSched + s); };  // the leader's are used
+  const uint32_t tmem_slot = aux + 8u * (8 + 2 * kSched);
+  const uint32_t ring = tmem_slot + 16u;
+  static_assert(8 * (2 * 4 + 8 + 2 * kSched) + 16 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
+  TileEntry* ring_p = reinterpret_cast<TileEntry*>(smem_raw + (ring - smem0));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);   // leader: its producer arms; both CTAs' loads complete_tx on it
+      mbar_init(empty_bar(s), 1);  // one multicast commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(hh_full(b), 1);
+      mbar_init(hh_empty(b), 2 * C::kEpiWarps);  // leader: the promotion warps of both CTAs
+      mbar_init(x_full(b), 1);
+      mbar_init(x_empty(b), 2 * C::kEpiWarps);
+    }
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(sched_full(s), 1);
+      mbar_init(sched_empty(s), 2 * C::kEpiWarps + 2);  // leader: MMA thread + peer's TMA thread + all promotion warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == C::kEpiWarps) tmem_alloc2(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  cluster_sync_all();  // both CTAs' barriers and tensor memory exist before anything crosses the pair
+
+  const int chunks = Cin / KC;
+  const int nkb = 9 * chunks;
+  const int n_pairs = (n_tiles + 1) / 2;
+
+  if (warp == C::kEpiWarps) {
+    if (lane == 0) {
+      // ---------------- tile scheduler (leader) + TMA producer (both CTAs) ----------------
+      uint32_t stage = 0, par = 0;
+      int cur_g = 0, last_map_g = -1;
+      RaggedDesc gd = groups[0];
+      int pr = leader ? atomicAdd(counter, 1) : 0;
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        TileEntry e;
+        if (leader) {
+          mbar_wait_cluster_trap(sched_empty(slot), ((ti / kSched) & 1) ^ 1);
+          TileEntry ent[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            TileEntry& x = ent[k];
+            x.g = -1;
+            x.n = x.h0 = x.w0 = x.H = x.W = x.OH = x.OW = 0;
+            x.out_off = 0;
+            x.pad = 0;  // pad = 1: real tile, 0: dummy (the pair's second tile does not exist)
+            if (pr < n_pairs) {
+              const int t = min(2 * pr + k, n_tiles - 1);
+              while (cur_g + 1 < n_groups && __ldg(&groups[cur_g + 1].first) <= t) {
+                ++cur_g;
+                gd = groups[cur_g];
+              }
+              int l = t - gd.first;
+              x.g = cur_g;
+              x.w0 = (l % gd.tiles_w) * kTW;
+              l /= gd.tiles_w;
+              x.h0 = (l % gd.tiles_h) * kTH;
+              x.n = l / gd.tiles_h;
+              x.H = gd.H; x.W = gd.W; x.OH = gd.OH; x.OW = gd.OW;
+              x.out_off = gd.out_off;
+              x.pad = (2 * pr + k < n_tiles) ? 1 : 0;
+              if (!x.pad) x.n = gd.N;  // outside the tensor: TMA fills zeros
+            }
+          }
+          ring_p[slot] = ent[0];
+          // the peer's entry through DSMEM (three 16-byte stores), then release-arrive on both rings
+          const uint32_t peer_entry = mapa(ring + slot * (uint32_t)sizeof(TileEntry), 1);
+          const uint4* src = reinterpret_cast<const uint4*>(&ent[1]);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) st_cluster_v4(peer_entry + 16u * q, src[q]);
+          mbar_arrive_remote_release(mapa(sched_full(slot), 1));
+          mbar_arrive(sched_full(slot));
+          e = ent[0];
+        } else {
+          mbar_wait_cluster_trap(sched_full(slot), (ti / kSched) & 1);
+          e = ring_p[slot];
+          mbar_arrive_remote_release(mapa(sched_empty(slot), 0));
+        }
+        if (e.g < 0) break;
+        int pr_next = 0;
+        if (leader) pr_next = atomicAdd(counter, 1);  // in flight while this tile's loads are issued
+        const CUtensorMap* m_hi = maps + 2 * e.g;
+        const CUtensorMap* m_lo = m_hi + 1;
+        if (e.g != last_map_g) {
+          fence_tensormap_acquire(m_hi);
+          fence_tensormap_acquire(m_lo);
+          last_map_g = e.g;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_trap(empty_bar(stage), par ^ 1);
+          const uint32_t st = base + stage * C::kStageBytes;
+          const uint32_t lead_full = mapa(full_bar(stage), 0);
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+          const int tap = kb / chunks, c0 = (kb - tap * chunks) * KC;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          tma2_load_4d(st, m_hi, c0, e.w0 + kw - 1, e.h0 + kh - 1, e.n, lead_full);
+          tma2_load_4d(st + C::kABytes, m_lo, c0, e.w0 + kw - 1, e.h0 + kh - 1, e.n, lead_full);
+          tma2_load_2d(st + 2 * C::kABytes, &tm_w_hi, tap * Cin + c0, (int)crank * (COUT / 2), lead_full);
+          tma2_load_2d(st + 2 * C::kABytes + C::kBHalf, &tm_w_lo, tap * Cin + c0, (int)crank * (COUT / 2), lead_full);
+          if (++stage == C::kStages) { stage = 0; par ^= 1; }
+        }
+        pr = pr_next;
+      }
+    }
+  } else if (warp == C::kEpiWarps + 1) {
+    if (lane == 0 && leader) {
+      // ---------------- MMA issuer (leader only) ----------------
+      // c_format F32 (bit 4), a/b format F16, N >> 3 at 17, M >> 4 at 24 with M = 256 over the pair
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((256u >> 4) << 24);
+      uint32_t stage = 0, par = 0, gc = 0;
+      unsigned long long c_sched = 0, c_xe = 0, c_hhe = 0, c_full = 0, c_iss = 0, n_tiles_done = 0;
+      const bool timing = dbg != nullptr;
+      const long long t_begin = timing ? clock64() : 0;
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        long long c0 = timing ? clock64() : 0;
+        mbar_wait_trap(sched_full(slot), (ti / kSched) & 1);
+        int g;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(g) : "r"(ring + slot * (uint32_t)sizeof(TileEntry)) : "memory");
+        mbar_arrive(sched_empty(slot));
+        if (g < 0) break;
+        const uint32_t tp = ti & 1;
+        const uint32_t d_x = tmem_base + 2 * COUT + tp * COUT;
+        long long c1 = timing ? clock64() : 0;
+        mbar_wait_cluster_trap(x_empty(tp), ((ti >> 1) & 1) ^ 1);
+        long long c2 = timing ? clock64() : 0;
+        c_sched += (unsigned long long)(c1 - c0);
+        c_xe += (unsigned long long)(c2 - c1);
+        for (int kb = 0; kb < nkb; ++gc) {
+          const uint32_t b = gc & 1;
+          const uint32_t d_hh = tmem_base + b * COUT;
+          const int nk = min(C::kGroupKb, nkb - kb);
+          long long g0 = timing ? clock64() : 0;
+          mbar_wait_cluster_trap(hh_empty(b), ((gc >> 1) & 1) ^ 1);
+          tc_fence_after();
+          long long g1 = timing ? clock64() : 0;
+          c_hhe += (unsigned long long)(g1 - g0);
+          for (int j = 0; j < nk; ++j) {
+            long long w0 = timing ? clock64() : 0;
+            mbar_wait_cluster_trap(full_bar(stage), par);
+            tc_fence_after();
+            if (timing) c_full += (unsigned long long)(clock64() - w0);
+            const uint64_t d0 = make_desc<KC>(base + stage * C::kStageBytes);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              const uint64_t da_hi = d0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABytes >> 4);
+              const uint64_t db_hi = da_hi + (uint64_t)((2 * C::kABytes) >> 4), db_lo = db_hi + (uint64_t)(C::kBHalf >> 4);
+              umma2_f16(d_hh, da_hi, db_hi, idesc, (j | k) ? 1u : 0u);
+              umma2_f16(d_x, da_hi, db_lo, idesc, (kb | j | k) ? 1u : 0u);
+              umma2_f16(d_x, da_lo, db_hi, idesc, 1u);
+            }
+            umma2_commit_mc(empty_bar(stage), 3);
+            if (++stage == C::kStages) { stage = 0; par ^= 1; }
+          }
+          umma2_commit_mc(hh_full(b), 3);
+          if (timing) c_iss += (unsigned long long)(clock64() - g1);
+          kb += nk;
+        }
+        umma2_commit_mc(x_full(tp), 3);
+        ++n_tiles_done;
+      }
+      if (timing) {
+        atomicAdd(dbg + 0, 2 * n_tiles_done);
+        atomicAdd(dbg + 1, n_tiles_done * (unsigned long long)nkb);
+        atomicAdd(dbg + 2, c_sched);
+        atomicAdd(dbg + 3, c_xe);
+        atomicAdd(dbg + 4, c_hhe);
+        atomicAdd(dbg + 5, c_full);
+        atomicAdd(dbg + 6, c_iss - c_full);
+        atomicAdd(dbg + 7, 0ull);
+        atomicAdd(dbg + 8, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(dbg + 9, 1ull);
+      }
+    }
+  } else {
+    // ---------------- promotion + epilogue (both CTAs, own tensor memory) ----------------
+    constexpr int kRowsPerWarp = 32 / kTW;
+    constexpr int CH = 32;
+    const int wq = warp & 3, hsel = warp >> 2;
+    const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + (uint32_t)(hsel * CH);
+    const int th = wq * kRowsPerWarp + lane / kTW, tw = lane % kTW;
+    const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
+    uint32_t gc = 0;
+    int sink = 0;  // overflow flag target of a dummy tile (its values are meaningless)
+    for (uint32_t ti = 0;; ++ti) {
+      const uint32_t slot = ti & (kSched - 1);
+      mbar_wait_cluster_trap(sched_full(slot), (ti / kSched) & 1);
+      const TileEntry e = ring_p[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_release(mapa(sched_empty(slot), 0));
+      if (e.g < 0) break;
+      const bool real_tile = e.pad != 0;
+      float acc[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+      for (int g = 0; g < ngroups; ++g, ++gc) {
+        const uint32_t b = gc & 1;
+        mbar_wait_trap(hh_full(b), (gc >> 1) & 1);
+        tc_fence_after();
+        {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_base + b * COUT, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(r[j]), promo_scale, acc[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(mapa(hh_empty(b), 0));  // no data handed over: the TMEM reads are done
+      }
+      const uint32_t tp = ti & 1;
+      mbar_wait_trap(x_full(tp), (ti >> 1) & 1);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + 2 * COUT + tp * COUT, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_relaxed(mapa(x_empty(tp), 0));
+
+      const int h = e.h0 + th, w = e.w0 + tw;
+      const int oh = h / ph, ow = w / pw;
+      const bool writer = real_tile && (ph == 1 || (lane & kTW) == 0) && (pw == 1 || (lane & 1) == 0) && oh < e.OH && ow < e.OW;
+      const size_t opix = (size_t)e.out_off + ((size_t)e.n * e.OH + oh) * e.OW + ow;
+#pragma unroll
+      for (int c0 = 0; c0 < CH; c0 += 8) {
+        uint32_t hp[4], lp[4];
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0 + 4));
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          float v0 = acc[c0 + j] + bb[j];
+          float v1 = acc[c0 + j + 1] + bb[j + 1];
+          if (relu) {
+            v0 = fmaxf(v0, 0.f);
+            v1 = fmaxf(v1, 0.f);
+          }
+          if (ph == 2) {
+            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, kTW));
+            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, kTW));
+          }
+          if (pw == 2) {
+            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
+            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
+          }
+          if (writer) split2(v0, v1, hp[j / 2], lp[j / 2], real_tile ? ovf : &sink);
         }
         if (writer) {
           *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
@@ -436,7 +853,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, C::kTmemCols);
+  cluster_sync_all();  // the peer may still read this CTA's operands / signal its barriers
+  if (warp == C::kEpiWarps) tmem_dealloc2(tmem_base, C::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -671,6 +1089,47 @@ bool conv_debug() {
   return on;
 }
 
+bool conv_pair_enabled() {
+  static const bool on = [] { const char* e = std::getenv("OCRS_B200_CONV_PAIR"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
+template <int COUT>
+void launch_conv_pair(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
+                      const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
+  using C = PairCfg<COUT>;
+  const int Cin = w.Cin;
+  uint64_t wd[2] = {(uint64_t)9 * Cin, (uint64_t)COUT};
+  uint64_t ws[1] = {(uint64_t)9 * Cin * 2};
+  uint32_t wb[2] = {(uint32_t)C::kKC, (uint32_t)(COUT / 2)};  // each CTA loads its half of the output channels
+  CUtensorMap tm_w_hi = make_map(w.w_hi.ptr, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tm_w_lo = make_map(w.w_lo.ptr, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+  OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_pair_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  const int n_pairs = (n_tiles + 1) / 2;
+  const int grid = 2 * std::max(1, std::min(n_pairs, sm_count() / 2));
+  unsigned long long* d_dbg = nullptr;
+  if (conv_debug()) {
+    OCRS_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_dbg), 16 * sizeof(unsigned long long), st));
+    OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 16 * sizeof(unsigned long long), st));
+  }
+  conv3x3_pair_kernel<COUT><<<grid, C::kThreads, C::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles,
+                                                                       d_counter, w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph,
+                                                                       pw, promo_scale(), ovf, d_dbg);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+  if (d_dbg) {
+    unsigned long long h[16];
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OCRS_CUDA_CHECK(cudaFreeAsync(d_dbg, st));
+    const double kb = (double)std::max<unsigned long long>(h[1], 1), cl = (double)std::max<unsigned long long>(h[9], 1);
+    fprintf(stderr,
+            "[conv dbg PAIR] Cin %d Cout %d pool %dx%d: %llu tiles, %d groups, %.0f clusters | per k-block of M=256 (cycles): ring %.0f, "
+            "x_empty %.0f, hh_empty %.0f, operands %.0f, issue %.0f | loop total %.0f (per cluster %.0f cycles)\n",
+            Cin, COUT, ph, pw, h[0], n_groups, cl, h[2] / kb, h[3] / kb, h[4] / kb, h[5] / kb, h[6] / kb, h[8] / kb, h[8] / cl);
+  }
+}
+
 template <int KC, int COUT>
 void launch_conv(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
                  const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
@@ -692,7 +1151,7 @@ void launch_conv(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_gr
     OCRS_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_dbg), 16 * sizeof(unsigned long long), st));
     OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 16 * sizeof(unsigned long long), st));
   }
-  conv3x3_tc_kernel<KC, COUT><<<grid, kConvThreads, C::kSmemBytes, st>>>(
+  conv3x3_tc_kernel<KC, COUT><<<grid, C::kThreads, C::kSmemBytes, st>>>(
       tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles, d_counter, w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph, pw,
       promo_scale(), ovf, d_dbg, conv_hh_first() ? 1 : 0);
   count_launch();
@@ -703,6 +1162,7 @@ void launch_conv(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_gr
     OCRS_CUDA_CHECK(cudaStreamSynchronize(st));
     OCRS_CUDA_CHECK(cudaFreeAsync(d_dbg, st));
     const double kb = (double)std::max<unsigned long long>(h[1], 1), ctas = (double)std::max<unsigned long long>(h[9], 1);
+    const double tl = (double)std::max<unsigned long long>(h[0], 1);
     fprintf(stderr,
             "[conv dbg] Cin %d Cout %d pool %dx%d: %llu tiles, %d groups, %.0f CTAs | per k-block (cycles): ring %.0f, x_empty %.0f, "
             "hh_empty %.0f, operands %.0f, issue HH %.0f, issue X %.0f | loop total %.0f (per CTA %.0f cycles)\n",
@@ -833,6 +1293,10 @@ void conv3x3_ragged(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n
   if (n_tiles == 0 || n_groups == 0) return;
   OCRS_CHECK((ph == 1 || ph == 2) && (pw == 1 || pw == 2), kInternal, "conv3x3 (tensor core): fused pool must be 1 or 2");
   const bool k64 = (w.Cin % 64 == 0);
+  if (k64 && w.Cout == 128 && conv_pair_enabled()) {
+    launch_conv_pair<128>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+    return;
+  }
   if (k64 && w.Cout == 128) launch_conv<64, 128>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
   else if (k64 && w.Cout == 64) launch_conv<64, 64>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
   else if (!k64 && w.Cout == 128) launch_conv<32, 128>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);

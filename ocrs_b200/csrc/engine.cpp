@@ -281,6 +281,60 @@ std::unique_ptr<OcrInput> Engine::prepare_input(const void* pixels, int dtype, i
   return in;
 }
 
+std::vector<std::unique_ptr<OcrInput>> Engine::prepare_inputs(const std::vector<PageSpec>& pages) {
+  // batched fast path: u8 HWC RGB pages of one shape -> one staging buffer, one conversion launch, one wait.
+  // Anything else goes page by page through prepare_input (same kernels, same bits).
+  const int N = (int)pages.size();
+  bool fast = N > 1;
+  for (int i = 0; i < N && fast; ++i) {
+    const PageSpec& p = pages[i];
+    fast = p.pixels != nullptr && p.dtype == 0 && p.order == 0 && p.C == 3 && p.H == pages[0].H && p.W == pages[0].W &&
+           (int64_t)p.H * p.W > 0 && ((int64_t)p.H * p.W) % 4 == 0 && (!p.on_device || reinterpret_cast<uintptr_t>(p.pixels) % 4 == 0);
+  }
+  std::vector<std::unique_ptr<OcrInput>> out;
+  if (!fast) {
+    for (const PageSpec& p : pages) out.push_back(prepare_input(p.pixels, p.dtype, p.order, p.H, p.W, p.C, p.on_device));
+    return out;
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  const int H = pages[0].H, W = pages[0].W;
+  const size_t hw = (size_t)H * W, bytes = hw * 3;
+  const size_t slot = (bytes + 255) / 256 * 256;
+  int n_host = 0;
+  for (const PageSpec& p : pages) n_host += p.on_device ? 0 : 1;
+  std::shared_ptr<Storage> staging;
+  if (n_host) staging = std::make_shared<Storage>(slot * (size_t)n_host, st_);
+  std::vector<img::PagePrepare> tab((size_t)N);
+  int k = 0;
+  for (int i = 0; i < N; ++i) {
+    auto in = std::make_unique<OcrInput>();
+    in->H = H; in->W = W; in->device = device_;
+    in->store = std::make_shared<Storage>(hw * sizeof(float), st_);
+    const void* src = pages[i].pixels;
+    if (!pages[i].on_device) {
+      void* d = static_cast<char*>(staging->ptr) + slot * (size_t)k++;
+      OCRS_CUDA_CHECK(cudaMemcpyAsync(d, pages[i].pixels, bytes, cudaMemcpyHostToDevice, st_));
+      h2d_bytes_ += (int64_t)bytes;
+      src = d;
+    }
+    tab[i] = img::PagePrepare{src, in->grey()};
+    out.push_back(std::move(in));
+  }
+  if (n_host) {
+    if (!ev_copy_) OCRS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
+    OCRS_CUDA_CHECK(cudaEventRecord(ev_copy_, st_));
+  }
+  tab_prep_.reserve(tab.size() * sizeof(img::PagePrepare));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(tab_prep_.ptr, tab.data(), tab.size() * sizeof(img::PagePrepare), cudaMemcpyHostToDevice, st_));
+  int tk = prof_.begin("stage/prepare_image", st_);
+  img::prepare_image_rgb8_batch(tab_prep_.as<img::PagePrepare>(), N, H, W, st_);
+  prof_.end(tk, st_, 0, (double)N * ((double)bytes + (double)hw * 4));
+  // the callers' buffers are only borrowed: wait for the copies, not for the kernel
+  if (n_host) OCRS_CUDA_CHECK(cudaEventSynchronize(ev_copy_));
+  return out;
+}
+
 namespace {
 DTensor wrap_tensor(float* ptr, std::vector<int64_t> shape) {
   DTensor t;
@@ -347,13 +401,18 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
   det_in_.reserve((size_t)N * plane * 4);
   int tk = prof_.begin("stage/resize_in", st_);
   double rs_bytes = 0;
-  for (int i = 0; i < N; ++i) {
-    const OcrInput& in = *pages[i];
-    rs_bytes += 4.0 * ((double)in.H * in.W + (double)plane);
-    OCRS_CHECK(in.device == device_, kInvalidArg, "input lives on another device");
-    int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
-    img::resize_padded(in.grey(), in.H, in.W, in.H + pb, in.W + pr, img::kBlackValue,
-                       det_in_.as<float>() + i * plane, in_h, in_w, 1, 0, 0, st_);
+  {
+    std::vector<img::PageResizeIn> tab((size_t)N);
+    for (int i = 0; i < N; ++i) {
+      const OcrInput& in = *pages[i];
+      rs_bytes += 4.0 * ((double)in.H * in.W + (double)plane);
+      OCRS_CHECK(in.device == device_, kInvalidArg, "input lives on another device");
+      int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
+      tab[i] = img::PageResizeIn{in.grey(), in.H, in.W, in.H + pb, in.W + pr};
+    }
+    tab_in_.reserve(tab.size() * sizeof(img::PageResizeIn));
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(tab_in_.ptr, tab.data(), tab.size() * sizeof(img::PageResizeIn), cudaMemcpyHostToDevice, st_));
+    img::resize_padded_batch(tab_in_.as<img::PageResizeIn>(), N, img::kBlackValue, det_in_.as<float>(), in_h, in_w, plane, st_);
   }
   prof_.end(tk, st_, 0, rs_bytes);
   ModelCost cost;
@@ -366,6 +425,26 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
              "detection output must be [N,1,H,W]");
   h_pin_.reserve((size_t)N * 8 * 4);
   int32_t* h_counters = h_pin_.as<int32_t>();
+  // detection epilogue (slice + resize + threshold) of all pages in one launch
+  {
+    std::vector<img::PageResizeOut> tab((size_t)N);
+    int max_h = 0, max_w = 0;
+    double rt_bytes = 0;
+    for (int i = 0; i < N; ++i) {
+      const OcrInput& in = *pages[i];
+      PageScratch& s = scratch_for(i, in.H, in.W);
+      int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
+      tab[i] = img::PageResizeOut{out.data + i * plane, nullptr, s.mask.as<uint8_t>(), in_h - pb, in_w - pr, in.H, in.W};
+      max_h = std::max(max_h, in.H);
+      max_w = std::max(max_w, in.W);
+      rt_bytes += 4.0 * (in_h - pb) * (in_w - pr) + (double)in.H * in.W;
+    }
+    tab_out_.reserve(tab.size() * sizeof(img::PageResizeOut));
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(tab_out_.ptr, tab.data(), tab.size() * sizeof(img::PageResizeOut), cudaMemcpyHostToDevice, st_));
+    int t1 = prof_.begin("stage/resize_threshold", st_);
+    img::resize_threshold_batch(tab_out_.as<img::PageResizeOut>(), N, in_w, max_h, max_w, text_threshold_, st_);
+    prof_.end(t1, st_, 0, rt_bytes);
+  }
   // post-processing of the N pages is independent: fork onto per-page side streams so the small,
   // latency-bound kernels (labelling, per-component border following) overlap
   const int n_aux = prof_.enabled ? 1 : std::min(N, 8);  // profiling brackets need serial kernels
@@ -375,12 +454,7 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
   for (int i = 0; i < N; ++i) {
     const OcrInput& in = *pages[i];
     cudaStream_t sa = aux_[i % n_aux];
-    PageScratch& s = scratch_for(i, in.H, in.W);
-    int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
-    int t1 = prof_.begin("stage/resize_threshold", sa);
-    img::resize_threshold(out.data + i * plane, in_h, in_w, in_h - pb, in_w - pr, nullptr, s.mask.as<uint8_t>(),
-                          in.H, in.W, text_threshold_, sa);
-    prof_.end(t1, sa, 0, 4.0 * (in_h - pb) * (in_w - pr) + (double)in.H * in.W);
+    PageScratch& s = *scratch_[i];
     int t2 = prof_.begin("stage/components_to_rects", sa);
     img::find_component_rects(s.mask.as<uint8_t>(), in.H, in.W, 2.0f /* detection.rs:50 */,
                               3.0f /* detection.rs:116 */, min_area_, s.bufs, sa);
@@ -830,6 +904,127 @@ std::vector<float> Engine::prepare_recognition_input(const OcrInput& in, const s
   OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
   *out_h = rec_h;
   *out_w = (int)rw;
+  return out;
+}
+
+std::vector<Engine::TextPixels> Engine::detect_text_pixels_batch(const std::vector<const OcrInput*>& pages, bool want_map,
+                                                                 bool want_mask) {
+  OCRS_CHECK(det_ != nullptr, kModelNotLoaded, "Detection model not loaded");  // lib.rs:211
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  const int N = (int)pages.size();
+  std::vector<TextPixels> result((size_t)N);
+  if (N == 0) return result;
+  const auto& shp = det_->input_shape();
+  OCRS_CHECK(shp.size() == 4 && shp[2] >= 0 && shp[3] >= 0, kRunFailed, "failed to get model dims");
+  const int in_h = (int)shp[2], in_w = (int)shp[3];
+  const int64_t plane = (int64_t)in_h * in_w;
+  det_in_.reserve((size_t)N * plane * 4);
+  {
+    std::vector<img::PageResizeIn> tab((size_t)N);
+    for (int i = 0; i < N; ++i) {
+      const OcrInput& in = *pages[i];
+      OCRS_CHECK(in.device == device_, kInvalidArg, "input lives on another device");
+      int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
+      tab[i] = img::PageResizeIn{in.grey(), in.H, in.W, in.H + pb, in.W + pr};
+    }
+    tab_in_.reserve(tab.size() * sizeof(img::PageResizeIn));
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(tab_in_.ptr, tab.data(), tab.size() * sizeof(img::PageResizeIn), cudaMemcpyHostToDevice, st_));
+    img::resize_padded_batch(tab_in_.as<img::PageResizeIn>(), N, img::kBlackValue, det_in_.as<float>(), in_h, in_w, plane, st_);
+  }
+  auto run_net = [&] { return det_->run(wrap_tensor(det_in_.as<float>(), {N, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_); };
+  const int tok = det_->tc_token();
+  DTensor out = run_net();
+  if (tok) {
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+    if (det_->take_tc_overflow(tok)) out = run_net();
+  }
+  OCRS_CHECK(out.shape.size() == 4 && out.numel() == (int64_t)N * plane, kWrongOutput, "detection output must be [N,1,H,W]");
+  for (int i = 0; i < N; ++i) {
+    const OcrInput& in = *pages[i];
+    PageScratch& s = scratch_for(i, in.H, in.W);
+    s.prob.reserve((size_t)in.H * in.W * 4 + 4);
+    int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
+    img::resize_threshold(out.data + i * plane, in_h, in_w, in_h - pb, in_w - pr, s.prob.as<float>(), s.mask.as<uint8_t>(), in.H,
+                          in.W, text_threshold_, st_);
+    result[i].H = in.H;
+    result[i].W = in.W;
+    const size_t hw = (size_t)in.H * in.W;
+    if (want_map) {
+      result[i].map.resize(hw);
+      OCRS_CUDA_CHECK(cudaMemcpyAsync(result[i].map.data(), s.prob.ptr, hw * 4, cudaMemcpyDeviceToHost, st_));
+      d2h_bytes_ += (int64_t)hw * 4;
+    }
+    if (want_mask) {
+      result[i].mask.resize(hw);
+      OCRS_CUDA_CHECK(cudaMemcpyAsync(result[i].mask.data(), s.mask.ptr, hw, cudaMemcpyDeviceToHost, st_));
+      d2h_bytes_ += (int64_t)hw;
+    }
+  }
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  return result;
+}
+
+Engine::LineImages Engine::prepare_recognition_inputs(const OcrInput& in,
+                                                      const std::vector<std::vector<RotatedRect>>& lines) {
+  OCRS_CHECK(rec_ != nullptr, kModelNotLoaded, "Recognition model not loaded");  // lib.rs:274
+  std::lock_guard<std::mutex> lk(mu_);
+  OCRS_CUDA_CHECK(cudaSetDevice(device_));
+  OCRS_CHECK(in.device == device_, kInvalidArg, "input lives on another device");
+  const int rec_h = (int)rec_input_height();
+  LineImages out;
+  out.height = rec_h;
+  const int n = (int)lines.size();
+  if (n == 0) return out;
+  std::vector<img::LineDesc> descs((size_t)n);
+  std::vector<int32_t> poly_xy;
+  int64_t dst_total = 0, cross_total = 0;
+  int max_w = 0, max_rows = 0;
+  for (int k = 0; k < n; ++k) {
+    OCRS_CHECK(!lines[k].empty(), kInvalidArg, "line has no words");
+    RectI line_rect;
+    layout::line_integral_rect(lines[k], &line_rect);
+    const uint32_t rw = layout::resized_line_width(geom::rwidth(line_rect), geom::rheight(line_rect), rec_h);
+    std::vector<PointI> poly = layout::line_polygon(lines[k]);
+    const RectI pr = layout::polygon_bounding_rect(poly);
+    img::LineDesc& d = descs[(size_t)k];
+    d.poly_off = (int32_t)(poly_xy.size() / 2);
+    d.poly_n = (int32_t)poly.size();
+    int non_horizontal = 0;
+    for (size_t v = 0; v < poly.size(); ++v) {
+      poly_xy.push_back(poly[v].x);
+      poly_xy.push_back(poly[v].y);
+      if (poly[v].y != poly[(v + 1) % poly.size()].y) ++non_horizontal;
+    }
+    d.top = pr.top; d.left = pr.left;
+    d.lh = std::max(geom::rheight(pr), 0); d.lw = std::max(geom::rwidth(pr), 0);
+    d.resized_width = (int32_t)rw; d.group_width = (int32_t)rw;  // no batch padding: exactly [height, w']
+    d.dst_off = dst_total; d.cross_off = cross_total; d.max_cross = non_horizontal; d.page = 0;
+    out.widths.push_back((int)rw);
+    out.offsets.push_back((size_t)dst_total);
+    dst_total += (int64_t)rec_h * rw;
+    cross_total += (int64_t)d.lh * (non_horizontal + 1);
+    max_w = std::max(max_w, (int)rw);
+    max_rows = std::max(max_rows, d.lh);
+  }
+  const float* page_ptr = in.grey();
+  int hw[2] = {in.H, in.W};
+  page_tab_.reserve(sizeof(float*) + 2 * sizeof(int));
+  line_desc_.reserve(descs.size() * sizeof(img::LineDesc));
+  poly_.reserve(poly_xy.size() * 4 + 4);
+  cross_.reserve((size_t)cross_total * 4 + 4);
+  rec_batch_.reserve((size_t)dst_total * 4 + 4);
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(page_tab_.ptr, &page_ptr, sizeof(float*), cudaMemcpyHostToDevice, st_));
+  int* d_hw = reinterpret_cast<int*>(page_tab_.as<char>() + sizeof(float*));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(d_hw, hw, sizeof(hw), cudaMemcpyHostToDevice, st_));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(line_desc_.ptr, descs.data(), descs.size() * sizeof(img::LineDesc), cudaMemcpyHostToDevice, st_));
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(poly_.ptr, poly_xy.data(), poly_xy.size() * 4, cudaMemcpyHostToDevice, st_));
+  img::crop_lines(page_tab_.as<const float*>(), d_hw, d_hw + 1, line_desc_.as<img::LineDesc>(), n, poly_.as<int32_t>(),
+                  cross_.as<int32_t>(), rec_batch_.as<float>(), rec_h, max_w, max_rows, st_);
+  out.images.resize((size_t)dst_total);
+  OCRS_CUDA_CHECK(cudaMemcpyAsync(out.images.data(), rec_batch_.ptr, out.images.size() * 4, cudaMemcpyDeviceToHost, st_));
+  d2h_bytes_ += dst_total * 4;
+  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
   return out;
 }
 

@@ -72,6 +72,14 @@ class Engine {
   std::unique_ptr<OcrInput> prepare_input(const void* pixels, int dtype, int order, int H, int W, int C,
                                           bool pixels_on_device = false);
 
+  // prepare_input for a batch of pages; pages of one shape (u8 HWC RGB) are converted by ONE launch.
+  struct PageSpec {
+    const void* pixels = nullptr;
+    int dtype = 0, order = 0, H = 0, W = 0, C = 0;
+    bool on_device = false;
+  };
+  std::vector<std::unique_ptr<OcrInput>> prepare_inputs(const std::vector<PageSpec>& pages);
+
   // lib.rs:207 / detection.rs:131-200 (host copy of the H x W probability map)
   std::vector<float> detect_text_pixels(const OcrInput& in);
   // lib.rs:193 / detection.rs:104-122, batched over pages; rects in contour-discovery order.
@@ -89,6 +97,24 @@ class Engine {
   // lib.rs:268 / recognition.rs:366-393: returns [input_height, resized_width] row-major.
   std::vector<float> prepare_recognition_input(const OcrInput& in, const std::vector<geom::RotatedRect>& line,
                                                int* out_h, int* out_w);
+
+  // Debug outputs of ocrs-cli (`--text-map`, `--text-mask`: main.rs:423-436) for a batch of pages in one
+  // detection pass: per page the H x W probability map and / or the thresholded mask (x > threshold).
+  struct TextPixels {
+    std::vector<float> map;     // empty unless requested
+    std::vector<uint8_t> mask;  // empty unless requested
+    int H = 0, W = 0;
+  };
+  std::vector<TextPixels> detect_text_pixels_batch(const std::vector<const OcrInput*>& pages, bool want_map, bool want_mask);
+  // `--text-line-images` (main.rs:441-443 -> write_preprocessed_text_line_images): the recognition inputs of ALL
+  // lines of a page in one crop launch.  Line i is [height, widths[i]] row-major at offsets[i] of `images`.
+  struct LineImages {
+    std::vector<float> images;
+    std::vector<int> widths;
+    std::vector<size_t> offsets;
+    int height = 0;
+  };
+  LineImages prepare_recognition_inputs(const OcrInput& in, const std::vector<std::vector<geom::RotatedRect>>& lines);
 
   // Whole pipeline on a batch of resident pages (detect -> layout -> recognise).
   std::vector<std::vector<TextLine>> ocr_pages(const std::vector<const OcrInput*>& pages);
@@ -135,6 +161,7 @@ class Engine {
   DeviceBuffer d_excluded_;
   std::vector<std::unique_ptr<PageScratch>> scratch_;
   DeviceBuffer det_in_, staging_, line_desc_, poly_, cross_, rec_batch_, ctc_scratch_, ctc_out_, page_tab_;
+  DeviceBuffer tab_in_, tab_out_, tab_prep_;  // per-batch page tables of the batched pixel kernels
   PinnedBuffer h_pin_;
   std::mutex mu_;
   Stats stats_;

@@ -185,6 +185,7 @@ struct Model::Impl {
   // tensor-core conv chains (Conv3x3 [+Relu] [+MaxPool]) keyed by their first node
   std::map<int, TcChain> tc_chains;
   std::map<int, std::unique_ptr<tc::GruWeightsTC>> tc_gru;  // per GRU node
+  std::unique_ptr<tc::LinearWeightsTC> head_fc;             // the packed head's Linear on the tensor cores
   // packed sequence head
   struct SeqHead {
     bool present = false;
@@ -196,6 +197,14 @@ struct Model::Impl {
   std::vector<int> tc_member;  // node is executed as part of a chain started earlier
   // detection-net fusions (fp32 CUDA cores)
   std::vector<int> dwpw_partner;     // per depthwise Conv node: index of the fused pointwise Conv (-1 = none)
+  // virtual input of a fused depthwise + pointwise node: the Concat (and the Pads feeding it) in front of
+  // it are absorbed -- the kernel reads the sources directly
+  struct SepPlan {
+    std::vector<std::string> src;   // source value names, in channel order
+    std::vector<int> pad_b, pad_r;  // end padding of each source (rows, columns)
+    std::vector<float> pad_v;
+  };
+  std::map<int, SepPlan> sep_plan;
   struct HeadFuse { int conv1x1 = -1, sigmoid = -1; };
   std::map<int, HeadFuse> head_fuse; // per ConvTranspose node: fused 1x1 conv + sigmoid
   bool tc_enabled = false;
@@ -308,6 +317,57 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
         impl->dwpw_partner[i] = j;
         m->skip_[j] = 1;
         impl->out_rename[i] = impl->out_rename[j].empty() ? pn.outputs[0] : impl->out_rename[j];
+        // ---- virtual input: Concat(axis 1) of tensors that may each be end-padded by a constant Pad ----
+        if (st[0] == 1) {
+          auto producer_of = [&](const std::string& name) -> int {
+            for (int q = 0; q < i; ++q)
+              if (!m->skip_[q] && !g.nodes[q].outputs.empty() && g.nodes[q].outputs[0] == name && impl->out_rename[q].empty()) return q;
+            return -1;
+          };
+          const int cn = producer_of(n.inputs[0]);
+          if (cn >= 0 && g.nodes[cn].op == "Concat" && g.nodes[cn].attr_i("axis", 0) == 1 && g.nodes[cn].inputs.size() >= 1 &&
+              g.nodes[cn].inputs.size() <= 2 && sole(n.inputs[0]) == i) {
+            Impl::SepPlan plan;
+            bool ok = true;
+            std::vector<int> pad_nodes;
+            for (const auto& in_name : g.nodes[cn].inputs) {
+              int pb = 0, pr = 0;
+              float pv = 0.f;
+              std::string src = in_name;
+              const int pd = producer_of(in_name);
+              if (pd >= 0 && g.nodes[pd].op == "Pad" && sole(in_name) == cn && g.nodes[pd].attr_s("mode", "constant") == "constant" &&
+                  g.nodes[pd].inputs.size() >= 2 && g.nodes[pd].inputs.size() <= 3) {
+                const TensorData* pt = winit(g.nodes[pd], 1);
+                const TensorData* vt = g.nodes[pd].inputs.size() > 2 && !g.nodes[pd].inputs[2].empty() ? winit(g.nodes[pd], 2) : nullptr;
+                bool pad_ok = pt != nullptr && (g.nodes[pd].inputs.size() < 3 || g.nodes[pd].inputs[2].empty() || vt != nullptr);
+                std::vector<int64_t> pv64;
+                if (pad_ok) {
+                  pv64 = pt->as_int64();
+                  pad_ok = pv64.size() == 8 && pv64[0] == 0 && pv64[1] == 0 && pv64[2] == 0 && pv64[3] == 0 && pv64[4] == 0 &&
+                           pv64[5] == 0 && pv64[6] > -4096 && pv64[7] > -4096 && pv64[6] < 4096 && pv64[7] < 4096;  // negative = crop
+                }
+                if (pad_ok && vt != nullptr) pad_ok = vt->dtype == onnx::kFloat && vt->numel() == 1;
+                if (pad_ok) {
+                  pb = (int)pv64[6];
+                  pr = (int)pv64[7];
+                  pv = vt ? vt->f32()[0] : 0.f;
+                  src = g.nodes[pd].inputs[0];
+                  pad_nodes.push_back(pd);
+                }
+              }
+              if (g.initializers.count(src)) ok = false;  // constant sources stay on the generic path
+              plan.src.push_back(src);
+              plan.pad_b.push_back(pb);
+              plan.pad_r.push_back(pr);
+              plan.pad_v.push_back(pv);
+            }
+            if (ok) {
+              m->skip_[cn] = 1;
+              for (int pd : pad_nodes) m->skip_[pd] = 1;
+              impl->sep_plan[i] = std::move(plan);
+            }
+          }
+        }
       } else if (n.op == "ConvTranspose" && m->fuse_relu_[i]) {
         const TensorData* w = winit(n, 1);
         if (!w || w->dims.size() != 4 || w->dims[2] != 2 || w->dims[3] != 2 || n.attr_i("group", 1) != 1) continue;
@@ -341,6 +401,11 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
   // remaining-use counts for the fused schedule
   for (int i = 0; i < nn_; ++i) {
     if (m->skip_[i]) continue;
+    auto sp = impl->sep_plan.find(i);
+    if (sp != impl->sep_plan.end()) {
+      for (const auto& in : sp->second.src) m->use_count_[in]++;
+      continue;  // the remaining inputs are initializers
+    }
     for (const auto& in : g.nodes[i].inputs)
       if (!in.empty()) m->use_count_[in]++;
   }
@@ -600,6 +665,15 @@ std::unique_ptr<Model> Model::load(const uint8_t* bytes, size_t len, int device)
       for (size_t k = 1; k < grus.size(); ++k)
         if (impl->tc_gru.at(grus[k])->I != 2 * hd.H) hd.present = false;
       if ((int)g.initializers.at(g.nodes[mm].inputs[1]).dims[0] != 2 * hd.H) hd.present = false;
+      if (hd.present && tc::linear_supported(hd.classes, 2 * hd.H) && std::getenv("OCRS_B200_DISABLE_TC_LINEAR") == nullptr) {
+        const auto& wt = g.initializers.at(g.nodes[mm].inputs[1]);  // [K][N]
+        const int64_t K = wt.dims[0], N = wt.dims[1];
+        std::vector<float> t((size_t)(K * N));
+        const float* wsrc = wt.f32();
+        for (int64_t k = 0; k < K; ++k)
+          for (int64_t c = 0; c < N; ++c) t[(size_t)(c * K + k)] = wsrc[k * N + c];
+        impl->head_fc = tc::prepare_linear(t.data(), g.initializers.at(m->fused_bias_[mm]).f32(), (int)N, (int)K);
+      }
     }
   }
 
@@ -735,9 +809,12 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
     }
     std::vector<Value> in;
     std::vector<bool> present;
-    for (const auto& name : n.inputs) {
+    const auto sep_it = impl->sep_plan.find(ni);
+    for (size_t ii = 0; ii < n.inputs.size(); ++ii) {
+      const std::string& name = n.inputs[ii];
+      const bool virt = ii == 0 && sep_it != impl->sep_plan.end();  // absorbed Concat: never materialised
       present.push_back(!name.empty());
-      in.push_back(name.empty() ? Value() : get(name));
+      in.push_back((name.empty() || virt) ? Value() : get(name));
     }
     auto has = [&](size_t i) { return i < in.size() && present[i]; };
     std::vector<Value> out;
@@ -746,21 +823,40 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
     int ptok = prof ? prof->begin(prof_prefix + op, st) : -1;
 
     if (op == "Conv" && impl->dwpw_partner[ni] >= 0) {
-      // depthwise 3x3 + pointwise 1x1 (+ReLU) in one kernel
+      // depthwise 3x3 + pointwise 1x1 (+ReLU) in one kernel; the input may be a virtual Concat of padded tensors
       const Node& pn = g.nodes[impl->dwpw_partner[ni]];
-      const Value& X = in[0];
-      OCRS_CHECK(!X.is_int && X.shape.size() == 4, kRunFailed, "Conv: expected 4-D input");
       Value PW = get(pn.inputs[1]);
       const float* dwb = has(2) ? in[2].t.data : nullptr;
       const float* pwb = (pn.inputs.size() > 2 && !pn.inputs[2].empty()) ? get(pn.inputs[2]).t.data : nullptr;
-      int N_ = (int)X.shape[0], C_ = (int)X.shape[1], H_ = (int)X.shape[2], W_ = (int)X.shape[3];
+      nn::SepInput srcs[2];
+      std::vector<Value> keep;  // sources stay alive until the launch is enqueued
+      int n_src = 0, N_ = 0, C_ = 0, H_ = 0, W_ = 0;
+      if (sep_it != impl->sep_plan.end()) {
+        const auto& plan = sep_it->second;
+        for (size_t k = 0; k < plan.src.size(); ++k) {
+          keep.push_back(get(plan.src[k]));
+          const Value& S = keep.back();
+          OCRS_CHECK(!S.is_int && S.shape.size() == 4, kRunFailed, "Concat: expected 4-D float inputs");
+          const int hv = (int)S.shape[2] + plan.pad_b[k], wv = (int)S.shape[3] + plan.pad_r[k];
+          OCRS_CHECK(hv > 0 && wv > 0, kRunFailed, "Pad: negative output dim");
+          if (k == 0) { N_ = (int)S.shape[0]; H_ = hv; W_ = wv; }
+          OCRS_CHECK((int)S.shape[0] == N_ && hv == H_ && wv == W_, kRunFailed, "Concat: shape mismatch");
+          srcs[n_src++] = nn::SepInput{S.t.data, (int)S.shape[1], (int)S.shape[2], (int)S.shape[3], plan.pad_v[k]};
+          C_ += (int)S.shape[1];
+        }
+      } else {
+        const Value& X = in[0];
+        OCRS_CHECK(!X.is_int && X.shape.size() == 4, kRunFailed, "Conv: expected 4-D input");
+        N_ = (int)X.shape[0]; C_ = (int)X.shape[1]; H_ = (int)X.shape[2]; W_ = (int)X.shape[3];
+        srcs[n_src++] = nn::SepInput{X.t.data, C_, H_, W_, 0.f};
+      }
       OCRS_CHECK(in[1].shape[0] == C_, kRunFailed, "Conv: channel mismatch");
       int K_ = (int)PW.shape[0];
       int stride = (int)n.attr_ints("strides", {1, 1})[0];
       int OH = (H_ + 2 - 3) / stride + 1, OW = (W_ + 2 - 3) / stride + 1;
       DTensor Y = alloc_tensor({N_, K_, OH, OW}, st);
-      nn::dwpw_conv(X.t.data, in[1].t.data, dwb, PW.t.data, pwb, Y.data, N_, C_, H_, W_, K_, stride,
-                    fuse_relu_[impl->dwpw_partner[ni]], st);
+      nn::dwpw_conv2(srcs, n_src, in[1].t.data, dwb, PW.t.data, pwb, Y.data, N_, H_, W_, K_, stride,
+                     fuse_relu_[impl->dwpw_partner[ni]], st);
       flops += 2.0 * N_ * OH * OW * (double)C_ * (9.0 + K_);
       out.push_back(dev_value(Y));
     } else if (op == "Conv") {
@@ -1217,7 +1313,8 @@ DTensor Model::run(const DTensor& input, cudaStream_t st, ModelCost* cost, Profi
       }
     }
     // release inputs whose last consumer just ran
-    for (const auto& name : n.inputs) {
+    const std::vector<std::string>& eff_inputs = sep_it != impl->sep_plan.end() ? sep_it->second.src : n.inputs;
+    for (const auto& name : eff_inputs) {
       if (name.empty()) continue;
       auto it = remaining.find(name);
       if (it != remaining.end() && --it->second <= 0) env.erase(name);
@@ -1488,9 +1585,17 @@ DTensor Model::run_seq_head(const float* X, int64_t rows, const std::vector<Pack
   const float* bias = reinterpret_cast<const float*>(dev_weights_.at(fused_bias_[hd.fc_node])->ptr);
   DTensor logits = alloc_tensor({rows, hd.classes}, st);
   int tk = prof ? prof->begin(prof_prefix + "Linear+LogSoftmax(packed)", st) : -1;
-  DTensor tmp = alloc_tensor({rows, hd.classes}, st);
-  nn::sgemm_nt(cur, Wt, bias, tmp.data, (int)rows, hd.classes, 2 * H, 0, st);
-  nn::log_softmax_lastdim(tmp.data, logits.data, rows, hd.classes, st);
+  if (impl_->head_fc) {
+    // split-bf16 tensor-core GEMM into a 128-column padded buffer, log-softmax over the real classes
+    const int npad = impl_->head_fc->Npad;
+    DTensor tmp = alloc_tensor({rows, npad}, st);
+    tc::linear_forward(cur, rows, *impl_->head_fc, tmp.data, alloc, st);
+    nn::log_softmax_rows(tmp.data, npad, logits.data, rows, hd.classes, st);
+  } else {
+    DTensor tmp = alloc_tensor({rows, hd.classes}, st);
+    nn::sgemm_nt(cur, Wt, bias, tmp.data, (int)rows, hd.classes, 2 * H, 0, st);
+    nn::log_softmax_lastdim(tmp.data, logits.data, rows, hd.classes, st);
+  }
   double f = 2.0 * (double)rows * hd.classes * 2 * H;
   flops += f;
   if (prof) prof->end(tk, st, f);

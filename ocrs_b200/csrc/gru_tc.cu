@@ -45,14 +45,17 @@ __global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restr
 
 // ------------------------------------------------------------------------------------------
 // C[M, Ntot] (f32) = A[M, K] * B[Ntot, K]^T + bias[Ntot]; A, B split bf16, K-major.
-// Tile 128 x 128, K chunks of 64, 3 stages (64 KB each).
+// Tile 128 x 128, K chunks of 32 (64-byte-swizzled rows), 3 stages of 32 KB: ~98 KB of shared memory and 128
+// TMEM columns per CTA, so TWO CTAs share an SM -- the kernel is a short main loop (K = 128 or 512) between a
+// prologue and an epilogue that nothing else overlaps, and a second resident CTA hides them.
 // ------------------------------------------------------------------------------------------
 constexpr int kGemmStages = 3;
-constexpr int kGemmTile = 128 * 64 * 2;                 // one operand plane of one stage
+constexpr int kGemmBK = 32;
+constexpr int kGemmTile = 128 * kGemmBK * 2;            // one operand plane of one stage (8 KB)
 constexpr int kGemmStageBytes = 4 * kGemmTile;          // A_hi, A_lo, B_hi, B_lo
 constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + 1024 + 256;
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const float* __restrict__ bias, float* __restrict__ Cout, int M, int Ntot, int K) {
@@ -80,7 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const int nkb = K / 64;
+  const int nkb = K / kGemmBK;
 
   if (warp == 0 && lane == 0) {
     for (int kb = 0; kb < nkb; ++kb) {
@@ -89,10 +92,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       mbar_wait(empty_bar(s), ph ^ 1);
       const uint32_t st = base + s * kGemmStageBytes;
       mbar_expect_tx(full_bar(s), kGemmStageBytes);
-      tma_load_2d(st, &tm_a_hi, kb * 64, m0, full_bar(s));
-      tma_load_2d(st + kGemmTile, &tm_a_lo, kb * 64, m0, full_bar(s));
-      tma_load_2d(st + 2 * kGemmTile, &tm_b_hi, kb * 64, n0, full_bar(s));
-      tma_load_2d(st + 3 * kGemmTile, &tm_b_lo, kb * 64, n0, full_bar(s));
+      tma_load_2d(st, &tm_a_hi, kb * kGemmBK, m0, full_bar(s));
+      tma_load_2d(st + kGemmTile, &tm_a_lo, kb * kGemmBK, m0, full_bar(s));
+      tma_load_2d(st + 2 * kGemmTile, &tm_b_hi, kb * kGemmBK, n0, full_bar(s));
+      tma_load_2d(st + 3 * kGemmTile, &tm_b_lo, kb * kGemmBK, n0, full_bar(s));
     }
   } else if (warp == 1 && lane == 0) {
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -103,10 +106,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       tc_fence_after();
       const uint32_t st = base + s * kGemmStageBytes;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kGemmBK / 16; ++k) {
         const uint32_t koff = k * 32;
-        const uint64_t da_hi = make_desc<64>(st + koff), da_lo = make_desc<64>(st + kGemmTile + koff);
-        const uint64_t db_hi = make_desc<64>(st + 2 * kGemmTile + koff), db_lo = make_desc<64>(st + 3 * kGemmTile + koff);
+        const uint64_t da_hi = make_desc<32>(st + koff), da_lo = make_desc<32>(st + kGemmTile + koff);
+        const uint64_t db_hi = make_desc<32>(st + 2 * kGemmTile + koff), db_lo = make_desc<32>(st + 3 * kGemmTile + koff);
         umma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
         umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
         umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
@@ -768,6 +771,58 @@ std::unique_ptr<GruWeightsTC> prepare_gru(const float* W, const float* R, const 
   return g;
 }
 
+namespace {
+// xw[M][Ntot] = A W^T + bias through gemm_tc_kernel; A given as f32 [M][K] (split here)
+void gemm_split_bf16(const float* X, int64_t M, int K, const void* w_hi, const void* w_lo, const float* bias, int Ntot, float* out,
+                     const ScratchAlloc& alloc, cudaStream_t st) {
+  auto* x_hi = static_cast<__nv_bfloat16*>(alloc((size_t)M * K * 2));
+  auto* x_lo = static_cast<__nv_bfloat16*>(alloc((size_t)M * K * 2));
+  const int64_t n8 = M * K / 8;
+  split_kernel<<<(unsigned)ceil_div(n8, 256), 256, 0, st>>>(X, x_hi, x_lo, n8);
+  count_launch();
+  uint64_t ad[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t as[1] = {(uint64_t)K * 2};
+  uint32_t box[2] = {(uint32_t)kGemmBK, 128};
+  CUtensorMap ta_hi = make_map(x_hi, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  CUtensorMap ta_lo = make_map(x_lo, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  uint64_t bd[2] = {(uint64_t)K, (uint64_t)Ntot};
+  CUtensorMap tb_hi = make_map(w_hi, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  CUtensorMap tb_lo = make_map(w_lo, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+  dim3 grid((unsigned)ceil_div(M, 128), (unsigned)(Ntot / 128));
+  gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, bias, out, (int)M, Ntot, K);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+bool linear_supported(int N, int K) { return available() && N >= 1 && K >= 32 && K % 32 == 0; }
+
+std::unique_ptr<LinearWeightsTC> prepare_linear(const float* Wt, const float* bias, int N, int K) {
+  auto l = std::make_unique<LinearWeightsTC>();
+  l->N = N; l->K = K; l->Npad = (int)round_up(N, 128);
+  std::vector<__nv_bfloat16> h((size_t)l->Npad * K, __float2bfloat16_rn(0.f)), lo((size_t)l->Npad * K, __float2bfloat16_rn(0.f));
+  for (size_t i = 0; i < (size_t)N * K; ++i) {
+    h[i] = __float2bfloat16_rn(Wt[i]);
+    lo[i] = __float2bfloat16_rn(Wt[i] - __bfloat162float(h[i]));
+  }
+  std::vector<float> b((size_t)l->Npad, 0.f);
+  if (bias) std::copy(bias, bias + N, b.begin());
+  l->w_hi.reserve(h.size() * 2);
+  l->w_lo.reserve(lo.size() * 2);
+  l->bias.reserve(b.size() * 4);
+  OCRS_CUDA_CHECK(cudaMemcpy(l->w_hi.ptr, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  OCRS_CUDA_CHECK(cudaMemcpy(l->w_lo.ptr, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+  OCRS_CUDA_CHECK(cudaMemcpy(l->bias.ptr, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  return l;
+}
+
+void linear_forward(const float* X, int64_t rows, const LinearWeightsTC& w, float* Y, const ScratchAlloc& alloc,
+                    cudaStream_t st) {
+  if (rows == 0) return;
+  gemm_split_bf16(X, rows, w.K, w.w_hi.ptr, w.w_lo.ptr, w.bias.as<float>(), w.Npad, Y, alloc, st);
+}
+
 void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* Y, float* Yh, int T, int N,
                  const int* reverse, const ScratchAlloc& alloc, cudaStream_t st) {
   if (T == 0 || N == 0) return;
@@ -785,12 +840,12 @@ void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* 
   {
     uint64_t ad[2] = {(uint64_t)I, (uint64_t)M};
     uint64_t as[1] = {(uint64_t)I * 2};
-    uint32_t box[2] = {64, 128};
-    CUtensorMap ta_hi = make_map(x_hi, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    CUtensorMap ta_lo = make_map(x_lo, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint32_t box[2] = {(uint32_t)kGemmBK, 128};
+    CUtensorMap ta_hi = make_map(x_hi, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    CUtensorMap ta_lo = make_map(x_lo, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
     uint64_t bd[2] = {(uint64_t)I, (uint64_t)Ntot};
-    CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
     OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     dim3 grid((unsigned)ceil_div(M, 128), (unsigned)(Ntot / 128));
     gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)M, Ntot, I);
@@ -830,12 +885,12 @@ void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, cons
   {
     uint64_t ad[2] = {(uint64_t)I, (uint64_t)rows};
     uint64_t as[1] = {(uint64_t)I * 2};
-    uint32_t box[2] = {64, 128};
-    CUtensorMap ta_hi = make_map(x_hi, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    CUtensorMap ta_lo = make_map(x_lo, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint32_t box[2] = {(uint32_t)kGemmBK, 128};
+    CUtensorMap ta_hi = make_map(x_hi, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    CUtensorMap ta_lo = make_map(x_lo, 2, ad, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
     uint64_t bd[2] = {(uint64_t)I, (uint64_t)Ntot};
-    CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
     OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     dim3 grid((unsigned)ceil_div(rows, 128), (unsigned)(Ntot / 128));
     gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)rows, Ntot, I);

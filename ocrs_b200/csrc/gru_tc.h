@@ -38,6 +38,20 @@ using ScratchAlloc = std::function<void*(size_t bytes)>;
 void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* Y, float* Yh, int T, int N,
                  const int* reverse, const ScratchAlloc& alloc, cudaStream_t st);
 
+// Linear layer on the same split-bf16 tensor-core GEMM (the CRNN's final 512 -> classes projection over the
+// packed rows of all lines): Y[rows, Npad] = X[rows, K] * W^T + b, Npad = N rounded up to 128 (extra columns
+// are zero weights, to be ignored by the consumer).
+struct LinearWeightsTC {
+  int N = 0, Npad = 0, K = 0;
+  DeviceBuffer w_hi, w_lo;  // bf16 [Npad][K]
+  DeviceBuffer bias;        // f32 [Npad]
+};
+bool linear_supported(int N, int K);
+// Wt: [N][K] row-major (i.e. the ONNX MatMul weight [K][N] transposed); bias may be null.
+std::unique_ptr<LinearWeightsTC> prepare_linear(const float* Wt, const float* bias, int N, int K);
+void linear_forward(const float* X, int64_t rows, const LinearWeightsTC& w, float* Y, const ScratchAlloc& alloc,
+                    cudaStream_t st);
+
 // One sequence of a ragged batch: own length and own element strides into xw / Y.
 struct SeqLine {
   int32_t T;                    // timesteps

@@ -109,6 +109,56 @@ __global__ void resize_threshold_kernel(const float* __restrict__ net, int inW, 
   mask[o] = v > thr ? 1 : 0;
 }
 
+// ---- batched over pages: one launch for the whole detection batch (page = blockIdx.z) ----
+__global__ void resize_padded_batch_kernel(const PageResizeIn* __restrict__ tab, float pad_value, float* __restrict__ dst,
+                                           int OH, int OW, int64_t dst_stride) {
+  const PageResizeIn pg = tab[blockIdx.z];
+  int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  int oy = blockIdx.y;
+  if (ox >= OW) return;
+  const float* s = pg.src;
+  const int H = pg.H, W = pg.W;
+  AxisTap ty = axis_tap(oy, pg.padH, OH);
+  AxisTap tx = axis_tap(ox, pg.padW, OW);
+  auto at = [&](int y, int x) -> float { return (y < H && x < W) ? __ldg(s + (int64_t)y * W + x) : pad_value; };
+  float v = lerp2(at(ty.i0, tx.i0), at(ty.i0, tx.i1), at(ty.i1, tx.i0), at(ty.i1, tx.i1), tx.w, ty.w);
+  dst[(int64_t)blockIdx.z * dst_stride + (int64_t)oy * OW + ox] = v;
+}
+
+__global__ void resize_threshold_batch_kernel(const PageResizeOut* __restrict__ tab, int inW, float thr) {
+  const PageResizeOut pg = tab[blockIdx.z];
+  int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  int oy = blockIdx.y;
+  if (ox >= pg.W || oy >= pg.H) return;
+  AxisTap ty = axis_tap(oy, pg.sliceH, pg.H);
+  AxisTap tx = axis_tap(ox, pg.sliceW, pg.W);
+  const float* r0 = pg.net + (int64_t)ty.i0 * inW;
+  const float* r1 = pg.net + (int64_t)ty.i1 * inW;
+  float v = lerp2(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), tx.w, ty.w);
+  int64_t o = (int64_t)oy * pg.W + ox;
+  if (pg.prob) pg.prob[o] = v;
+  pg.mask[o] = v > thr ? 1 : 0;
+}
+
+// u8 HWC RGB pages of one shape, 4 pixels (12 bytes) per thread, page = blockIdx.y
+__global__ void prepare_image_rgb8_x4_batch_kernel(const PagePrepare* __restrict__ tab, int64_t quads, PrepWeights pw) {
+  const PagePrepare pg = tab[blockIdx.y];
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= quads) return;
+  const uint32_t* px = reinterpret_cast<const uint32_t*>(pg.src);
+  uint32_t a = __ldg(px + q * 3 + 0), b = __ldg(px + q * 3 + 1), c = __ldg(px + q * 3 + 2);
+  float r0 = (float)(a & 0xFF), g0 = (float)((a >> 8) & 0xFF), b0 = (float)((a >> 16) & 0xFF);
+  float r1 = (float)(a >> 24), g1 = (float)(b & 0xFF), b1 = (float)((b >> 8) & 0xFF);
+  float r2 = (float)((b >> 16) & 0xFF), g2 = (float)(b >> 24), b2 = (float)(c & 0xFF);
+  float r3 = (float)((c >> 8) & 0xFF), g3 = (float)((c >> 16) & 0xFF), b3 = (float)(c >> 24);
+  float4 o;
+  o.x = ((kBlackValue + r0 * pw.w[0]) + g0 * pw.w[1]) + b0 * pw.w[2];
+  o.y = ((kBlackValue + r1 * pw.w[0]) + g1 * pw.w[1]) + b1 * pw.w[2];
+  o.z = ((kBlackValue + r2 * pw.w[0]) + g2 * pw.w[1]) + b2 * pw.w[2];
+  o.w = ((kBlackValue + r3 * pw.w[0]) + g3 * pw.w[1]) + b3 * pw.w[2];
+  reinterpret_cast<float4*>(pg.dst)[q] = o;
+}
+
 __global__ void threshold_kernel(const float* __restrict__ p, uint8_t* __restrict__ m, int64_t n, float thr) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) m[i] = p[i] > thr ? 1 : 0;
@@ -505,23 +555,31 @@ __global__ void ctc_argmax_rows_kernel(const float* __restrict__ logits, int64_t
   if (lane == 0) labels[warp] = bi;
 }
 
+// one warp per line: a label is emitted where it differs from its predecessor and is not blank (equivalent to
+// the sequential `last` rule of decode_greedy); order-preserving compaction through ballots
 __global__ void ctc_collapse_lines_kernel(const int32_t* __restrict__ labels, const CtcLine* __restrict__ lines,
                                           int n_lines, int32_t* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= n_lines) return;
   const CtcLine L = lines[i];
-  int last = 0, n = 0;
-  for (int pos = 0; pos < L.T; ++pos) {
-    int v = labels[L.base + (int64_t)pos * L.stride];
-    if (v == last) continue;
-    last = v;
-    if (v > 0) {
-      out[L.lab_off + n] = v;
-      out[L.pos_off + n] = pos;
-      ++n;
+  int n = 0, carry = 0;  // carry = label at the last position of the previous chunk (0 before the line starts)
+  for (int p0 = 0; p0 < L.T; p0 += 32) {
+    const int pos = p0 + lane;
+    const int v = pos < L.T ? labels[L.base + (int64_t)pos * L.stride] : 0;
+    int prev = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) prev = carry;
+    const bool emit = pos < L.T && v != prev && v > 0;
+    const unsigned m = __ballot_sync(0xffffffffu, emit);
+    if (emit) {
+      const int k = n + __popc(m & ((1u << lane) - 1u));
+      out[L.lab_off + k] = v;
+      out[L.pos_off + k] = pos;
     }
+    n += __popc(m);
+    carry = __shfl_sync(0xffffffffu, v, 31);
   }
-  out[L.cnt_off] = n;
+  if (lane == 0) out[L.cnt_off] = n;
 }
 
 }  // namespace
@@ -578,6 +636,42 @@ void resize_threshold(const float* net_out, int inH, int inW, int sliceH, int sl
   if (H == 0 || W == 0) return;
   dim3 grid(grid1d(W, 128), H);
   resize_threshold_kernel<<<grid, 128, 0, st>>>(net_out, inW, sliceH, sliceW, prob, mask, H, W, thr);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void resize_padded_batch(const PageResizeIn* d_tab, int n, float pad_value, float* dst, int OH, int OW, int64_t dst_stride,
+                         cudaStream_t st) {
+  if (OH == 0 || OW == 0 || n == 0) return;
+  dim3 grid(grid1d(OW, 128), OH, n);
+  resize_padded_batch_kernel<<<grid, 128, 0, st>>>(d_tab, pad_value, dst, OH, OW, dst_stride);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+void resize_threshold_batch(const PageResizeOut* d_tab, int n, int inW, int maxH, int maxW, float thr, cudaStream_t st) {
+  if (maxH == 0 || maxW == 0 || n == 0) return;
+  dim3 grid(grid1d(maxW, 128), maxH, n);
+  resize_threshold_batch_kernel<<<grid, 128, 0, st>>>(d_tab, inW, thr);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
+bool prepare_image_batchable(const void* pixels, int dtype, int order, int H, int W, int C, const float* out) {
+  const int64_t hw = (int64_t)H * W;
+  return dtype == 0 && order == 0 && C == 3 && hw > 0 && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(pixels) % 4 == 0) &&
+         (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+}
+
+void prepare_image_rgb8_batch(const PagePrepare* d_tab, int n, int H, int W, cudaStream_t st) {
+  const int64_t hw = (int64_t)H * W;
+  if (hw == 0 || n == 0) return;
+  const float itu[3] = {0.299f, 0.587f, 0.114f};  // preprocess.rs:171
+  PrepWeights pw;
+  pw.n = 3;
+  for (int c = 0; c < 3; ++c) pw.w[c] = itu[c] / 255.0f;  // preprocess.rs:184
+  dim3 grid(grid1d(hw / 4), (unsigned)n);
+  prepare_image_rgb8_x4_batch_kernel<<<grid, kThreads, 0, st>>>(d_tab, hw / 4, pw);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -647,7 +741,7 @@ void ctc_greedy_packed(const float* logits, int64_t rows, int C, const uint8_t* 
     ctc_argmax_rows_kernel<<<grid1d(rows * 32), kThreads, 0, st>>>(logits, rows, C, excluded, row_labels);
     count_launch();
   }
-  ctc_collapse_lines_kernel<<<grid1d(n_lines, 32), 32, 0, st>>>(row_labels, lines, n_lines, out);
+  ctc_collapse_lines_kernel<<<grid1d((int64_t)n_lines * 32, 128), 128, 0, st>>>(row_labels, lines, n_lines, out);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }

@@ -34,6 +34,28 @@ void resize_threshold(const float* net_out, int inH, int inW, int sliceH, int sl
 
 void threshold(const float* prob, uint8_t* mask, int64_t n, float thr, cudaStream_t st);
 
+// ---- the same pixel stages for a whole batch of pages in ONE launch each (device tables, page = grid z / y) ----
+struct PageResizeIn {   // input of the detection resize: grey page [H, W], virtually padded to [padH, padW]
+  const float* src;
+  int32_t H, W, padH, padW;
+};
+struct PageResizeOut {  // output of the detection epilogue: slice of the net output -> [H, W] mask (+ prob map)
+  const float* net;     // this page's [inH, inW] network output
+  float* prob;          // may be null
+  uint8_t* mask;
+  int32_t sliceH, sliceW, H, W;
+};
+struct PagePrepare {    // u8 HWC RGB page -> grey f32
+  const void* src;
+  float* dst;
+};
+void resize_padded_batch(const PageResizeIn* d_tab, int n, float pad_value, float* dst, int OH, int OW, int64_t dst_stride,
+                         cudaStream_t st);
+void resize_threshold_batch(const PageResizeOut* d_tab, int n, int inW, int maxH, int maxW, float thr, cudaStream_t st);
+// true when a page can take the batched fast path of prepare_image (u8, HWC, RGB, aligned, H*W % 4 == 0)
+bool prepare_image_batchable(const void* pixels, int dtype, int order, int H, int W, int C, const float* out);
+void prepare_image_rgb8_batch(const PagePrepare* d_tab, int n, int H, int W, cudaStream_t st);
+
 // ---- connected components -> word rects -------------------------------------------------------
 struct ComponentBuffers {
   int32_t* labels;       // [H*W + 1] union-find parents / final labels (+1 virtual frame node)

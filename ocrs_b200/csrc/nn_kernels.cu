@@ -191,58 +191,217 @@ __global__ void conv_transpose_kernel(const float* __restrict__ x, const float* 
 // Fused depthwise 3x3 + pointwise 1x1 (+ReLU).  One thread per output pixel, KOUT accumulators in
 // registers, all weights in shared memory.  Removes the depthwise intermediate (write + read).
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Separable-convolution family of the detection U-Net (detection.rs:131-184 runs it through rten):
+//   phase 1  per (pixel, channel): depthwise 3x3 (pad 1, stride 1 | 2) over a VIRTUAL input -- the channel
+//            concatenation of up to two tensors, each optionally end-padded with a constant (the decoder's
+//            Pad + Concat never materialise) -- or, for ConvTranspose, the input value itself; result in
+//            shared memory as [C][P];
+//   phase 2  pointwise: [P x C] x [C x KO] from shared memory, KC = 32 output channels at a time, PPT pixels x
+//            KPT outputs per thread; epilogue bias (+ ReLU) and either a plain NCHW store or the 2x2
+//            pixel shuffle of ConvTranspose(k = 2, s = 2) (KO = 4 K, column kk = k*4 + a*2 + b).
+// Two shapes: P = 128 pixels per block for the wide, shallow levels; P = 32 for the deep levels (few pixels,
+// C up to 256) so that they still fill SMs.
+// ---------------------------------------------------------------------------------------------
+struct SepSrc {
+  const float* x;  // [N, C, H, W]
+  int C, H, W;     // valid extent; reads at y >= H or x >= W (inside the virtual grid) return `pad`
+  float pad;
+};
+struct SepParams {
+  SepSrc src[2];
+  int n_src;
+  int N, C, Hv, Wv;        // virtual input: C = sum of source channels, Hv x Wv
+  int OH, OW, stride;      // grid of phase-1 pixels (depthwise output; for ConvTranspose = input grid)
+  int KO;                  // pointwise outputs (ConvTranspose: 4 * K)
+  int relu, mode;          // mode 0: depthwise + pointwise, NCHW store; 1: ConvTranspose 2x2 s2 (no depthwise)
+  int w_ck;                // pointwise weights already laid out [C][KO] (ConvTranspose); else [KO][C]
+  const float *dw_w, *dw_b, *pw_w, *pw_b;
+  float* y;
+};
+
+constexpr int kSepKC = 32;
+
+// Shallow levels (few channels, many pixels): one thread per output pixel, KOUT accumulators in registers,
+// all weights in shared memory; the depthwise value of each channel is consumed as soon as it is formed.
 template <int KOUT>
-__global__ void __launch_bounds__(128)
-dwpw_kernel(const float* __restrict__ x, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-            const float* __restrict__ pw_w, const float* __restrict__ pw_b, float* __restrict__ y, int N, int C, int H,
-            int W, int OH, int OW, int stride, int relu) {
+__global__ void __launch_bounds__(128) dwpw_pixel_kernel(SepParams p) {
   extern __shared__ float sm[];
-  float* s_dw = sm;                 // [C][9]
-  float* s_db = s_dw + C * 9;       // [C]
-  float* s_pw = s_db + C;           // [C][KOUT]  (transposed for broadcast reads)
-  float* s_pb = s_pw + C * KOUT;    // [KOUT]
-  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) s_dw[i] = dw_w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = dw_b ? dw_b[i] : 0.f;
-  for (int i = threadIdx.x; i < C * KOUT; i += blockDim.x) {
+  float* s_dw = sm;                   // [C][9]
+  float* s_db = s_dw + p.C * 9;       // [C]
+  float* s_pw = s_db + p.C;           // [C][KOUT]  (transposed for broadcast reads)
+  float* s_pb = s_pw + p.C * KOUT;    // [KOUT]
+  for (int i = threadIdx.x; i < p.C * 9; i += blockDim.x) s_dw[i] = p.dw_w[i];
+  for (int i = threadIdx.x; i < p.C; i += blockDim.x) s_db[i] = p.dw_b ? p.dw_b[i] : 0.f;
+  for (int i = threadIdx.x; i < p.C * KOUT; i += blockDim.x) {
     int c = i / KOUT, k = i - c * KOUT;
-    s_pw[i] = pw_w[k * C + c];
+    s_pw[i] = p.pw_w[k * p.C + c];
   }
-  for (int i = threadIdx.x; i < KOUT; i += blockDim.x) s_pb[i] = pw_b ? pw_b[i] : 0.f;
+  for (int i = threadIdx.x; i < KOUT; i += blockDim.x) s_pb[i] = p.pw_b ? p.pw_b[i] : 0.f;
   __syncthreads();
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  const int oy = blockIdx.y;
-  const int n = blockIdx.z;
-  if (ox >= OW) return;
+  const int ohw = p.OH * p.OW;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (idx >= ohw) return;
+  const int oy = idx / p.OW, ox = idx - oy * p.OW;
   float acc[KOUT];
 #pragma unroll
   for (int k = 0; k < KOUT; ++k) acc[k] = s_pb[k];
-  const int iy0 = oy * stride - 1, ix0 = ox * stride - 1;
-  const float* xn = x + (int64_t)n * C * H * W;
-  for (int c = 0; c < C; ++c) {
-    const float* xc = xn + (int64_t)c * H * W;
-    const float* wd = s_dw + c * 9;
-    float v = s_db[c];
+  const int iy0 = oy * p.stride - 1, ix0 = ox * p.stride - 1;
+  int c = 0;
+#pragma unroll 1
+  for (int si = 0; si < p.n_src; ++si) {
+    const SepSrc s = p.src[si];
+    const float* xs = s.x + (int64_t)n * s.C * s.H * s.W;
+    // tap validity is the same for every channel of the source
+    bool inside[9], real[9];
+    int off[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int iy = iy0 + r;
-      if (iy < 0 || iy >= H) continue;
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const int ix = ix0 + q;
-        if (ix < 0 || ix >= W) continue;
-        v = fmaf(__ldg(xc + (int64_t)iy * W + ix), wd[r * 3 + q], v);
+        const int iy = iy0 + r, ix = ix0 + q;
+        inside[r * 3 + q] = iy >= 0 && iy < p.Hv && ix >= 0 && ix < p.Wv;
+        real[r * 3 + q] = inside[r * 3 + q] && iy < s.H && ix < s.W;
+        off[r * 3 + q] = iy * s.W + ix;
       }
-    }
-    const float* wp = s_pw + c * KOUT;
+    for (int cs = 0; cs < s.C; ++cs, ++c) {
+      const float* xc = xs + (int64_t)cs * s.H * s.W;
+      const float* wd = s_dw + c * 9;
+      float v = s_db[c];
 #pragma unroll
-    for (int k = 0; k < KOUT; ++k) acc[k] = fmaf(v, wp[k], acc[k]);
+      for (int t = 0; t < 9; ++t) {
+        const float xv = real[t] ? __ldg(xc + off[t]) : (inside[t] ? s.pad : 0.f);
+        v = fmaf(xv, wd[t], v);
+      }
+      const float* wp = s_pw + c * KOUT;
+#pragma unroll
+      for (int k = 0; k < KOUT; ++k) acc[k] = fmaf(v, wp[k], acc[k]);
+    }
   }
-  float* yn = y + (int64_t)n * KOUT * OH * OW + (int64_t)oy * OW + ox;
+  float* yn = p.y + (int64_t)n * KOUT * ohw + idx;
 #pragma unroll
   for (int k = 0; k < KOUT; ++k) {
     float v = acc[k];
-    if (relu) v = fmaxf(v, 0.f);
-    yn[(int64_t)k * OH * OW] = v;
+    if (p.relu) v = fmaxf(v, 0.f);
+    yn[(int64_t)k * ohw] = v;
+  }
+}
+
+template <int P, int PPT, int KPT>
+__global__ void __launch_bounds__(256) sepconv_kernel(SepParams p) {
+  extern __shared__ float sm[];
+  float* s_dwv = sm;                          // [C][P]
+  float* s_pw = s_dwv + (size_t)p.C * P;      // [C][kSepKC]
+  float* s_dw = s_pw + (size_t)p.C * kSepKC;  // [C][9] + [C] (mode 0)
+  const int tid = threadIdx.x;
+  const int ohw = p.OH * p.OW;
+  const int npix = p.N * ohw;
+  const int pix0 = blockIdx.x * P;
+  const int k0 = blockIdx.y * kSepKC;         // this block's chunk of pointwise outputs
+  if (p.mode == 0) {
+    for (int i = tid; i < p.C * 9; i += 256) s_dw[i] = p.dw_w[i];
+    for (int i = tid; i < p.C; i += 256) s_dw[p.C * 9 + i] = p.dw_b ? p.dw_b[i] : 0.f;
+  }
+  for (int i = tid; i < p.C * kSepKC; i += 256) {
+    const int c = i / kSepKC, kk = i - c * kSepKC;
+    float w = 0.f;
+    if (k0 + kk < p.KO) w = p.w_ck ? p.pw_w[(int64_t)c * p.KO + k0 + kk] : p.pw_w[(int64_t)(k0 + kk) * p.C + c];
+    s_pw[i] = w;
+  }
+  __syncthreads();
+  // ---- phase 1: every (channel, pixel) of the block; pixel decode once per thread (P divides 256 or vice versa) ----
+  {
+    constexpr int CSTEP = 256 / P;            // channels advanced per iteration (P = 32: 8; P = 128: 2)
+    const int pp = tid % P, c_first = tid / P;
+    const int pix = pix0 + pp;
+    const bool live = pix < npix;
+    int n = 0, oy = 0, ox = 0;
+    if (live) {
+      n = pix / ohw;
+      const int rem = pix - n * ohw;
+      oy = rem / p.OW;
+      ox = rem - oy * p.OW;
+    }
+    const int iy0 = oy * p.stride - 1, ix0 = ox * p.stride - 1;
+    for (int c = c_first; c < p.C; c += CSTEP) {
+      float v = 0.f;
+      if (live) {
+        const bool second = p.n_src > 1 && c >= p.src[0].C;
+        const SepSrc& s = second ? p.src[1] : p.src[0];
+        const int cs = second ? c - p.src[0].C : c;
+        const float* xc = s.x + ((int64_t)n * s.C + cs) * s.H * s.W;
+        if (p.mode == 0) {
+          const float* wd = s_dw + c * 9;
+          v = s_dw[p.C * 9 + c];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const int iy = iy0 + r;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const int ix = ix0 + q;
+              float xv = 0.f;  // conv zero padding outside the virtual grid
+              if (iy >= 0 && iy < p.Hv && ix >= 0 && ix < p.Wv) xv = (iy < s.H && ix < s.W) ? __ldg(xc + iy * s.W + ix) : s.pad;
+              v = fmaf(xv, wd[r * 3 + q], v);
+            }
+          }
+        } else {
+          v = __ldg(xc + oy * s.W + ox);
+        }
+      }
+      s_dwv[c * P + pp] = v;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2 ----
+  constexpr int PL = P / PPT;            // pixel lanes
+  constexpr int KG = kSepKC / KPT;       // output groups
+  static_assert(PL * KG == 256, "thread mapping");
+  const int pl = tid % PL, kq = tid / PL;
+  float acc[PPT][KPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j)
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) acc[j][k] = 0.f;
+  const float* wrow = s_pw + kq * KPT;
+#pragma unroll 4
+  for (int c = 0; c < p.C; ++c) {
+    float a[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) a[j] = s_dwv[c * P + pl + j * PL];
+    float w[KPT];
+#pragma unroll
+    for (int k = 0; k < KPT; k += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(wrow + c * kSepKC + k);
+      w[k] = t.x; w[k + 1] = t.y; w[k + 2] = t.z; w[k + 3] = t.w;
+    }
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+#pragma unroll
+      for (int k = 0; k < KPT; ++k) acc[j][k] = fmaf(a[j], w[k], acc[j][k]);
+  }
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int pix = pix0 + pl + j * PL;
+    if (pix >= npix) continue;
+    const int n = pix / ohw;
+    const int rem = pix - n * ohw;
+    const int oy = rem / p.OW, ox = rem - oy * p.OW;
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int kk = k0 + kq * KPT + k;
+      if (kk >= p.KO) continue;
+      if (p.mode == 0) {
+        float v = acc[j][k] + (p.pw_b ? __ldg(p.pw_b + kk) : 0.f);
+        if (p.relu) v = fmaxf(v, 0.f);
+        p.y[((int64_t)n * p.KO + kk) * ohw + rem] = v;
+      } else {
+        const int ko = kk >> 2, t = kk & 3;
+        float v = acc[j][k] + (p.pw_b ? __ldg(p.pw_b + ko) : 0.f);
+        if (p.relu) v = fmaxf(v, 0.f);
+        p.y[(((int64_t)n * (p.KO >> 2) + ko) * (2 * p.OH) + 2 * oy + (t >> 1)) * (2 * p.OW) + 2 * ox + (t & 1)] = v;
+      }
+    }
   }
 }
 
@@ -498,11 +657,11 @@ __global__ void pad4d_kernel(const float* __restrict__ x, float* __restrict__ y,
 }
 
 // one warp per row
-__global__ void log_softmax_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int cols) {
+__global__ void log_softmax_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t rows, int cols) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   int lane = threadIdx.x % 32;
   if (row >= rows) return;
-  const float* xr = x + row * cols;
+  const float* xr = x + row * ldx;
   float m = -INFINITY;
   for (int c = lane; c < cols; c += 32) m = fmaxf(m, xr[c]);
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -608,35 +767,85 @@ void conv_transpose2d(const float* x, const float* w, const float* b, float* y, 
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
-bool dwpw_supported(int C, int K) { return (K == 8 || K == 16 || K == 32) && C >= 1 && C <= 64; }
+namespace {
+void launch_sep(const SepParams& p, cudaStream_t st) {
+  const int64_t npix = (int64_t)p.N * p.OH * p.OW;
+  if (npix == 0 || p.KO == 0) return;
+  OCRS_CHECK(npix < ((int64_t)1 << 30), kInternal, "separable conv: too many pixels for one launch");
+  // the choice depends on the PAGE size only, never on the batch size: a page's result is the same
+  // bits whether it runs alone or in a batch of eight
+  if (p.mode == 0 && p.C <= 64 && (p.KO == 8 || p.KO == 16 || p.KO == 32) && (int64_t)p.OH * p.OW >= 4096) {
+    // shallow levels: thread per pixel
+    dim3 grid((unsigned)ceil_div((int64_t)p.OH * p.OW, 128), (unsigned)p.N);
+    const size_t smem = (size_t)(p.C * 9 + p.C + p.C * p.KO + p.KO) * sizeof(float);
+    if (p.KO == 8) dwpw_pixel_kernel<8><<<grid, 128, smem, st>>>(p);
+    else if (p.KO == 16) dwpw_pixel_kernel<16><<<grid, 128, smem, st>>>(p);
+    else dwpw_pixel_kernel<32><<<grid, 128, smem, st>>>(p);
+    count_launch();
+    OCRS_CHECK(cudaGetLastError() == cudaSuccess, kCuda, "dwpw_pixel_kernel launch failed");
+    return;
+  }
+  // deep levels: [C][32 pixels] tile in shared memory, one 32-wide chunk of outputs per block (grid.y)
+  const size_t smem = ((size_t)p.C * 32 + (size_t)p.C * kSepKC + (size_t)p.C * 10) * sizeof(float);
+  OCRS_CHECK(smem <= 200 * 1024, kInternal, "separable conv: channel count too large for shared memory");
+  if (smem > 48 * 1024)
+    OCRS_CUDA_CHECK(cudaFuncSetAttribute(sepconv_kernel<32, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  dim3 grid((unsigned)ceil_div(npix, 32), (unsigned)ceil_div(p.KO, kSepKC));
+  sepconv_kernel<32, 1, 4><<<grid, 256, smem, st>>>(p);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+bool dwpw_supported(int C, int K) { return C >= 1 && C <= 1024 && K >= 1 && K <= 4096 && (size_t)C * (32 + kSepKC + 10) * 4 <= 200 * 1024; }
+
+void dwpw_conv2(const SepInput* srcs, int n_src, const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_b,
+                float* y, int N, int Hv, int Wv, int K, int stride, int relu, cudaStream_t st) {
+  SepParams p{};
+  p.n_src = n_src;
+  p.C = 0;
+  for (int i = 0; i < n_src; ++i) {
+    p.src[i] = SepSrc{srcs[i].x, srcs[i].C, srcs[i].H, srcs[i].W, srcs[i].pad};
+    p.C += srcs[i].C;
+  }
+  p.N = N; p.Hv = Hv; p.Wv = Wv; p.stride = stride;
+  p.OH = (Hv + 2 - 3) / stride + 1;
+  p.OW = (Wv + 2 - 3) / stride + 1;
+  if (N == 0 || p.OH <= 0 || p.OW <= 0) return;
+  p.KO = K; p.relu = relu; p.mode = 0; p.w_ck = 0;
+  p.dw_w = dw_w; p.dw_b = dw_b; p.pw_w = pw_w; p.pw_b = pw_b; p.y = y;
+  launch_sep(p, st);
+}
 
 void dwpw_conv(const float* x, const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_b, float* y,
                int N, int C, int H, int W, int K, int stride, int relu, cudaStream_t st) {
-  const int OH = (H + 2 - 3) / stride + 1, OW = (W + 2 - 3) / stride + 1;
-  if (N == 0 || OH <= 0 || OW <= 0) return;
-  dim3 grid((unsigned)ceil_div(OW, 128), (unsigned)OH, (unsigned)N);
-  size_t smem = (size_t)(C * 9 + C + C * K + K) * sizeof(float);
-  if (K == 8) dwpw_kernel<8><<<grid, 128, smem, st>>>(x, dw_w, dw_b, pw_w, pw_b, y, N, C, H, W, OH, OW, stride, relu);
-  else if (K == 16) dwpw_kernel<16><<<grid, 128, smem, st>>>(x, dw_w, dw_b, pw_w, pw_b, y, N, C, H, W, OH, OW, stride, relu);
-  else dwpw_kernel<32><<<grid, 128, smem, st>>>(x, dw_w, dw_b, pw_w, pw_b, y, N, C, H, W, OH, OW, stride, relu);
-  count_launch();
-  OCRS_CUDA_CHECK(cudaGetLastError());
+  SepInput s{x, C, H, W, 0.f};
+  dwpw_conv2(&s, 1, dw_w, dw_b, pw_w, pw_b, y, N, H, W, K, stride, relu, st);
 }
 
 void conv_transpose_2x2s2(const float* x, const float* w, const float* b, float* y, int N, int C, int H, int W, int K,
                           int relu, cudaStream_t st) {
-  int64_t total = (int64_t)N * H * W;
-  if (!total || !K) return;
-  static bool attr = false;
-  size_t smem = (size_t)C * CT_KB * 4 * sizeof(float);
-  if (!attr && smem > 48 * 1024) {
-    OCRS_CUDA_CHECK(cudaFuncSetAttribute(convt2x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+  if ((int64_t)N * H * W == 0 || !K) return;
+  if (!dwpw_supported(C, 4 * K)) {  // very wide layers: the simple kernel
+    static bool attr = false;
+    size_t smem = (size_t)C * CT_KB * 4 * sizeof(float);
+    if (!attr && smem > 48 * 1024) {
+      OCRS_CUDA_CHECK(cudaFuncSetAttribute(convt2x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    dim3 grid((unsigned)ceil_div((int64_t)N * H * W, 128), (unsigned)ceil_div(K, CT_KB));
+    convt2x2_kernel<<<grid, 128, smem, st>>>(x, w, b, y, N, C, H, W, K, relu);
+    count_launch();
+    OCRS_CUDA_CHECK(cudaGetLastError());
+    return;
   }
-  dim3 grid((unsigned)ceil_div(total, 128), (unsigned)ceil_div(K, CT_KB));
-  convt2x2_kernel<<<grid, 128, smem, st>>>(x, w, b, y, N, C, H, W, K, relu);
-  count_launch();
-  OCRS_CUDA_CHECK(cudaGetLastError());
+  SepParams p{};
+  p.n_src = 1;
+  p.src[0] = SepSrc{x, C, H, W, 0.f};
+  p.C = C; p.N = N; p.Hv = H; p.Wv = W; p.OH = H; p.OW = W; p.stride = 1;
+  p.KO = 4 * K; p.relu = relu; p.mode = 1; p.w_ck = 1;
+  p.pw_w = w; p.pw_b = b; p.y = y;
+  launch_sep(p, st);
 }
 
 void conv_transpose_2x2s2_head(const float* x, const float* w, const float* b, const float* w2, const float* b2,
@@ -750,8 +959,12 @@ void pad4d(const float* x, float* y, const int64_t in_shape[4], const int64_t be
 }
 
 void log_softmax_lastdim(const float* x, float* y, int64_t rows, int cols, cudaStream_t st) {
+  log_softmax_rows(x, cols, y, rows, cols, st);
+}
+
+void log_softmax_rows(const float* x, int64_t ldx, float* y, int64_t rows, int cols, cudaStream_t st) {
   if (!rows) return;
-  log_softmax_kernel<<<grid1d(rows * 32), kThreads, 0, st>>>(x, y, rows, cols);
+  log_softmax_kernel<<<grid1d(rows * 32), kThreads, 0, st>>>(x, ldx, y, rows, cols);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }

@@ -32,8 +32,17 @@ struct ConvTParams {
 void conv_transpose2d(const float* x, const float* w, const float* b, float* y, const ConvTParams& p, cudaStream_t st);
 
 // Fused depthwise 3x3 (pad 1, stride s) + pointwise 1x1 (+ ReLU): y = relu?(pw(dw(x))).
-// x [N,C,H,W]; dw_w [C][9], dw_b [C]; pw_w [K][C], pw_b [K]; y [N,K,OH,OW].  K in {8,16,32}, C <= 64.
+// x [N,C,H,W]; dw_w [C][9], dw_b [C]; pw_w [K][C], pw_b [K]; y [N,K,OH,OW].
 bool dwpw_supported(int C, int K);
+// Same with a VIRTUAL input: the channel concatenation of up to two tensors, each optionally end-padded
+// (bottom / right) with a constant up to Hv x Wv -- the U-Net decoder's Pad + Concat are never written.
+struct SepInput {
+  const float* x;  // [N, C, H, W]
+  int C, H, W;
+  float pad;       // value of the end padding (H..Hv, W..Wv)
+};
+void dwpw_conv2(const SepInput* srcs, int n_src, const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_b,
+                float* y, int N, int Hv, int Wv, int K, int stride, int relu, cudaStream_t st);
 void dwpw_conv(const float* x, const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_b, float* y,
                int N, int C, int H, int W, int K, int stride, int relu, cudaStream_t st);
 
@@ -78,6 +87,8 @@ void fill(float* y, float v, int64_t n, cudaStream_t st);
 
 // log-softmax over the last axis
 void log_softmax_lastdim(const float* x, float* y, int64_t rows, int cols, cudaStream_t st);
+// same with a row stride `ldx` (elements) on the input; y stays dense [rows, cols]
+void log_softmax_rows(const float* x, int64_t ldx, float* y, int64_t rows, int cols, cudaStream_t st);
 
 // One GRU time step for both directions (ONNX gate order z, r, h).
 //   xw   : [D][T][N][3H] input projections incl. Wb

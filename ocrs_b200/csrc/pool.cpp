@@ -203,13 +203,12 @@ void Pool::run_worker(Worker* w) {
       }
     }
     try {
-      std::vector<std::unique_ptr<OcrInput>> inputs;
+      std::vector<Engine::PageSpec> specs;
+      specs.reserve(job->pages.size());
+      for (const PoolPage& pg : job->pages) specs.push_back(Engine::PageSpec{pg.pixels, pg.dtype, pg.order, pg.H, pg.W, pg.C, pg.on_device});
+      std::vector<std::unique_ptr<OcrInput>> inputs = w->engine->prepare_inputs(specs);
       std::vector<const OcrInput*> ptrs;
-      inputs.reserve(job->pages.size());
-      for (const PoolPage& pg : job->pages) {
-        inputs.push_back(w->engine->prepare_input(pg.pixels, pg.dtype, pg.order, pg.H, pg.W, pg.C, pg.on_device));
-        ptrs.push_back(inputs.back().get());
-      }
+      for (const auto& in : inputs) ptrs.push_back(in.get());
       job->result = w->engine->ocr_pages(ptrs);
       inputs.clear();
     } catch (...) {

@@ -451,6 +451,52 @@ class OcrEngine:
         lib.ocrs_b200_free(out)
         return res
 
+    # -- ocrs-cli debug outputs, batched (main.rs:423-443)
+    def detect_text_pixels_batch(self, inputs: Sequence[OcrInput], maps: bool = True, masks: bool = True):
+        """`--text-map` / `--text-mask` for a batch of pages in one detection pass: returns (maps, masks), lists of
+        f32 [H, W] probability maps and u8 [H, W] masks (x > detection_threshold); a list is None when not requested."""
+        n = len(inputs)
+        hs = (C.c_void_p * max(n, 1))(*[i._h for i in inputs])
+        mp = (C.c_void_p * max(n, 1))() if maps else None
+        mk = (C.c_void_p * max(n, 1))() if masks else None
+        check(lib.ocrs_b200_engine_detect_text_pixels_batch(self._h, hs, n, mp, mk))
+        out_maps, out_masks = ([] if maps else None), ([] if masks else None)
+        for i, inp in enumerate(inputs):
+            _, h, w = inp.shape
+            if maps:
+                out_maps.append(np.ctypeslib.as_array(C.cast(mp[i], C.POINTER(C.c_float)), shape=(h * w,)).copy().reshape(h, w))
+                lib.ocrs_b200_free(mp[i])
+            if masks:
+                out_masks.append(np.ctypeslib.as_array(C.cast(mk[i], C.POINTER(C.c_uint8)), shape=(h * w,)).copy().reshape(h, w))
+                lib.ocrs_b200_free(mk[i])
+        return out_maps, out_masks
+
+    def prepare_recognition_inputs(self, inp: OcrInput, lines: Sequence[Sequence[RotatedRect]]) -> List[np.ndarray]:
+        """`--text-line-images`: the [height, w'] recognition input of every line of a page, one crop launch."""
+        flat = [w for line in lines for w in line]
+        arr = _rects_to_c(flat)
+        offs = (C.c_size_t * (len(lines) + 1))()
+        k = 0
+        for i, line in enumerate(lines):
+            offs[i] = k
+            k += len(line)
+        offs[len(lines)] = k
+        images = C.POINTER(C.c_float)()
+        height = C.c_int()
+        widths = C.POINTER(C.c_int)()
+        offsets = C.POINTER(C.c_size_t)()
+        check(lib.ocrs_b200_engine_prepare_recognition_inputs(self._h, inp._h, arr, offs, len(lines), C.byref(images),
+                                                              C.byref(height), C.byref(widths), C.byref(offsets)))
+        out = []
+        for i in range(len(lines)):
+            n = height.value * widths[i]
+            a = np.ctypeslib.as_array(C.cast(C.addressof(images.contents) + 4 * offsets[i], C.POINTER(C.c_float)), shape=(n,))
+            out.append(a.copy().reshape(height.value, widths[i]))
+        lib.ocrs_b200_free(images)
+        lib.ocrs_b200_free(widths)
+        lib.ocrs_b200_free(offsets)
+        return out
+
     # -- lib.rs:282
     def detection_threshold(self) -> float:
         return float(lib.ocrs_b200_engine_detection_threshold(self._h))
