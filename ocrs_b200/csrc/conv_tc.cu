@@ -87,6 +87,85 @@ struct TileEntry {
 };
 static_assert(sizeof(TileEntry) == 48, "TileEntry layout");
 
+// In-register transpose of 16-byte chunks inside groups of G lanes (G = 4): x holds G chunks of 4 words;
+// afterwards chunk q of lane r (r = lane % G) is what chunk r of lane (lane - r + q) was.
+template <int G>
+__device__ __forceinline__ void transpose_chunks(uint32_t (&x)[4 * G], int lane) {
+#pragma unroll
+  for (int m = 1; m < G; m <<= 1) {
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+      if (c & m) continue;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t a = x[4 * c + w], b = x[4 * (c | m) + w];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, up ? a : b, m);
+        if (up) x[4 * c + w] = recv;
+        else x[4 * (c | m) + w] = recv;
+      }
+    }
+  }
+}
+
+// Epilogue of one tile for a promotion warp (32 pixels x 32 channels per warp): bias, ReLU, max-pool by warp
+// shuffles, fp16 split; the four 16-byte chunks of a thread are then transposed inside groups of 4 lanes so that
+// lane r of a group holds chunk r of each of the group's 4 pixels -- a store instruction writes 64 contiguous
+// bytes per pixel instead of 32 scattered 16-byte pieces.  (Measured with the in-kernel timers: the scattered
+// stores cost ~2.5 cycles per lane, 7.7-10.6k cycles per tile, during which no accumulator is promoted and the
+// MMA thread runs out of buffers -- profiles/r02g_conv_promotion_timers.log.)
+template <int COUT>
+__device__ __forceinline__ void epilogue_store(const float (&acc)[32], const TileEntry& e, int wq, int hsel, int lane, int relu,
+                                               int ph, int pw, bool real_tile, const float* __restrict__ bias,
+                                               act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, int* __restrict__ ovf) {
+  constexpr int CH = 32, kRowsPerWarp = 32 / kTW;
+  const int th = wq * kRowsPerWarp + lane / kTW, tw = lane % kTW;
+  const int h = e.h0 + th, w = e.w0 + tw;
+  const int oh = h / ph, ow = w / pw;
+  const bool writer = real_tile && (ph == 1 || (lane & kTW) == 0) && (pw == 1 || (lane & 1) == 0) && oh < e.OH && ow < e.OW;
+  uint32_t hp[16], lp[16];
+#pragma unroll
+  for (int c0 = 0; c0 < CH; c0 += 8) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0 + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float v0 = acc[c0 + j] + bb[j];
+      float v1 = acc[c0 + j + 1] + bb[j + 1];
+      if (relu) {
+        v0 = fmaxf(v0, 0.f);
+        v1 = fmaxf(v1, 0.f);
+      }
+      if (ph == 2) {
+        v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, kTW));
+        v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, kTW));
+      }
+      if (pw == 2) {
+        v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
+        v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
+      }
+      const int k = (c0 + j) / 2;
+      if (writer) split2(v0, v1, hp[k], lp[k], ovf);
+      else hp[k] = lp[k] = 0u;
+    }
+  }
+  transpose_chunks<4>(hp, lane);
+  transpose_chunks<4>(lp, lane);
+  const uint32_t wmask = __ballot_sync(0xffffffffu, writer);
+  const int r = lane & 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int L = (lane & ~3) + q;  // the lane (pixel) whose chunk r this lane now holds
+    if ((wmask >> L) & 1u) {
+      const int hq = e.h0 + wq * kRowsPerWarp + L / kTW, wqx = e.w0 + L % kTW;
+      const size_t opix = (size_t)e.out_off + ((size_t)e.n * e.OH + hq / ph) * e.OW + wqx / pw;
+      *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + r * 8) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+      *reinterpret_cast<uint4*>(out_lo + opix * COUT + hsel * CH + r * 8) = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+    }
+  }
+}
+
 __device__ __forceinline__ void fence_tensormap_acquire(const void* p) {
   asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(p) : "memory");
 }
@@ -345,11 +424,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
     // ---------------- promotion + epilogue: warps 0 .. kEpiWarps-1 ----------------
     // warp & 3 = TMEM lane quadrant (a warp may only touch lanes 32*(warp % 4)..+31), warp >> 2 = which
     // 32 output channels; each thread keeps 32 partial sums.
-    constexpr int kRowsPerWarp = 32 / kTW;
     constexpr int CH = 32;
     const int wq = warp & 3, hsel = warp >> 2;
     const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + (uint32_t)(hsel * CH);
-    const int th = wq * kRowsPerWarp + lane / kTW, tw = lane % kTW;
     const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
     uint32_t gc = 0;
     const bool etime = dbg != nullptr && warp == 0 && lane == 0;
@@ -417,39 +494,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(x_empty(tp));
 
-      const int h = e.h0 + th, w = e.w0 + tw;
-      const int oh = h / ph, ow = w / pw;
-      const bool writer = (ph == 1 || (lane & kTW) == 0) && (pw == 1 || (lane & 1) == 0) && oh < e.OH && ow < e.OW;
-      const size_t opix = (size_t)e.out_off + ((size_t)e.n * e.OH + oh) * e.OW + ow;
-#pragma unroll
-      for (int c0 = 0; c0 < CH; c0 += 8) {
-        uint32_t hp[4], lp[4];
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0 + 4));
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          float v0 = acc[c0 + j] + bb[j];
-          float v1 = acc[c0 + j + 1] + bb[j + 1];
-          if (relu) {
-            v0 = fmaxf(v0, 0.f);
-            v1 = fmaxf(v1, 0.f);
-          }
-          if (ph == 2) {
-            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, kTW));
-            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, kTW));
-          }
-          if (pw == 2) {
-            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
-            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
-          }
-          if (writer) split2(v0, v1, hp[j / 2], lp[j / 2], ovf);
-        }
-        if (writer) {
-          *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(out_lo + opix * COUT + hsel * CH + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-        }
-      }
+      epilogue_store<COUT>(acc, e, wq, hsel, lane, relu, ph, pw, true, bias, out_hi, out_lo, ovf);
       if (etime) {
         e_xf += (unsigned long long)(q4 - q3);
         e_epi += (unsigned long long)(clock64() - q4);
@@ -769,14 +814,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_co
     }
   } else {
     // ---------------- promotion + epilogue (both CTAs, own tensor memory) ----------------
-    constexpr int kRowsPerWarp = 32 / kTW;
     constexpr int CH = 32;
     const int wq = warp & 3, hsel = warp >> 2;
     const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + (uint32_t)(hsel * CH);
-    const int th = wq * kRowsPerWarp + lane / kTW, tw = lane % kTW;
     const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
     uint32_t gc = 0;
-    int sink = 0;  // overflow flag target of a dummy tile (its values are meaningless)
     for (uint32_t ti = 0;; ++ti) {
       const uint32_t slot = ti & (kSched - 1);
       mbar_wait_cluster_trap(sched_full(slot), (ti / kSched) & 1);
@@ -815,39 +857,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(mapa(x_empty(tp), 0));
 
-      const int h = e.h0 + th, w = e.w0 + tw;
-      const int oh = h / ph, ow = w / pw;
-      const bool writer = real_tile && (ph == 1 || (lane & kTW) == 0) && (pw == 1 || (lane & 1) == 0) && oh < e.OH && ow < e.OW;
-      const size_t opix = (size_t)e.out_off + ((size_t)e.n * e.OH + oh) * e.OW + ow;
-#pragma unroll
-      for (int c0 = 0; c0 < CH; c0 += 8) {
-        uint32_t hp[4], lp[4];
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0 + 4));
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          float v0 = acc[c0 + j] + bb[j];
-          float v1 = acc[c0 + j + 1] + bb[j + 1];
-          if (relu) {
-            v0 = fmaxf(v0, 0.f);
-            v1 = fmaxf(v1, 0.f);
-          }
-          if (ph == 2) {
-            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, kTW));
-            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, kTW));
-          }
-          if (pw == 2) {
-            v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
-            v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
-          }
-          if (writer) split2(v0, v1, hp[j / 2], lp[j / 2], real_tile ? ovf : &sink);
-        }
-        if (writer) {
-          *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + c0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(out_lo + opix * COUT + hsel * CH + c0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-        }
-      }
+      epilogue_store<COUT>(acc, e, wq, hsel, lane, relu, ph, pw, real_tile, bias, out_hi, out_lo, ovf);
     }
   }
   __syncwarp();
@@ -1165,9 +1175,10 @@ void launch_conv(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_gr
     const double tl = (double)std::max<unsigned long long>(h[0], 1);
     fprintf(stderr,
             "[conv dbg] Cin %d Cout %d pool %dx%d: %llu tiles, %d groups, %.0f CTAs | per k-block (cycles): ring %.0f, x_empty %.0f, "
-            "hh_empty %.0f, operands %.0f, issue HH %.0f, issue X %.0f | loop total %.0f (per CTA %.0f cycles)\n",
+            "hh_empty %.0f, operands %.0f, issue HH %.0f, issue X %.0f | loop total %.0f (per CTA %.0f cycles) | promotion warp 0 of "
+            "every CTA, per TILE: ring %.0f, wait hh_full %.0f, promote %.0f, wait x_full %.0f, X + epilogue %.0f\n",
             Cin, COUT, ph, pw, h[0], n_groups, ctas, h[2] / kb, h[3] / kb, h[4] / kb, h[5] / kb, h[6] / kb, h[7] / kb, h[8] / kb,
-            h[8] / ctas);
+            h[8] / ctas, h[10] / tl, h[11] / tl, h[12] / tl, h[13] / tl, h[14] / tl);
   }
 }
 

@@ -7,10 +7,13 @@
 // a language model, log space) and is checked against oracle/recognition.py::ctc_decode_beam.
 //
 // Per line the block keeps `width` prefixes as nodes of a trie (parent, label, timestep) in
-// global memory plus (log p_blank, log p_non_blank) per prefix in shared memory.  Every
-// timestep:
+// global memory plus (log p_blank, log p_non_blank) per prefix in shared memory.  A prefix can be
+// created more than once (it drops out of the beam and is reached again later, with new timesteps), so
+// every node also carries the CANONICAL id of its prefix -- the id of the first node ever created for
+// (canonical parent, label), found through per-node child lists -- and prefix identity is decided on
+// canonical ids, exactly like a decoder that keys its beam on the label tuple.  Every timestep:
 //   1. each beam's "stay" entry is scored (blank path + repeat path + the extension of its
-//      parent prefix when the parent is also in the beam -- the only way two candidates can
+//      parent prefix when the parent prefix is also in the beam -- the only way two candidates can
 //      name the same prefix);
 //   2. every (beam, class) extension that is not merged into a stay entry is a candidate;
 //   3. the `width` best candidates (score descending, creation order ascending, i.e. the order in which
@@ -31,6 +34,7 @@ namespace img {
 namespace {
 
 constexpr int kBeamThreads = 128;
+constexpr int kNodeInts = 6;
 constexpr int kHistBins = 2048;
 
 __device__ __forceinline__ double lae(double a, double b) {
@@ -51,8 +55,8 @@ struct BeamShared {
   double *s_pb, *s_pnb, *s_tot;  // their stay entries at this timestep
   double *n_pb, *n_pnb;          // next beams
   double* sel_score;             // [Wp2]
-  int *b_node, *b_parent, *b_last, *b_pj, *b_oid;
-  int *n_node, *n_parent, *n_last;
+  int *b_node, *b_parent, *b_last, *b_pj, *b_oid, *b_canon, *b_pcanon;
+  int *n_node, *n_parent, *n_last, *n_canon, *n_pcanon;
   int *sel_id, *sel_oid;         // [Wp2] candidate id, creation-order id
   unsigned* mask;                // [W * Cw]
   int* hist;                     // [kHistBins]
@@ -119,18 +123,21 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const float* __r
     s.sel_score = d; d += Wp2;
     int* q = reinterpret_cast<int*>(d);
     s.b_node = q; q += W; s.b_parent = q; q += W; s.b_last = q; q += W; s.b_pj = q; q += W; s.b_oid = q; q += W;
-    s.n_node = q; q += W; s.n_parent = q; q += W; s.n_last = q; q += W;
+    s.b_canon = q; q += W; s.b_pcanon = q; q += W;
+    s.n_node = q; q += W; s.n_parent = q; q += W; s.n_last = q; q += W; s.n_canon = q; q += W; s.n_pcanon = q; q += W;
     s.sel_id = q; q += Wp2; s.sel_oid = q; q += Wp2;
     s.mask = reinterpret_cast<unsigned*>(q); q += W * Cw;
     s.hist = q; q += kHistBins;
     s.misc = q;
   }
-  int32_t* nd = nodes + L.node_off * 3;  // [(W*T + 1)][parent, label, pos]
+  // node record: [parent, label, pos, canonical id, next sibling, first child]; the sibling lists hang off the
+  // CANONICAL node of the parent prefix and hold one node per distinct (parent prefix, label)
+  int32_t* nd = nodes + L.node_off * kNodeInts;
   int nb = 1;
   if (tid == 0) {
-    s.b_node[0] = 0; s.b_parent[0] = -1; s.b_last[0] = 0;
+    s.b_node[0] = 0; s.b_parent[0] = -1; s.b_last[0] = 0; s.b_canon[0] = 0; s.b_pcanon[0] = -1;
     s.b_pb[0] = 0.0; s.b_pnb[0] = -INFINITY; s.b_tot[0] = 0.0;
-    nd[0] = -1; nd[1] = 0; nd[2] = 0;
+    nd[0] = -1; nd[1] = 0; nd[2] = 0; nd[3] = 0; nd[4] = -1; nd[5] = -1;
   }
   __syncthreads();
 
@@ -140,10 +147,10 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const float* __r
     for (int w = tid; w < nb * Cw; w += nthr) s.mask[w] = 0u;
     // parent-in-beam lookup
     for (int i = tid; i < nb; i += nthr) {
-      int par = s.b_parent[i], pj = -1;
+      int par = s.b_pcanon[i], pj = -1;  // prefix identity = canonical id
       if (par >= 0)
         for (int j = 0; j < nb; ++j)
-          if (s.b_node[j] == par) { pj = j; break; }
+          if (s.b_canon[j] == par) { pj = j; break; }
       s.b_pj[i] = pj;
     }
     __syncthreads();
@@ -282,25 +289,42 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const float* __r
       }
     }
     // ---- next beams ----
+    // phase 1 (read only): new nodes look their prefix up in the child list of the parent's canonical node
     for (int r = tid; r < K; r += nthr) {
       int id = s.sel_id[r];
       int i = id / C, c = id - i * C;
       if (c == 0) {
         s.n_node[r] = s.b_node[i]; s.n_parent[r] = s.b_parent[i]; s.n_last[r] = s.b_last[i];
+        s.n_canon[r] = s.b_canon[i]; s.n_pcanon[r] = s.b_pcanon[i];
         s.n_pb[r] = s.s_pb[i]; s.n_pnb[r] = s.s_pnb[i];
       } else {
         int node = 1 + t * W + r;
-        int par = s.b_node[i];
-        nd[3 * (int64_t)node] = par; nd[3 * (int64_t)node + 1] = c; nd[3 * (int64_t)node + 2] = t;
+        int par = s.b_node[i], pc = s.b_canon[i];
+        int canon = -1;
+        for (int ch = nd[kNodeInts * (int64_t)pc + 5]; ch >= 0; ch = nd[kNodeInts * (int64_t)ch + 4])
+          if (nd[kNodeInts * (int64_t)ch + 1] == c) { canon = ch; break; }
+        int32_t* rec = nd + kNodeInts * (int64_t)node;
+        rec[0] = par; rec[1] = c; rec[2] = t; rec[3] = canon < 0 ? node : canon; rec[4] = -1; rec[5] = -1;
         s.n_node[r] = node; s.n_parent[r] = par; s.n_last[r] = c;
+        s.n_canon[r] = canon < 0 ? node : canon; s.n_pcanon[r] = pc;
         s.n_pb[r] = -INFINITY; s.n_pnb[r] = s.sel_score[r];
       }
     }
     __syncthreads();
+    // phase 2: first-time prefixes become the canonical node: push onto the parent's child list
+    for (int r = tid; r < K; r += nthr) {
+      const int node = s.n_node[r];
+      if (node == 1 + t * W + r && s.n_canon[r] == node) {
+        const int old = atomicExch(&nd[kNodeInts * (int64_t)s.n_pcanon[r] + 5], node);
+        nd[kNodeInts * (int64_t)node + 4] = old;
+      }
+    }
     for (int r = tid; r < K; r += nthr) {
       s.b_node[r] = s.n_node[r]; s.b_parent[r] = s.n_parent[r]; s.b_last[r] = s.n_last[r];
+      s.b_canon[r] = s.n_canon[r]; s.b_pcanon[r] = s.n_pcanon[r];
       s.b_pb[r] = s.n_pb[r]; s.b_pnb[r] = s.n_pnb[r]; s.b_tot[r] = s.sel_score[r];
     }
+    __threadfence_block();
     nb = K;
     __syncthreads();
   }
@@ -308,12 +332,12 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const float* __r
   if (tid == 0) {
     __threadfence_block();
     int n = 0;
-    for (int node = s.b_node[0]; node != 0; node = nd[3 * (int64_t)node]) ++n;
+    for (int node = s.b_node[0]; node != 0; node = nd[kNodeInts * (int64_t)node]) ++n;
     int k = n;
-    for (int node = s.b_node[0]; node != 0; node = nd[3 * (int64_t)node]) {
+    for (int node = s.b_node[0]; node != 0; node = nd[kNodeInts * (int64_t)node]) {
       --k;
-      out[L.lab_off + k] = nd[3 * (int64_t)node + 1];
-      out[L.pos_off + k] = nd[3 * (int64_t)node + 2];
+      out[L.lab_off + k] = nd[kNodeInts * (int64_t)node + 1];
+      out[L.pos_off + k] = nd[kNodeInts * (int64_t)node + 2];
     }
     out[L.cnt_off] = n;
   }
@@ -327,7 +351,7 @@ int next_pow2(int v) {
 
 size_t beam_smem_bytes(int C, int W, int Wp2) {
   size_t Cw = (size_t)(C + 31) / 32;
-  return (size_t)(((C + 1) & ~1) + 8 * W + Wp2) * 8 + (size_t)(8 * W + 2 * Wp2 + W * Cw + kHistBins + 8) * 4;
+  return (size_t)(((C + 1) & ~1) + 8 * W + Wp2) * 8 + (size_t)(12 * W + 2 * Wp2 + W * Cw + kHistBins + 8) * 4;
 }
 
 }  // namespace

@@ -76,7 +76,7 @@ struct Engine::HostTimer {
 
 struct Engine::PageScratch {
   int cap_hw = 0;
-  DeviceBuffer mask, prob, labels, comp_roots, counters, pts, simp_idx, stack, fpts, hull, rects, rect_root;
+  DeviceBuffer mask, bits, wstart, prob, labels, comp_roots, counters, pts, simp_idx, stack, fpts, hull, rects, rect_root;
   img::ComponentBuffers bufs{};
 };
 
@@ -88,6 +88,8 @@ Engine::PageScratch& Engine::scratch_for(int slot, int H, int W) {
     int64_t pool = 2 * hw + 16;
     int32_t max_comps = (int32_t)(((int64_t)(H + 1) / 2) * ((W + 1) / 2) + 1);
     s.mask.reserve((size_t)hw);
+    s.bits.reserve((size_t)H * ((W + 31) / 32) * 4 + 4);
+    s.wstart.reserve((size_t)H * ((W + 31) / 32) * 2 + 4);
     s.labels.reserve((size_t)(hw + 1) * 4);
     s.comp_roots.reserve((size_t)max_comps * 4);
     s.counters.reserve(8 * 4);
@@ -434,7 +436,7 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
       const OcrInput& in = *pages[i];
       PageScratch& s = scratch_for(i, in.H, in.W);
       int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
-      tab[i] = img::PageResizeOut{out.data + i * plane, nullptr, s.mask.as<uint8_t>(), in_h - pb, in_w - pr, in.H, in.W};
+      tab[i] = img::PageResizeOut{out.data + i * plane, nullptr, s.mask.as<uint8_t>(), s.bits.as<uint32_t>(), in_h - pb, in_w - pr, in.H, in.W};
       max_h = std::max(max_h, in.H);
       max_w = std::max(max_w, in.W);
       rt_bytes += 4.0 * (in_h - pb) * (in_w - pr) + (double)in.H * in.W;
@@ -445,26 +447,31 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
     img::resize_threshold_batch(tab_out_.as<img::PageResizeOut>(), N, in_w, max_h, max_w, text_threshold_, st_);
     prof_.end(t1, st_, 0, rt_bytes);
   }
-  // post-processing of the N pages is independent: fork onto per-page side streams so the small,
-  // latency-bound kernels (labelling, per-component border following) overlap
-  const int n_aux = prof_.enabled ? 1 : std::min(N, 8);  // profiling brackets need serial kernels
-  ensure_aux(n_aux);
-  OCRS_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
-  for (int a = 0; a < n_aux; ++a) OCRS_CUDA_CHECK(cudaStreamWaitEvent(aux_[a], ev_fork_, 0));
-  for (int i = 0; i < N; ++i) {
-    const OcrInput& in = *pages[i];
-    cudaStream_t sa = aux_[i % n_aux];
-    PageScratch& s = *scratch_[i];
-    int t2 = prof_.begin("stage/components_to_rects", sa);
-    img::find_component_rects(s.mask.as<uint8_t>(), in.H, in.W, 2.0f /* detection.rs:50 */,
-                              3.0f /* detection.rs:116 */, min_area_, s.bufs, sa);
-    prof_.end(t2, sa, 0, 5.0 * in.H * in.W);  // read mask + write/read labels
-    OCRS_CUDA_CHECK(cudaMemcpyAsync(h_counters + 8 * i, s.bufs.counters, 8 * 4, cudaMemcpyDeviceToHost, sa));
-    d2h_bytes_ += 32;
-  }
-  for (int a = 0; a < n_aux; ++a) {
-    OCRS_CUDA_CHECK(cudaEventRecord(aux_done_[a], aux_[a]));
-    OCRS_CUDA_CHECK(cudaStreamWaitEvent(st_, aux_done_[a], 0));
+  // labelling + contours -> rects of all pages: four launches for the batch
+  {
+    std::vector<img::CclPage> ctab((size_t)N);
+    double cc_bytes = 0;
+    for (int i = 0; i < N; ++i) {
+      const OcrInput& in = *pages[i];
+      PageScratch& s = *scratch_[i];
+      img::CclPage& c = ctab[(size_t)i];
+      c.bits = s.bits.as<uint32_t>();
+      c.wstart = s.wstart.as<uint16_t>();
+      c.labels = s.bufs.labels;
+      c.H = in.H; c.W = in.W; c.wd = (in.W + 31) / 32;
+      c.bufs = s.bufs;
+      cc_bytes += (double)in.H * c.wd * 4.0 * 3.0;  // packed mask: init, union, flatten passes
+    }
+    tab_ccl_.reserve(ctab.size() * sizeof(img::CclPage));
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(tab_ccl_.ptr, ctab.data(), ctab.size() * sizeof(img::CclPage), cudaMemcpyHostToDevice, st_));
+    int t2 = prof_.begin("stage/components_to_rects", st_);
+    img::find_component_rects_batch(tab_ccl_.as<img::CclPage>(), ctab.data(), N, 2.0f /* detection.rs:50 */,
+                                    3.0f /* detection.rs:116 */, min_area_, st_);
+    prof_.end(t2, st_, 0, cc_bytes);
+    for (int i = 0; i < N; ++i) {
+      OCRS_CUDA_CHECK(cudaMemcpyAsync(h_counters + 8 * i, scratch_[i]->bufs.counters, 8 * 4, cudaMemcpyDeviceToHost, st_));
+      d2h_bytes_ += 32;
+    }
   }
   OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
   std::vector<std::vector<int32_t>> roots((size_t)N);
@@ -674,7 +681,7 @@ std::vector<std::vector<TextLine>> Engine::recognize_text_locked(
       }
     const size_t lab_bytes = ((size_t)rows * 4 + 15) / 16 * 16;
     const size_t desc_bytes = (cl.size() * sizeof(img::CtcLine) + 15) / 16 * 16;
-    ctc_scratch_.reserve(lab_bytes + desc_bytes + (size_t)n_nodes * 12 + 64);
+    ctc_scratch_.reserve(lab_bytes + desc_bytes + (size_t)n_nodes * 24 + 64);
     int32_t* row_labels = ctc_scratch_.as<int32_t>();
     auto* d_cl = reinterpret_cast<img::CtcLine*>(ctc_scratch_.as<char>() + lab_bytes);
     int32_t* d_nodes = reinterpret_cast<int32_t*>(ctc_scratch_.as<char>() + lab_bytes + desc_bytes);

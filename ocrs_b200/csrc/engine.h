@@ -161,7 +161,7 @@ class Engine {
   DeviceBuffer d_excluded_;
   std::vector<std::unique_ptr<PageScratch>> scratch_;
   DeviceBuffer det_in_, staging_, line_desc_, poly_, cross_, rec_batch_, ctc_scratch_, ctc_out_, page_tab_;
-  DeviceBuffer tab_in_, tab_out_, tab_prep_;  // per-batch page tables of the batched pixel kernels
+  DeviceBuffer tab_in_, tab_out_, tab_prep_, tab_ccl_;  // per-batch page tables of the batched pixel kernels
   PinnedBuffer h_pin_;
   std::mutex mu_;
   Stats stats_;

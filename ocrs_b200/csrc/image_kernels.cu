@@ -127,17 +127,26 @@ __global__ void resize_padded_batch_kernel(const PageResizeIn* __restrict__ tab,
 
 __global__ void resize_threshold_batch_kernel(const PageResizeOut* __restrict__ tab, int inW, float thr) {
   const PageResizeOut pg = tab[blockIdx.z];
-  int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  int ox = blockIdx.x * blockDim.x + threadIdx.x;  // a warp covers 32 consecutive x starting at a multiple of 32
   int oy = blockIdx.y;
-  if (ox >= pg.W || oy >= pg.H) return;
-  AxisTap ty = axis_tap(oy, pg.sliceH, pg.H);
-  AxisTap tx = axis_tap(ox, pg.sliceW, pg.W);
-  const float* r0 = pg.net + (int64_t)ty.i0 * inW;
-  const float* r1 = pg.net + (int64_t)ty.i1 * inW;
-  float v = lerp2(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), tx.w, ty.w);
-  int64_t o = (int64_t)oy * pg.W + ox;
-  if (pg.prob) pg.prob[o] = v;
-  pg.mask[o] = v > thr ? 1 : 0;
+  if (oy >= pg.H) return;
+  const bool in = ox < pg.W;
+  bool fg = false;
+  if (in) {
+    AxisTap ty = axis_tap(oy, pg.sliceH, pg.H);
+    AxisTap tx = axis_tap(ox, pg.sliceW, pg.W);
+    const float* r0 = pg.net + (int64_t)ty.i0 * inW;
+    const float* r1 = pg.net + (int64_t)ty.i1 * inW;
+    float v = lerp2(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), tx.w, ty.w);
+    int64_t o = (int64_t)oy * pg.W + ox;
+    if (pg.prob) pg.prob[o] = v;
+    fg = v > thr;
+    pg.mask[o] = fg ? 1 : 0;
+  }
+  // bit-packed copy of the mask (bit x & 31 of word x >> 5; bits beyond W are 0) for labelling / contours
+  const unsigned word = __ballot_sync(0xffffffffu, fg);
+  const int wd = (pg.W + 31) >> 5;
+  if ((threadIdx.x & 31) == 0 && pg.bits != nullptr && (ox >> 5) < wd) pg.bits[(int64_t)oy * wd + (ox >> 5)] = word;
 }
 
 // u8 HWC RGB pages of one shape, 4 pixels (12 bytes) per thread, page = blockIdx.y
@@ -165,10 +174,19 @@ __global__ void threshold_kernel(const float* __restrict__ p, uint8_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// Connected components: union-find with atomicMin (root = smallest pixel index of the set).
+// Connected components on the bit-packed mask, run based.
 // Foreground is 8-connected, background 4-connected (so that holes are what Suzuki-Abe's
-// outermost-border rule sees); background pixels on the image border are united with the
-// virtual frame node at index H*W.
+// outermost-border rule sees); background pixels on the image border are united with a virtual
+// frame node at index H*W.  Nodes of the union-find are the START pixels of horizontal runs of
+// equal value (index y*W + x; root = smallest index of the set, so the root of a foreground
+// component is its first pixel in raster order).  One warp per row, lane = 32-pixel word:
+//   ccl_init   : parent[start] = start for every run start; wstart[y][w] = start x of the run that
+//                covers bit 0 of word w (warp scan over "uniform" words);
+//   ccl_union  : for the three 8-neighbour offsets d (foreground) / d = 0 (background) the pair masks
+//                P_d = cur & shift(up, d); one union per maximal run of P_d (a run of pairs joins the
+//                same two runs) -- no per-pixel work, no shared-memory atomics;
+//   ccl_flatten: parent[start] = root; foreground roots are appended to the component list.
+// All pages of a batch run in one launch each (blockIdx.y = page).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int uf_find(const int32_t* L, int i) {
   int p = L[i];
@@ -197,110 +215,171 @@ __device__ void uf_union(int32_t* L, int a, int b) {
   }
 }
 
-__global__ void ccl_frame_init_kernel(int32_t* L, int64_t n) { L[n] = (int32_t)n; }
-
-// ---- two-level labelling: tile-local union-find in shared memory, then unions across tile borders ----
-constexpr int kTile = 32;
-
-__device__ __forceinline__ int suf_find(const int* L, int i) {
-  int p = L[i];
-  while (p != i) {
-    i = p;
-    p = L[i];
-  }
-  return i;
-}
-__device__ __forceinline__ void suf_union(int* L, int a, int b) {
-  bool done = false;
-  while (!done) {
-    a = suf_find(L, a);
-    b = suf_find(L, b);
-    if (a < b) {
-      int old = atomicMin(&L[b], a);
-      done = (old == b);
-      b = old;
-    } else if (b < a) {
-      int old = atomicMin(&L[a], b);
-      done = (old == a);
-      a = old;
-    } else {
-      done = true;
-    }
-  }
+// start x of the run (of equal mask value) that contains pixel x of row y
+__device__ __forceinline__ int run_start(const uint32_t* __restrict__ bits, const uint16_t* __restrict__ wstart, int wd,
+                                         int y, int x) {
+  const int w = x >> 5, b = x & 31;
+  const uint32_t word = bits[(int64_t)y * wd + w];
+  const uint32_t same = ((word >> b) & 1u) ? word : ~word;  // bits equal to pixel x's value
+  const uint32_t z = ~same & ((1u << b) - 1u);              // different-valued bits below b
+  if (z) return (w << 5) + (32 - __clz(z));
+  return wstart[(int64_t)y * wd + w];
 }
 
-__global__ void __launch_bounds__(256) ccl_tile_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ L, int H,
-                                                       int W) {
-  __shared__ int sl[kTile * kTile];
-  __shared__ uint8_t sm[kTile * kTile];
-  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
-  const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;  // 8 rows per pass
-  for (int ty = ty0; ty < kTile; ty += 8) {
-    int x = x0 + tx, y = y0 + ty, li = ty * kTile + tx;
-    sl[li] = li;
-    sm[li] = (x < W && y < H) ? (mask[(int64_t)y * W + x] ? 1 : 0) : 2;  // 2 = outside the image
-  }
-  __syncthreads();
-  for (int ty = ty0; ty < kTile; ty += 8) {
-    int li = ty * kTile + tx;
-    uint8_t v = sm[li];
-    if (v == 2) continue;
-    if (v) {
-      if (tx > 0 && sm[li - 1] == 1) suf_union(sl, li, li - 1);
-      if (ty > 0) {
-        if (sm[li - kTile] == 1) suf_union(sl, li, li - kTile);
-        if (tx > 0 && sm[li - kTile - 1] == 1) suf_union(sl, li, li - kTile - 1);
-        if (tx + 1 < kTile && sm[li - kTile + 1] == 1) suf_union(sl, li, li - kTile + 1);
+constexpr int kCclWarps = 4;
+
+__global__ void __launch_bounds__(kCclWarps * 32) ccl_init_kernel(const CclPage* __restrict__ pages) {
+  const CclPage pg = pages[blockIdx.y];
+  const int y = blockIdx.x * kCclWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) pg.labels[(int64_t)pg.H * pg.W] = pg.H * pg.W;  // frame node
+  if (y >= pg.H) return;
+  const int wd = pg.wd, W = pg.W;
+  uint32_t prev_last = 0;       // last pixel value of the previous chunk's last word
+  int carry_start = 0;          // start of the run reaching the end of the previous chunk
+  for (int w0 = 0; w0 < wd; w0 += 32) {
+    const int w = w0 + lane;
+    const uint32_t m = w < wd ? pg.bits[(int64_t)y * wd + w] : 0u;
+    uint32_t p31 = __shfl_up_sync(0xffffffffu, m >> 31, 1);
+    if (lane == 0) p31 = w0 == 0 ? ((~m) & 1u) : prev_last;  // the first pixel of a row always starts a run
+    const uint32_t c = m ^ ((m << 1) | p31);                  // bit x: value differs from pixel x-1 -> run start
+    if (w < wd) {
+      uint32_t cc = c;
+      while (cc) {
+        const int bpos = __ffs(cc) - 1;
+        cc &= cc - 1;
+        const int x = (w << 5) + bpos;
+        if (x < W) pg.labels[(int64_t)y * W + x] = y * W + x;
       }
-    } else {
-      if (tx > 0 && sm[li - 1] == 0) suf_union(sl, li, li - 1);
-      if (ty > 0 && sm[li - kTile] == 0) suf_union(sl, li, li - kTile);
     }
-  }
-  __syncthreads();
-  for (int ty = ty0; ty < kTile; ty += 8) {
-    int x = x0 + tx, y = y0 + ty, li = ty * kTile + tx;
-    if (x >= W || y >= H) continue;
-    int r = suf_find(sl, li);
-    L[(int64_t)y * W + x] = (y0 + r / kTile) * W + x0 + (r % kTile);  // global index of the tile-local root
+    // start of the run that covers the LAST bit of each word; words without a change are transparent
+    const int last_start = c ? (w << 5) + (31 - __clz(c)) : 0;
+    const unsigned nt = __ballot_sync(0xffffffffu, c != 0u && w < wd);
+    const unsigned below = nt & (0xffffffffu >> (31 - lane));  // non-transparent lanes <= lane
+    const int src = below ? 31 - __clz(below) : 0;
+    int resolved = __shfl_sync(0xffffffffu, last_start, src);
+    if (!below) resolved = carry_start;
+    int prev_resolved = __shfl_up_sync(0xffffffffu, resolved, 1);
+    if (lane == 0) prev_resolved = carry_start;
+    if (w < wd) pg.wstart[(int64_t)y * wd + w] = (uint16_t)((c & 1u) ? (w << 5) : prev_resolved);
+    carry_start = __shfl_sync(0xffffffffu, resolved, 31);
+    prev_last = __shfl_sync(0xffffffffu, m >> 31, 31);
   }
 }
 
-// unions across tile borders + the virtual frame node (index H*W) for background on the image border
-__global__ void ccl_border_kernel(const uint8_t* __restrict__ mask, int32_t* L, int H, int W) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y;
-  if (x >= W) return;
-  const bool on_v = (x % kTile) == 0, on_h = (y % kTile) == 0;
-  const bool img_border = (x == 0 || y == 0 || x == W - 1 || y == H - 1);
-  const bool right_edge = (x % kTile) == kTile - 1;  // NE neighbour lies in the next tile column
-  if (!on_v && !on_h && !img_border && !right_edge) return;
-  int p = y * W + x;
-  uint8_t v = mask[p];
-  if (v) {
-    if (on_v && x > 0 && mask[p - 1]) uf_union(L, p, p - 1);
-    if (y > 0) {
-      if (on_h && mask[p - W]) uf_union(L, p, p - W);
-      if ((on_h || on_v) && x > 0 && mask[p - W - 1]) uf_union(L, p, p - W - 1);
-      if ((on_h || right_edge) && x + 1 < W && mask[p - W + 1]) uf_union(L, p, p - W + 1);
+__global__ void __launch_bounds__(kCclWarps * 32) ccl_union_kernel(const CclPage* __restrict__ pages) {
+  const CclPage pg = pages[blockIdx.y];
+  const int y = blockIdx.x * kCclWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (y >= pg.H) return;
+  const int wd = pg.wd, W = pg.W, H = pg.H;
+  const int frame = H * W;
+  int32_t* L = pg.labels;
+  const uint32_t* bits = pg.bits;
+  const uint16_t* ws = pg.wstart;
+  // carries between chunks of 32 words: last bit of the pair masks of the previous chunk's last word
+  uint32_t cm = 0, cu = 0, cP0 = 0, cPm = 0, cPp = 0, cQ = 0;
+  for (int w0 = 0; w0 < wd; w0 += 32) {
+    const int w = w0 + lane;
+    const bool live = w < wd;
+    const uint32_t m = live ? bits[(int64_t)y * wd + w] : 0u;
+    const uint32_t u = (live && y > 0) ? bits[(int64_t)(y - 1) * wd + w] : 0u;
+    uint32_t valid = 0u;
+    if (live) valid = (W - (w << 5) >= 32) ? 0xffffffffu : ((1u << (W - (w << 5))) - 1u);
+    // neighbour bits of the upper row across word boundaries
+    uint32_t u_prev31 = __shfl_up_sync(0xffffffffu, u >> 31, 1);
+    if (lane == 0) u_prev31 = cu;
+    uint32_t u_next0 = __shfl_down_sync(0xffffffffu, u & 1u, 1);
+    if (lane == 31) u_next0 = (w + 1 < wd && y > 0) ? (bits[(int64_t)(y - 1) * wd + w + 1] & 1u) : 0u;
+    const uint32_t up_m1 = (u << 1) | u_prev31;          // upper pixel at x - 1
+    const uint32_t up_p1 = (u >> 1) | (u_next0 << 31);   // upper pixel at x + 1
+    const uint32_t P0 = m & u, Pm = m & up_m1, Pp = m & up_p1;
+    const uint32_t bgm = ~m & valid, bgu = (y > 0) ? (~u & valid) : 0u;
+    const uint32_t Q = bgm & bgu;
+    auto prev31 = [&](uint32_t v, uint32_t carry) {
+      uint32_t p = __shfl_up_sync(0xffffffffu, v >> 31, 1);
+      return lane == 0 ? carry : p;
+    };
+    const uint32_t E0 = P0 & ~((P0 << 1) | prev31(P0, cP0));
+    const uint32_t Em = Pm & ~((Pm << 1) | prev31(Pm, cPm));
+    const uint32_t Ep = Pp & ~((Pp << 1) | prev31(Pp, cPp));
+    const uint32_t EQ = Q & ~((Q << 1) | prev31(Q, cQ));
+    if (live && y > 0) {
+      for (int d = -1; d <= 1; ++d) {
+        uint32_t e = d == 0 ? E0 : (d < 0 ? Em : Ep);
+        while (e) {
+          const int bpos = __ffs(e) - 1;
+          e &= e - 1;
+          const int x = (w << 5) + bpos;
+          uf_union(L, y * W + run_start(bits, ws, wd, y, x), (y - 1) * W + run_start(bits, ws, wd, y - 1, x + d));
+        }
+      }
+      uint32_t e = EQ;
+      while (e) {
+        const int bpos = __ffs(e) - 1;
+        e &= e - 1;
+        const int x = (w << 5) + bpos;
+        uf_union(L, y * W + run_start(bits, ws, wd, y, x), (y - 1) * W + run_start(bits, ws, wd, y - 1, x));
+      }
     }
-  } else {
-    if (on_v && x > 0 && !mask[p - 1]) uf_union(L, p, p - 1);
-    if (on_h && y > 0 && !mask[p - W]) uf_union(L, p, p - W);
-    if (img_border) uf_union(L, p, H * W);
+    // background on the image border joins the frame node
+    if (live) {
+      uint32_t border = 0u;
+      if (w == 0) border |= bgm & 1u;
+      if (w == ((W - 1) >> 5)) border |= bgm & (1u << ((W - 1) & 31));
+      while (border) {
+        const int bpos = __ffs(border) - 1;
+        border &= border - 1;
+        uf_union(L, y * W + run_start(bits, ws, wd, y, (w << 5) + bpos), frame);
+      }
+    }
+    if (y == 0 || y == H - 1) {
+      // run starts of background in this word (value changes where the new value is background)
+      uint32_t p31 = __shfl_up_sync(0xffffffffu, m >> 31, 1);
+      if (lane == 0) p31 = w0 == 0 ? ((~m) & 1u) : cm;
+      uint32_t sb = (m ^ ((m << 1) | p31)) & bgm;
+      while (live && sb) {
+        const int bpos = __ffs(sb) - 1;
+        sb &= sb - 1;
+        uf_union(L, y * W + (w << 5) + bpos, frame);
+      }
+    }
+    cm = __shfl_sync(0xffffffffu, m >> 31, 31);
+    cu = __shfl_sync(0xffffffffu, u >> 31, 31);
+    cP0 = __shfl_sync(0xffffffffu, P0 >> 31, 31);
+    cPm = __shfl_sync(0xffffffffu, Pm >> 31, 31);
+    cPp = __shfl_sync(0xffffffffu, Pp >> 31, 31);
+    cQ = __shfl_sync(0xffffffffu, Q >> 31, 31);
   }
 }
 
-__global__ void ccl_flatten_kernel(const uint8_t* __restrict__ mask, int32_t* L, int64_t n, int32_t* comp_roots,
-                                   int32_t* counters, int max_comps) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > n) return;
-  int r = uf_find(L, (int)i);
-  L[i] = r;
-  if (i < n && r == (int)i && mask[i]) {
-    int slot = atomicAdd(&counters[0], 1);
-    if (slot < max_comps) comp_roots[slot] = (int)i;
-    else atomicExch(&counters[2], 1);
+__global__ void __launch_bounds__(kCclWarps * 32) ccl_flatten_kernel(const CclPage* __restrict__ pages) {
+  const CclPage pg = pages[blockIdx.y];
+  const int y = blockIdx.x * kCclWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int W = pg.W, wd = pg.wd;
+  int32_t* L = pg.labels;
+  if (blockIdx.x == 0 && threadIdx.x == 0) L[(int64_t)pg.H * W] = uf_find(L, pg.H * W);
+  if (y >= pg.H) return;
+  uint32_t prev_last = 0;
+  for (int w0 = 0; w0 < wd; w0 += 32) {
+    const int w = w0 + lane;
+    const uint32_t m = w < wd ? pg.bits[(int64_t)y * wd + w] : 0u;
+    uint32_t p31 = __shfl_up_sync(0xffffffffu, m >> 31, 1);
+    if (lane == 0) p31 = w0 == 0 ? ((~m) & 1u) : prev_last;
+    uint32_t c = m ^ ((m << 1) | p31);
+    while (w < wd && c) {
+      const int bpos = __ffs(c) - 1;
+      c &= c - 1;
+      const int x = (w << 5) + bpos;
+      if (x >= W) break;
+      const int node = y * W + x;
+      const int r = uf_find(L, node);
+      L[node] = r;
+      if (((m >> bpos) & 1u) && r == node) {
+        const int slot = atomicAdd(&pg.bufs.counters[0], 1);
+        if (slot < pg.bufs.max_comps) pg.bufs.comp_roots[slot] = node;
+        else atomicExch(&pg.bufs.counters[2], 1);
+      }
+    }
+    prev_last = __shfl_sync(0xffffffffu, m >> 31, 31);
   }
 }
 
@@ -311,46 +390,60 @@ __constant__ int kDy[8] = {0, 1, 1, 1, 0, -1, -1, -1};  // clockwise from E (ima
 __constant__ int kDx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 __constant__ int kDirOf[9] = {5, 6, 7, 4, -1, 0, 3, 2, 1};  // [(dy+1)*3 + (dx+1)]
 
-struct MaskView {
-  const uint8_t* m;
-  int H, W;
-  __device__ __forceinline__ int at(int y, int x) const {
-    return (y >= 0 && y < H && x >= 0 && x < W) ? m[y * W + x] : 0;
+struct BitView {
+  const uint32_t* bits;
+  int H, W, wd;
+  // the three mask bits (x-1, x, x+1) of row y as bits 0..2; 0 outside the image
+  __device__ __forceinline__ uint32_t row3(int y, int x) const {
+    if (y < 0 || y >= H) return 0u;
+    const uint32_t* r = bits + (int64_t)y * wd;
+    const int x0 = x - 1;  // may be -1
+    const int w = x0 >> 5;  // arithmetic shift: -1 for x0 = -1
+    const uint64_t lo = w >= 0 ? r[w] : 0u;
+    const uint64_t hi = (w + 1 < wd) ? r[w + 1] : 0u;
+    const uint64_t both = lo | (hi << 32);
+    return (uint32_t)(both >> (x0 & 31)) & 7u;  // bits beyond W are 0 in the packed mask
+  }
+  // 8-neighbourhood of (y, x): bit d = neighbour in direction d (kDy / kDx order)
+  __device__ __forceinline__ uint32_t nb8(int y, int x) const {
+    const uint32_t a = row3(y - 1, x), b = row3(y, x), c = row3(y + 1, x);
+    // directions: 0 E (0,+1), 1 SE (+1,+1), 2 S (+1,0), 3 SW (+1,-1), 4 W (0,-1), 5 NW (-1,-1), 6 N (-1,0), 7 NE (-1,+1)
+    return ((b >> 2) & 1u) | (((c >> 2) & 1u) << 1) | (((c >> 1) & 1u) << 2) | ((c & 1u) << 3) | ((b & 1u) << 4) |
+           ((a & 1u) << 5) | (((a >> 1) & 1u) << 6) | (((a >> 2) & 1u) << 7);
   }
 };
 
 // Follows the outer border that starts at (i, j) (the component's first pixel in raster
 // order).  When `out` is non-null writes (x, y) pairs.  Returns the number of points, or -1 if
-// `limit` would be exceeded.
-__device__ int trace_border(const MaskView& mv, int i, int j, int16_t* out, int64_t limit) {
+// `limit` would be exceeded.  One neighbourhood fetch (three rows of the packed mask) per step.
+__device__ int trace_border(const BitView& mv, int i, int j, int16_t* out, int64_t limit) {
   int i1 = 0, j1 = 0;
-  bool found = false;
-  for (int k = 0; k < 8; ++k) {  // (3.1) clockwise from W around (i, j)
-    int d = (4 + k) & 7;
-    if (mv.at(i + kDy[d], j + kDx[d])) {
-      i1 = i + kDy[d];
-      j1 = j + kDx[d];
-      found = true;
-      break;
+  {  // (3.1) clockwise from W around (i, j): d = 4, 5, 6, 7, 0, 1, 2, 3
+    const uint32_t nb = mv.nb8(i, j);
+    const uint32_t t = nb | (nb << 8);
+    const uint32_t w = (t >> 4) & 0xFFu;
+    if (!w) {  // isolated pixel
+      if (limit < 1) return -1;
+      if (out) { out[0] = (int16_t)j; out[1] = (int16_t)i; }
+      return 1;
     }
-  }
-  if (!found) {  // isolated pixel
-    if (limit < 1) return -1;
-    if (out) { out[0] = (int16_t)j; out[1] = (int16_t)i; }
-    return 1;
+    const int d = (4 + (__ffs(w) - 1)) & 7;
+    i1 = i + kDy[d];
+    j1 = j + kDx[d];
   }
   int i2 = i1, j2 = j1, i3 = i, j3 = j;
   int n = 0;
   while (true) {
-    int d0 = kDirOf[(i2 - i3 + 1) * 3 + (j2 - j3 + 1)];
+    const int d0 = kDirOf[(i2 - i3 + 1) * 3 + (j2 - j3 + 1)];
+    // counter-clockwise from the direction after d0: d = d0-1, d0-2, ..., d0-8
+    const uint32_t nb = mv.nb8(i3, j3);
+    const uint32_t t = nb | (nb << 8);
+    const uint32_t w = (t >> d0) & 0xFFu;  // bit q = direction (d0 + q) & 7; scan q = 7 down to 0
     int i4 = i3, j4 = j3;
-    for (int k = 1; k <= 8; ++k) {
-      int d = (d0 - k) & 7;
-      if (mv.at(i3 + kDy[d], j3 + kDx[d])) {
-        i4 = i3 + kDy[d];
-        j4 = j3 + kDx[d];
-        break;
-      }
+    if (w) {
+      const int d = (d0 + (31 - __clz(w))) & 7;
+      i4 = i3 + kDy[d];
+      j4 = j3 + kDx[d];
     }
     if (n >= limit) return -1;
     if (out) { out[2 * n] = (int16_t)j3; out[2 * n + 1] = (int16_t)i3; }
@@ -361,8 +454,10 @@ __device__ int trace_border(const MaskView& mv, int i, int j, int16_t* out, int6
   return n;
 }
 
-__global__ void component_rects_kernel(const uint8_t* __restrict__ mask, int H, int W, float eps, float expand,
-                                       float min_area, ComponentBuffers b) {
+__global__ void component_rects_kernel(const CclPage* __restrict__ pages, float eps, float expand, float min_area) {
+  const CclPage pg = pages[blockIdx.y];
+  const ComponentBuffers& b = pg.bufs;
+  const int H = pg.H, W = pg.W;
   int ci = blockIdx.x * blockDim.x + threadIdx.x;
   int n_comps = min(b.counters[0], b.max_comps);
   if (ci >= n_comps) return;
@@ -370,8 +465,8 @@ __global__ void component_rects_kernel(const uint8_t* __restrict__ mask, int H, 
   int i = root / W, j = root - i * W;
   // outermost-border rule (Suzuki-Abe App. II): the 0-pixel left of the first pixel must belong
   // to the background component that touches the frame.
-  if (j > 0 && b.labels[root - 1] != b.labels[(int64_t)H * W]) return;
-  MaskView mv{mask, H, W};
+  if (j > 0 && pg.labels[(int64_t)i * W + run_start(pg.bits, pg.wstart, pg.wd, i, j - 1)] != pg.labels[(int64_t)H * W]) return;
+  BitView mv{pg.bits, H, W, pg.wd};
   int n = trace_border(mv, i, j, nullptr, b.pool_cap);
   if (n < 0) { atomicExch(&b.counters[2], 2); return; }
   int64_t off = (int64_t)atomicAdd((unsigned long long*)(void*)&b.counters[4], (unsigned long long)(n + 2));
@@ -683,28 +778,29 @@ void threshold(const float* prob, uint8_t* mask, int64_t n, float thr, cudaStrea
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
-void find_component_rects(const uint8_t* mask, int H, int W, float eps, float expand_dist, float min_area,
-                          const ComponentBuffers& b, cudaStream_t st) {
-  int64_t n = (int64_t)H * W;
-  OCRS_CUDA_CHECK(cudaMemsetAsync(b.counters, 0, 8 * sizeof(int32_t), st));
-  if (n == 0) return;
-  OCRS_CHECK(H < 32768 && W < 32768, kInvalidArg, "image dimensions exceed 32767");
-  {
-    dim3 tg((unsigned)ceil_div(W, kTile), (unsigned)ceil_div(H, kTile));
-    ccl_tile_kernel<<<tg, 256, 0, st>>>(mask, b.labels, H, W);
-    count_launch();
-    ccl_frame_init_kernel<<<1, 1, 0, st>>>(b.labels, n);
-    count_launch();
-    dim3 grid(grid1d(W, 128), H);
-    ccl_border_kernel<<<grid, 128, 0, st>>>(mask, b.labels, H, W);
-    count_launch();
+void find_component_rects_batch(const CclPage* d_pages, const CclPage* h_pages, int n_pages, float eps, float expand_dist,
+                                float min_area, cudaStream_t st) {
+  if (n_pages == 0) return;
+  int max_h = 0, max_c = 0;
+  for (int i = 0; i < n_pages; ++i) {
+    OCRS_CHECK(h_pages[i].H < 32768 && h_pages[i].W < 32768, kInvalidArg, "image dimensions exceed 32767");
+    OCRS_CHECK((int64_t)h_pages[i].H * h_pages[i].W < ((int64_t)1 << 31) - 1, kInvalidArg, "image too large");
+    OCRS_CUDA_CHECK(cudaMemsetAsync(h_pages[i].bufs.counters, 0, 8 * sizeof(int32_t), st));
+    max_h = std::max(max_h, h_pages[i].H);
+    max_c = std::max(max_c, h_pages[i].bufs.max_comps);
   }
-  ccl_flatten_kernel<<<grid1d(n + 1), kThreads, 0, st>>>(mask, b.labels, n, b.comp_roots, b.counters, b.max_comps);
+  if (max_h == 0) return;
+  dim3 rows((unsigned)ceil_div(max_h, kCclWarps), (unsigned)n_pages);
+  ccl_init_kernel<<<rows, kCclWarps * 32, 0, st>>>(d_pages);
+  count_launch();
+  ccl_union_kernel<<<rows, kCclWarps * 32, 0, st>>>(d_pages);
+  count_launch();
+  ccl_flatten_kernel<<<rows, kCclWarps * 32, 0, st>>>(d_pages);
   count_launch();
   // one thread per component; the count is only known on the device, so launch for the
-  // theoretical maximum in chunks guarded by counters[0] (cheap: threads beyond n_comps exit).
-  int max_c = b.max_comps;
-  component_rects_kernel<<<grid1d(max_c, 64), 64, 0, st>>>(mask, H, W, eps, expand_dist, min_area, b);
+  // theoretical maximum (cheap: threads beyond n_comps exit).
+  dim3 comps(grid1d(max_c, 64), (unsigned)n_pages);
+  component_rects_kernel<<<comps, 64, 0, st>>>(d_pages, eps, expand_dist, min_area);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }

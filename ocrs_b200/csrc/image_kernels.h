@@ -43,6 +43,7 @@ struct PageResizeOut {  // output of the detection epilogue: slice of the net ou
   const float* net;     // this page's [inH, inW] network output
   float* prob;          // may be null
   uint8_t* mask;
+  uint32_t* bits;       // bit-packed mask [H][ceil(W/32)] (may be null)
   int32_t sliceH, sliceW, H, W;
 };
 struct PagePrepare {    // u8 HWC RGB page -> grey f32
@@ -58,7 +59,7 @@ void prepare_image_rgb8_batch(const PagePrepare* d_tab, int n, int H, int W, cud
 
 // ---- connected components -> word rects -------------------------------------------------------
 struct ComponentBuffers {
-  int32_t* labels;       // [H*W + 1] union-find parents / final labels (+1 virtual frame node)
+  int32_t* labels;       // [H*W + 1] union-find parents of run-start pixels (+1 virtual frame node); other entries unused
   int32_t* comp_roots;   // [max_comps] root pixel index of each foreground component (unordered)
   int32_t* counters;     // [8]: [0] n_comps, [2] error flag, [3] n_rects, [4..5] pool top (u64)
   int16_t* pts;          // [pool_cap * 2] traced border points (x, y)
@@ -72,12 +73,22 @@ struct ComponentBuffers {
   int32_t max_comps;
 };
 
-// Computes word rects of `mask` [H, W] (detection.rs:41-62 semantics): outer contours of
-// 8-connected components that are not nested inside holes, RDP(eps), min-area rect, expanded
-// by 2*expand_dist, kept when area >= min_area.  Results: bufs.rects / bufs.rect_root,
-// count in bufs.counters[3]; unordered -- sort by rect_root for discovery order.
-void find_component_rects(const uint8_t* mask, int H, int W, float eps, float expand_dist, float min_area,
-                          const ComponentBuffers& bufs, cudaStream_t st);
+// One page of a detection batch for labelling + contour extraction.
+struct CclPage {
+  const uint32_t* bits;  // bit-packed mask [H][wd], bit (x & 31) of word (x >> 5); bits beyond W are 0
+  uint16_t* wstart;      // [H][wd] scratch: start x of the run covering bit 0 of each word
+  int32_t* labels;       // == bufs.labels
+  int32_t H, W, wd;
+  ComponentBuffers bufs;
+};
+
+// Word rects of a batch of masks (detection.rs:41-62 semantics): outer contours of 8-connected
+// components that are not nested inside holes, RDP(eps), min-area rect, expanded by 2*expand_dist,
+// kept when area >= min_area.  Results per page: bufs.rects / bufs.rect_root, count in
+// bufs.counters[3]; unordered -- sort by rect_root for discovery order.  `d_pages` is the device copy
+// of `h_pages`.  Four launches for the whole batch.
+void find_component_rects_batch(const CclPage* d_pages, const CclPage* h_pages, int n_pages, float eps, float expand_dist,
+                                float min_area, cudaStream_t st);
 
 // ---- line crops ------------------------------------------------------------------------------
 struct LineDesc {
@@ -117,7 +128,7 @@ void ctc_greedy_packed(const float* logits, int64_t rows, int C, const uint8_t* 
 
 // CTC prefix beam search (`DecodeMethod::BeamSearch { width }`, ocrs/src/recognition.rs:199-205,
 // 512-514), one thread block per line.  Same line descriptors and output layout as the greedy
-// decoder; `nodes` is scratch of 3 int32 per trie node, ctc_beam_nodes_per_line(T, width) nodes per
+// decoder; `nodes` is scratch of 6 int32 per trie node, ctc_beam_nodes_per_line(T, width) nodes per
 // line starting at CtcLine::node_off.
 constexpr int kMaxBeamWidth = 1024;
 int64_t ctc_beam_nodes_per_line(int T, int width);

@@ -64,7 +64,7 @@ def test_config1_640x480(engines):
     _staged_check(eng, ora, page)
 
 
-@pytest.mark.parametrize("seed", [200, 201])
+@pytest.mark.parametrize("seed", list(range(200, 208)))  # all eight pages of BASELINE.json configs[2]
 def test_config3_1024x768(engines, seed):
     eng, ora = engines
     page, _ = make_page(seed)
@@ -85,3 +85,17 @@ def test_engine_reads_the_page(engines):
     got = eng.get_text(inp).split("\n")
     assert len(got) == len(texts)
     assert sum(1 for g in got if g in texts) >= 0.9 * len(texts)
+
+
+def test_config3_batch_of_eight_through_the_pool(engines):
+    """The benchmark's own call path: the 8-page batch of configs[2] through the engine pool (host pages,
+    ocrs_b200_pool_submit / wait_text) gives, page by page, what the single-page calls give."""
+    eng, _ = engines
+    det, rec = model_paths()
+    pages = [make_page(seed)[0] for seed in range(200, 208)]
+    pool = ob.OcrPool(ob.OcrEngineParams(detection_model=det, recognition_model=rec), devices=[0], in_flight=2)
+    t1 = pool.submit([ob.ImageSource.from_tensor(p, ob.DimOrder.Hwc) for p in pages])
+    t2 = pool.submit([ob.ImageSource.from_tensor(p, ob.DimOrder.Hwc) for p in pages[::-1]])
+    got, got_rev = pool.wait_text(t1), pool.wait_text(t2)
+    single = [eng.get_text(eng.prepare_input(ob.ImageSource.from_tensor(p, ob.DimOrder.Hwc))) for p in pages]
+    assert got == single and got_rev == single[::-1]
