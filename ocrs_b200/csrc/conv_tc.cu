@@ -48,6 +48,18 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
   hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
   lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
 }
+// packed form for the conv epilogue: two cvt.rn.f16x2.f32 instead of four scalar conversions (the scalar
+// F2F.F16.F32 issues at a quarter of the ALU rate).  Overflow = the hi half came out as inf / NaN.
+// Returns non-zero when a value left the fp16 range (the caller ORs these and raises the flag once).
+__device__ __forceinline__ uint32_t split2_packed(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+  const uint32_t t = hi & 0x7C007C00u;  // exponent fields; all ones <=> inf / NaN
+  return (t + 0x04000400u) & 0x80008000u;
+}
 __device__ __forceinline__ float join_lo(uint32_t hi, uint32_t lo) {
   return __half2float(__ushort_as_half((uint16_t)(hi & 0xFFFFu))) + __half2float(__ushort_as_half((uint16_t)(lo & 0xFFFFu)));
 }
@@ -119,11 +131,14 @@ __device__ __forceinline__ void epilogue_store(const float (&acc)[32], const Til
                                                int ph, int pw, bool real_tile, const float* __restrict__ bias,
                                                act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, int* __restrict__ ovf) {
   constexpr int CH = 32, kRowsPerWarp = 32 / kTW;
-  const int th = wq * kRowsPerWarp + lane / kTW, tw = lane % kTW;
-  const int h = e.h0 + th, w = e.w0 + tw;
-  const int oh = h / ph, ow = w / pw;
+  // pooling factors are 1 or 2: divisions become shifts (an integer division costs ~20 issue slots, and the
+  // epilogue is issue-bound: profiles/r02i_conv_sass_stalls.md)
+  const int sh = ph >> 1, sw = pw >> 1;
+  const int th = wq * kRowsPerWarp + (lane >> 4), tw = lane & (kTW - 1);
+  const int oh = (e.h0 + th) >> sh, ow = (e.w0 + tw) >> sw;
   const bool writer = real_tile && (ph == 1 || (lane & kTW) == 0) && (pw == 1 || (lane & 1) == 0) && oh < e.OH && ow < e.OW;
   uint32_t hp[16], lp[16];
+  uint32_t bad = 0u;  // branch-free: every lane splits its values, only writers' overflow counts
 #pragma unroll
   for (int c0 = 0; c0 < CH; c0 += 8) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + hsel * CH + c0));
@@ -146,22 +161,26 @@ __device__ __forceinline__ void epilogue_store(const float (&acc)[32], const Til
         v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
       }
       const int k = (c0 + j) / 2;
-      if (writer) split2(v0, v1, hp[k], lp[k], ovf);
-      else hp[k] = lp[k] = 0u;
+      bad |= split2_packed(v0, v1, hp[k], lp[k]);
     }
   }
+  if (writer && bad) *ovf = 1;
   transpose_chunks<4>(hp, lane);
   transpose_chunks<4>(lp, lane);
   const uint32_t wmask = __ballot_sync(0xffffffffu, writer);
   const int r = lane & 3;
+  // the 4 pixels of this lane's group share a tile row; their output pixels differ only in the column
+  const int w4 = e.w0 + (lane & (kTW - 4));
+  const size_t row_pix = (size_t)e.out_off + ((size_t)e.n * e.OH + oh) * e.OW;
+  act_t* const row_hi = out_hi + row_pix * COUT + hsel * CH + r * 8;
+  act_t* const row_lo = out_lo + row_pix * COUT + hsel * CH + r * 8;
+  const uint32_t wm4 = wmask >> (lane & ~3);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int L = (lane & ~3) + q;  // the lane (pixel) whose chunk r this lane now holds
-    if ((wmask >> L) & 1u) {
-      const int hq = e.h0 + wq * kRowsPerWarp + L / kTW, wqx = e.w0 + L % kTW;
-      const size_t opix = (size_t)e.out_off + ((size_t)e.n * e.OH + hq / ph) * e.OW + wqx / pw;
-      *reinterpret_cast<uint4*>(out_hi + opix * COUT + hsel * CH + r * 8) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
-      *reinterpret_cast<uint4*>(out_lo + opix * COUT + hsel * CH + r * 8) = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+    if ((wm4 >> q) & 1u) {  // lane (lane & ~3) + q writes: this lane holds chunk r of its pixel
+      const int off = ((w4 + q) >> sw) * COUT;
+      *reinterpret_cast<uint4*>(row_hi + off) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+      *reinterpret_cast<uint4*>(row_lo + off) = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
     }
   }
 }
@@ -506,6 +525,260 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
       atomicAdd(dbg + 12, e_promo);
       atomicAdd(dbg + 13, e_xf);
       atomicAdd(dbg + 14, e_epi);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::kEpiWarps) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Small-layer form (C_in = KC: one channel chunk, all 9 weight tiles fit in shared memory): the 32 -> 64 layer.
+// The single-CTA kernel above streams 24 KB per k-block for 192 cycles of tensor work and sits at the L2 -> SM
+// delivery rate.  Here
+//   * the WEIGHTS are loaded once per CTA and stay resident (9 taps x (hi, lo) x C_out x KC x 2 B = 72 KB);
+//   * the activation is loaded as one 10-row box per horizontal tap kw (rows h0-1 .. h0+8) and the three vertical
+//     taps read it through descriptors advanced by whole tile rows, as in the CTA-pair + halo kernel below:
+//     60 KB per tile instead of 216 KB;
+//   * three hi*hi accumulators + one cross-term accumulator in tensor memory (see the halo kernel).
+// k-blocks run in (kw, kh) order; promotion groups stay 128 K-elements (4 k-blocks of 32 channels).
+// ------------------------------------------------------------------------------------------
+template <int KC_, int COUT>
+struct ResCfg {
+  static constexpr int kKC = KC_;
+  static constexpr int kABox = (kTH + 2) * kTW * kKC * 2;     // one plane of the 10 x 16 pixel box
+  static constexpr int kStageBytes = 2 * kABox;                // hi + lo
+  static constexpr int kStages = 4;
+  static constexpr int kBTile = COUT * kKC * 2;                // one plane of one tap's weights
+  static constexpr int kBBytes = 9 * 2 * kBTile;               // resident weights
+  static constexpr int kGroupKb = 128 / kKC;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 1024 + kBarBytes;
+  static constexpr int kTmemCols = 4 * COUT;
+  static constexpr int kEpiWarps = 4 * (COUT / 32);
+  static constexpr int kThreads = 32 * (kEpiWarps + 2);
+  static_assert(kABox % 1024 == 0 && kBTile % 1024 == 0, "operand tiles must keep the swizzle phase");
+  static_assert(kSmemBytes <= 227 * 1024, "resident weights do not fit");
+};
+
+template <int KC_, int COUT>
+__global__ void __launch_bounds__((ResCfg<KC_, COUT>::kThreads), 1)
+conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                   const CUtensorMap* __restrict__ maps, const RaggedDesc* __restrict__ groups, int n_groups, int n_tiles,
+                   int* __restrict__ counter, const float* __restrict__ bias, act_t* __restrict__ out_hi,
+                   act_t* __restrict__ out_lo, int Cin, int relu, int ph, int pw, float promo_scale, int* __restrict__ ovf) {
+  using C = ResCfg<KC_, COUT>;
+  constexpr int KC = C::kKC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t base = (smem0 + 1023u) & ~1023u;
+  const uint32_t bres = base + C::kStages * C::kStageBytes;      // resident weights: tap t at bres + t * 2 * kBTile (hi, lo)
+  const uint32_t bar_base = bres + C::kBBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  const uint32_t aux = bar_base + 8u * (2 * C::kStages);
+  auto hh_full = [&](int b) { return aux + 8u * b; };
+  auto hh_empty = [&](int b) { return aux + 8u * (3 + b); };
+  const uint32_t x_full = aux + 8u * 6, x_empty = aux + 8u * 7, b_full = aux + 8u * 8;
+  auto sched_full = [&](int s) { return aux + 8u * (9 + s); };
+  auto sched_empty = [&](int s) { return aux + 8u * (9 + kSched + s); };
+  const uint32_t tmem_slot = aux + 8u * (9 + 2 * kSched);
+  const uint32_t ring = tmem_slot + 8u + ((tmem_slot + 8u) & 8u);  // 16-byte aligned
+  static_assert(8 * (2 * C::kStages + 9 + 2 * kSched) + 24 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
+  TileEntry* ring_p = reinterpret_cast<TileEntry*>(smem_raw + (ring - smem0));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(hh_full(b), 1);
+      mbar_init(hh_empty(b), C::kEpiWarps);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, C::kEpiWarps);
+    mbar_init(b_full, 1);
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(sched_full(s), 1);
+      mbar_init(sched_empty(s), C::kEpiWarps + 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == C::kEpiWarps) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  constexpr int nkb = 9;  // Cin == KC
+  (void)Cin;
+
+  if (warp == C::kEpiWarps) {
+    if (lane == 0) {
+      // ---------------- weights once, then tile scheduler + TMA producer ----------------
+      mbar_expect_tx(b_full, C::kBBytes);
+      for (int t = 0; t < 9; ++t) {
+        tma_load_2d(bres + t * 2 * C::kBTile, &tm_w_hi, t * KC, 0, b_full);
+        tma_load_2d(bres + t * 2 * C::kBTile + C::kBTile, &tm_w_lo, t * KC, 0, b_full);
+      }
+      uint32_t stage = 0, par = 0;
+      int cur_g = 0, last_map_g = -1;
+      RaggedDesc gd = groups[0];
+      int t = atomicAdd(counter, 1);
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        mbar_wait(sched_empty(slot), ((ti / kSched) & 1) ^ 1);
+        TileEntry e;
+        e.g = -1;
+        e.n = e.h0 = e.w0 = e.H = e.W = e.OH = e.OW = 0;
+        e.out_off = 0;
+        e.pad = 0;
+        if (t < n_tiles) {
+          while (cur_g + 1 < n_groups && __ldg(&groups[cur_g + 1].first) <= t) {
+            ++cur_g;
+            gd = groups[cur_g];
+          }
+          int l = t - gd.first;
+          e.g = cur_g;
+          e.w0 = (l % gd.tiles_w) * kTW;
+          l /= gd.tiles_w;
+          e.h0 = (l % gd.tiles_h) * kTH;
+          e.n = l / gd.tiles_h;
+          e.H = gd.H; e.W = gd.W; e.OH = gd.OH; e.OW = gd.OW;
+          e.out_off = gd.out_off;
+        }
+        ring_p[slot] = e;
+        mbar_arrive(sched_full(slot));
+        if (e.g < 0) break;
+        const int t_next = atomicAdd(counter, 1);
+        const CUtensorMap* m_hi = maps + 2 * e.g;
+        const CUtensorMap* m_lo = m_hi + 1;
+        if (e.g != last_map_g) {
+          fence_tensormap_acquire(m_hi);
+          fence_tensormap_acquire(m_lo);
+          last_map_g = e.g;
+        }
+        for (int kw = 0; kw < 3; ++kw) {
+          mbar_wait(empty_bar(stage), par ^ 1);
+          const uint32_t st = base + stage * C::kStageBytes;
+          mbar_expect_tx(full_bar(stage), C::kStageBytes);
+          tma_load_4d(st, m_hi, 0, e.w0 + kw - 1, e.h0 - 1, e.n, full_bar(stage));
+          tma_load_4d(st + C::kABox, m_lo, 0, e.w0 + kw - 1, e.h0 - 1, e.n, full_bar(stage));
+          if (++stage == C::kStages) { stage = 0; par ^= 1; }
+        }
+        t = t_next;
+      }
+    }
+  } else if (warp == C::kEpiWarps + 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t stage = 0, par = 0, hb = 0, hpar = 0;
+      const uint32_t d_x = tmem_base + 3 * COUT;
+      mbar_wait(b_full, 0);
+      const uint64_t db_base = make_desc<KC>(bres);
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        mbar_wait(sched_full(slot), (ti / kSched) & 1);
+        int g;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(g) : "r"(ring + slot * (uint32_t)sizeof(TileEntry)) : "memory");
+        mbar_arrive(sched_empty(slot));
+        if (g < 0) break;
+        int kbi = 0;
+        for (int kw = 0; kw < 3; ++kw) {
+          mbar_wait(full_bar(stage), par);
+          tc_fence_after();
+          const uint64_t d0 = make_desc<KC>(base + stage * C::kStageBytes);
+#pragma unroll 1
+          for (int kh = 0; kh < 3; ++kh, ++kbi) {
+            const uint32_t d_hh = tmem_base + hb * COUT;
+            if ((kbi & (C::kGroupKb - 1)) == 0) {
+              mbar_wait(hh_empty(hb), hpar ^ 1);
+              tc_fence_after();
+            }
+            const uint64_t da0 = d0 + (uint64_t)((kh * kTW * KC * 2) >> 4);
+            const uint64_t db0 = db_base + (uint64_t)(((kh * 3 + kw) * 2 * C::kBTile) >> 4);
+            if (kbi == 0) {
+              // hi*hi of the first k-block goes out before the wait for the cross-term accumulator
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                umma_bf16(d_hh, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+              mbar_wait(x_empty, (ti & 1) ^ 1);
+              tc_fence_after();
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                const uint64_t da_hi = da0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABox >> 4);
+                const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(C::kBTile >> 4);
+                umma_bf16(d_x, da_hi, db_lo, idesc, k ? 1u : 0u);
+                umma_bf16(d_x, da_lo, db_hi, idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                const uint64_t da_hi = da0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABox >> 4);
+                const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(C::kBTile >> 4);
+                umma_bf16(d_hh, da_hi, db_hi, idesc, ((kbi & (C::kGroupKb - 1)) | k) ? 1u : 0u);
+                umma_bf16(d_x, da_hi, db_lo, idesc, 1u);
+                umma_bf16(d_x, da_lo, db_hi, idesc, 1u);
+              }
+            }
+            if ((kbi & (C::kGroupKb - 1)) == C::kGroupKb - 1 || kbi == nkb - 1) {
+              umma_commit(hh_full(hb));
+              if (++hb == 3) { hb = 0; hpar ^= 1; }
+            }
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == C::kStages) { stage = 0; par ^= 1; }
+        }
+        umma_commit(x_full);
+      }
+    }
+  } else {
+    // ---------------- promotion + epilogue ----------------
+    constexpr int CH = 32;
+    const int wq = warp & 3, hsel = warp >> 2;
+    const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + (uint32_t)(hsel * CH);
+    constexpr int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
+    uint32_t hb = 0, hpar = 0;
+    for (uint32_t ti = 0;; ++ti) {
+      const uint32_t slot = ti & (kSched - 1);
+      mbar_wait(sched_full(slot), (ti / kSched) & 1);
+      const TileEntry e = ring_p[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sched_empty(slot));
+      if (e.g < 0) break;
+      float acc[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+      for (int g = 0; g < ngroups; ++g) {
+        mbar_wait(hh_full(hb), hpar);
+        tc_fence_after();
+        {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_base + hb * COUT, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(r[j]), promo_scale, acc[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hh_empty(hb));
+        if (++hb == 3) { hb = 0; hpar ^= 1; }
+      }
+      mbar_wait(x_full, ti & 1);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + 3 * COUT, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_empty);
+      epilogue_store<COUT>(acc, e, wq, hsel, lane, relu, ph, pw, true, bias, out_hi, out_lo, ovf);
     }
   }
   __syncwarp();
@@ -868,6 +1141,355 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA pair + halo reuse.  Same pair protocol as conv3x3_pair_kernel; the operand pipeline is re-cut so that the
+// 3x3 window re-reads almost nothing from L2: per (64-channel chunk, horizontal tap kw) ONE box of 10 rows x 16
+// pixels of the activation is loaded (rows h0-1 .. h0+8) and the three vertical taps read it through descriptors
+// advanced by whole 16-pixel rows (2 KB = two swizzle atoms, so the 128-byte swizzle phase is unchanged), plus
+// this CTA's half of the three taps' weight tiles.  Per k-block and CTA: 30 KB of TMA traffic instead of 64 KB
+// (single CTA) / 48 KB (pair) -- below the L2 -> SM delivery rate that bounds the other two forms.
+// k-blocks run in (chunk, kw, kh) order, promotion groups are still 128 K-elements (2 or 4 k-blocks).
+// (KC = 32 works too -- 64-byte rows, SWIZZLE_64B, a tile row is 1 KB = two atoms -- but is not instantiated.)
+// ------------------------------------------------------------------------------------------
+template <int KC_, int COUT>
+struct HaloCfg {
+  static constexpr int kKC = KC_;
+  static constexpr int kABox = (kTH + 2) * kTW * kKC * 2;   // one plane of the 10 x 16 pixel box: 20 KB
+  static constexpr int kBHalf = (COUT / 2) * kKC * 2;        // one plane of this CTA's half of one tap's weights: 8 KB
+  static constexpr int kStageBytes = 2 * kABox + 3 * 2 * kBHalf;  // 88 KB for 64 x 128, 32 KB for 32 x 64
+  static constexpr int kStagesRaw = (180 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;
+  static constexpr int kGroupKb = 128 / kKC;     // k-blocks per promotion group (128 K-elements)
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
+  static constexpr int kTmemCols = 4 * COUT;
+  static constexpr int kEpiWarps = 4 * (COUT / 32);
+  static constexpr int kThreads = 32 * (kEpiWarps + 2);
+  static_assert(kABox % 1024 == 0 && kBHalf % 1024 == 0, "operand tiles must keep the swizzle phase");
+};
+
+template <int KC_, int COUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((HaloCfg<KC_, COUT>::kThreads), 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                    const CUtensorMap* __restrict__ maps, const RaggedDesc* __restrict__ groups, int n_groups, int n_tiles,
+                    int* __restrict__ counter, const float* __restrict__ bias, act_t* __restrict__ out_hi,
+                    act_t* __restrict__ out_lo, int Cin, int relu, int ph, int pw, float promo_scale, int* __restrict__ ovf,
+                    unsigned long long* __restrict__ dbg) {
+  using C = HaloCfg<KC_, COUT>;
+  constexpr int KC = C::kKC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t base = (smem0 + 1023u) & ~1023u;
+  const uint32_t bar_base = base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };       // the leader's are used
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  const uint32_t aux = bar_base + 8u * (2 * C::kStages);
+  // tensor memory: three hi*hi accumulators (a promotion group each) + ONE cross-term accumulator.  The third
+  // hi*hi buffer is what lets the MMA thread run 6 k-blocks ahead while the promotion warps are in the epilogue of
+  // the previous tile; the cross-term accumulator needs no double buffer because it is read out at the very start
+  // of the epilogue, and the next tile's first hi*hi MMAs are issued before the MMA thread waits for that.
+  auto hh_full = [&](int b) { return aux + 8u * b; };
+  auto hh_empty = [&](int b) { return aux + 8u * (3 + b); };      // the leader's are used
+  const uint32_t x_full = aux + 8u * 6;
+  const uint32_t x_empty = aux + 8u * 7;                          // the leader's is used
+  auto sched_full = [&](int s) { return aux + 8u * (8 + s); };
+  auto sched_empty = [&](int s) { return aux + 8u * (8 + kSched + s); };  // the leader's are used
+  const uint32_t tmem_slot = aux + 8u * (8 + 2 * kSched);
+  const uint32_t ring = tmem_slot + 16u;
+  static_assert(8 * (2 * 4 + 8 + 2 * kSched) + 16 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
+  TileEntry* ring_p = reinterpret_cast<TileEntry*>(smem_raw + (ring - smem0));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);   // leader: its producer arms; both CTAs' loads complete_tx on it
+      mbar_init(empty_bar(s), 1);  // one multicast commit
+    }
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(hh_full(b), 1);
+      mbar_init(hh_empty(b), 2 * C::kEpiWarps);  // leader: the promotion warps of both CTAs
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 2 * C::kEpiWarps);
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(sched_full(s), 1);
+      mbar_init(sched_empty(s), 2 * C::kEpiWarps + 2);  // leader: MMA thread + peer's TMA thread + all promotion warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == C::kEpiWarps) tmem_alloc2(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  cluster_sync_all();  // both CTAs' barriers and tensor memory exist before anything crosses the pair
+
+  const int chunks = Cin / KC;
+  const int nkb = 9 * chunks;
+  const int n_pairs = (n_tiles + 1) / 2;
+
+  if (warp == C::kEpiWarps) {
+    if (lane == 0) {
+      // ---------------- tile scheduler (leader) + TMA producer (both CTAs) ----------------
+      uint32_t stage = 0, par = 0;
+      int cur_g = 0, last_map_g = -1;
+      RaggedDesc gd = groups[0];
+      int pr = leader ? atomicAdd(counter, 1) : 0;
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        TileEntry e;
+        if (leader) {
+          mbar_wait_cluster_trap(sched_empty(slot), ((ti / kSched) & 1) ^ 1);
+          TileEntry ent[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            TileEntry& x = ent[k];
+            x.g = -1;
+            x.n = x.h0 = x.w0 = x.H = x.W = x.OH = x.OW = 0;
+            x.out_off = 0;
+            x.pad = 0;  // pad = 1: real tile, 0: dummy (the pair's second tile does not exist)
+            if (pr < n_pairs) {
+              const int t = min(2 * pr + k, n_tiles - 1);
+              while (cur_g + 1 < n_groups && __ldg(&groups[cur_g + 1].first) <= t) {
+                ++cur_g;
+                gd = groups[cur_g];
+              }
+              int l = t - gd.first;
+              x.g = cur_g;
+              x.w0 = (l % gd.tiles_w) * kTW;
+              l /= gd.tiles_w;
+              x.h0 = (l % gd.tiles_h) * kTH;
+              x.n = l / gd.tiles_h;
+              x.H = gd.H; x.W = gd.W; x.OH = gd.OH; x.OW = gd.OW;
+              x.out_off = gd.out_off;
+              x.pad = (2 * pr + k < n_tiles) ? 1 : 0;
+              if (!x.pad) x.n = gd.N;  // outside the tensor: TMA fills zeros
+            }
+          }
+          ring_p[slot] = ent[0];
+          // the peer's entry through DSMEM (three 16-byte stores), then release-arrive on both rings
+          const uint32_t peer_entry = mapa(ring + slot * (uint32_t)sizeof(TileEntry), 1);
+          const uint4* src = reinterpret_cast<const uint4*>(&ent[1]);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) st_cluster_v4(peer_entry + 16u * q, src[q]);
+          mbar_arrive_remote_release(mapa(sched_full(slot), 1));
+          mbar_arrive(sched_full(slot));
+          e = ent[0];
+        } else {
+          mbar_wait_cluster_trap(sched_full(slot), (ti / kSched) & 1);
+          e = ring_p[slot];
+          mbar_arrive_remote_release(mapa(sched_empty(slot), 0));
+        }
+        if (e.g < 0) break;
+        int pr_next = 0;
+        if (leader) pr_next = atomicAdd(counter, 1);  // in flight while this tile's loads are issued
+        const CUtensorMap* m_hi = maps + 2 * e.g;
+        const CUtensorMap* m_lo = m_hi + 1;
+        if (e.g != last_map_g) {
+          fence_tensormap_acquire(m_hi);
+          fence_tensormap_acquire(m_lo);
+          last_map_g = e.g;
+        }
+        // one stage per (channel chunk, horizontal tap): the 10-row box of the activation serves the three
+        // vertical taps (descriptor advanced by whole rows), plus this CTA's half of their three weight tiles
+        for (int c = 0; c < chunks; ++c) {
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait_trap(empty_bar(stage), par ^ 1);
+            const uint32_t st = base + stage * C::kStageBytes;
+            const uint32_t lead_full = mapa(full_bar(stage), 0);
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+            tma2_load_4d(st, m_hi, c * KC, e.w0 + kw - 1, e.h0 - 1, e.n, lead_full);
+            tma2_load_4d(st + C::kABox, m_lo, c * KC, e.w0 + kw - 1, e.h0 - 1, e.n, lead_full);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint32_t bt = st + 2 * C::kABox + kh * 2 * C::kBHalf;
+              tma2_load_2d(bt, &tm_w_hi, (kh * 3 + kw) * Cin + c * KC, (int)crank * (COUT / 2), lead_full);
+              tma2_load_2d(bt + C::kBHalf, &tm_w_lo, (kh * 3 + kw) * Cin + c * KC, (int)crank * (COUT / 2), lead_full);
+            }
+            if (++stage == C::kStages) { stage = 0; par ^= 1; }
+          }
+        }
+        pr = pr_next;
+      }
+    }
+  } else if (warp == C::kEpiWarps + 1) {
+    if (lane == 0 && leader) {
+      // ---------------- MMA issuer (leader only) ----------------
+      // c_format F32 (bit 4), a/b format F16, N >> 3 at 17, M >> 4 at 24 with M = 256 over the pair
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((256u >> 4) << 24);
+      uint32_t stage = 0, par = 0, hb = 0, hpar = 0;  // hb: hi*hi buffer of the current group, hpar: its use parity
+      const uint32_t d_x = tmem_base + 3 * COUT;
+      unsigned long long c_sched = 0, c_xe = 0, c_hhe = 0, c_full = 0, c_iss = 0, n_tiles_done = 0;
+      const bool timing = dbg != nullptr;
+      const long long t_begin = timing ? clock64() : 0;
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        long long c0 = timing ? clock64() : 0;
+        mbar_wait_trap(sched_full(slot), (ti / kSched) & 1);
+        int g;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(g) : "r"(ring + slot * (uint32_t)sizeof(TileEntry)) : "memory");
+        mbar_arrive(sched_empty(slot));
+        if (g < 0) break;
+        if (timing) c_sched += (unsigned long long)(clock64() - c0);
+        int kbi = 0;  // k-block of the tile, in (chunk, kw, kh) order; promotion groups = kGroupKb k-blocks
+        for (int sidx = 0; sidx < 3 * chunks; ++sidx) {
+          long long w0 = timing ? clock64() : 0;
+          mbar_wait_cluster_trap(full_bar(stage), par);
+          tc_fence_after();
+          if (timing) c_full += (unsigned long long)(clock64() - w0);
+          const uint64_t d0 = make_desc<KC>(base + stage * C::kStageBytes);
+#pragma unroll 1
+          for (int kh = 0; kh < 3; ++kh, ++kbi) {
+            const uint32_t d_hh = tmem_base + hb * COUT;
+            if ((kbi & (C::kGroupKb - 1)) == 0) {
+              long long g0 = timing ? clock64() : 0;
+              mbar_wait_cluster_trap(hh_empty(hb), hpar ^ 1);
+              tc_fence_after();
+              if (timing) c_hhe += (unsigned long long)(clock64() - g0);
+            }
+            long long g1 = timing ? clock64() : 0;
+            // A: rows kh .. kh+7 of the 10-row box (16 pixels x 128 B per row); B: the tap's weight half
+            const uint64_t da0 = d0 + (uint64_t)((kh * kTW * KC * 2) >> 4);
+            const uint64_t db0 = d0 + (uint64_t)((2 * C::kABox + kh * 2 * C::kBHalf) >> 4);
+            if (kbi == 0) {
+              // first k-block of a tile: the hi*hi MMAs go out before the wait for the cross-term accumulator
+              // (the promotion warps read the previous tile's out of it right after that tile's last commit)
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                umma2_f16(d_hh, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+              long long x0 = timing ? clock64() : 0;
+              mbar_wait_cluster_trap(x_empty, (ti & 1) ^ 1);
+              tc_fence_after();
+              if (timing) {
+                const unsigned long long xw = (unsigned long long)(clock64() - x0);
+                c_xe += xw;
+                c_iss -= xw;  // the enclosing issue interval contains this wait
+              }
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                const uint64_t da_hi = da0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABox >> 4);
+                const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(C::kBHalf >> 4);
+                umma2_f16(d_x, da_hi, db_lo, idesc, k ? 1u : 0u);
+                umma2_f16(d_x, da_lo, db_hi, idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                const uint64_t da_hi = da0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABox >> 4);
+                const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(C::kBHalf >> 4);
+                umma2_f16(d_hh, da_hi, db_hi, idesc, ((kbi & (C::kGroupKb - 1)) | k) ? 1u : 0u);
+                umma2_f16(d_x, da_hi, db_lo, idesc, 1u);
+                umma2_f16(d_x, da_lo, db_hi, idesc, 1u);
+              }
+            }
+            if ((kbi & (C::kGroupKb - 1)) == C::kGroupKb - 1 || kbi == nkb - 1) {
+              umma2_commit_mc(hh_full(hb), 3);
+              if (++hb == 3) { hb = 0; hpar ^= 1; }
+            }
+            if (timing) c_iss += (unsigned long long)(clock64() - g1);
+          }
+          umma2_commit_mc(empty_bar(stage), 3);
+          if (++stage == C::kStages) { stage = 0; par ^= 1; }
+        }
+        umma2_commit_mc(x_full, 3);
+        ++n_tiles_done;
+      }
+      if (timing) {
+        atomicAdd(dbg + 0, 2 * n_tiles_done);
+        atomicAdd(dbg + 1, n_tiles_done * (unsigned long long)nkb);
+        atomicAdd(dbg + 2, c_sched);
+        atomicAdd(dbg + 3, c_xe);
+        atomicAdd(dbg + 4, c_hhe);
+        atomicAdd(dbg + 5, c_full);
+        atomicAdd(dbg + 6, c_iss);
+        atomicAdd(dbg + 7, 0ull);
+        atomicAdd(dbg + 8, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(dbg + 9, 1ull);
+      }
+    }
+  } else {
+    // ---------------- promotion + epilogue (both CTAs, own tensor memory) ----------------
+    constexpr int CH = 32;
+    const int wq = warp & 3, hsel = warp >> 2;
+    const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + (uint32_t)(hsel * CH);
+    const int ngroups = (nkb + C::kGroupKb - 1) / C::kGroupKb;
+    uint32_t hb = 0, hpar = 0;
+    const bool etime = dbg != nullptr && warp == 0 && lane == 0;  // promotion warp 0 of every CTA
+    unsigned long long e_ring = 0, e_hhf = 0, e_promo = 0, e_xf = 0, e_epi = 0, e_tiles = 0;
+    for (uint32_t ti = 0;; ++ti) {
+      const uint32_t slot = ti & (kSched - 1);
+      long long q0 = etime ? clock64() : 0;
+      mbar_wait_cluster_trap(sched_full(slot), (ti / kSched) & 1);
+      if (etime) e_ring += (unsigned long long)(clock64() - q0);
+      const TileEntry e = ring_p[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_release(mapa(sched_empty(slot), 0));
+      if (e.g < 0) break;
+      const bool real_tile = e.pad != 0;
+      float acc[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+      for (int g = 0; g < ngroups; ++g) {
+        long long q1 = etime ? clock64() : 0;
+        mbar_wait_trap(hh_full(hb), hpar);
+        tc_fence_after();
+        long long q2 = etime ? clock64() : 0;
+        {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_base + hb * COUT, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(r[j]), promo_scale, acc[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(mapa(hh_empty(hb), 0));  // no data handed over: the TMEM reads are done
+        if (++hb == 3) { hb = 0; hpar ^= 1; }
+        if (etime) {
+          e_hhf += (unsigned long long)(q2 - q1);
+          e_promo += (unsigned long long)(clock64() - q2);
+        }
+      }
+      long long q3 = etime ? clock64() : 0;
+      mbar_wait_trap(x_full, ti & 1);
+      tc_fence_after();
+      long long q4 = etime ? clock64() : 0;
+      {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + 3 * COUT, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_relaxed(mapa(x_empty, 0));
+
+      epilogue_store<COUT>(acc, e, wq, hsel, lane, relu, ph, pw, real_tile, bias, out_hi, out_lo, ovf);
+      if (etime) {
+        e_xf += (unsigned long long)(q4 - q3);
+        e_epi += (unsigned long long)(clock64() - q4);
+        ++e_tiles;
+      }
+    }
+    if (etime) {
+      atomicAdd(dbg + 10, e_ring);
+      atomicAdd(dbg + 11, e_hhf);
+      atomicAdd(dbg + 12, e_promo);
+      atomicAdd(dbg + 13, e_xf);
+      atomicAdd(dbg + 14, e_epi);
+      atomicAdd(dbg + 15, e_tiles);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still read this CTA's operands / signal its barriers
+  if (warp == C::kEpiWarps) tmem_dealloc2(tmem_base, C::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
 // layout converters / pooling (bandwidth-bound helpers)
 // ------------------------------------------------------------------------------------------
 
@@ -1030,6 +1652,7 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const fl
 #pragma unroll 1
   for (int c8 = 0; c8 < COUT; c8 += 8) {
     uint32_t ph[4], pl[4];
+    float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float* k = sw + (c8 + j) * 9;
@@ -1045,17 +1668,12 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const fl
             for (int s = 0; s < 3; ++s) a = fmaf(p[dy + r][dx + s], k[r * 3 + s], a);
           best = fmaxf(best, a);
         }
-      const float v = fmaxf(best + sw[COUT * 9 + c8 + j], 0.f);
-      uint16_t hi, lo;
-      split1(v, hi, lo, ovf);
-      if (j & 1) {
-        ph[j / 2] |= (uint32_t)hi << 16;
-        pl[j / 2] |= (uint32_t)lo << 16;
-      } else {
-        ph[j / 2] = (uint32_t)hi;
-        pl[j / 2] = (uint32_t)lo;
-      }
+      v[j] = fmaxf(best + sw[COUT * 9 + c8 + j], 0.f);
     }
+    uint32_t bad = 0u;  // packed conversions (two values per F2FP) instead of scalar F2F at a quarter of the rate
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bad |= split2_packed(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+    if (bad) *ovf = 1;
     *reinterpret_cast<uint4*>(oh_ptr + c8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     *reinterpret_cast<uint4*>(ol_ptr + c8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
@@ -1099,22 +1717,44 @@ bool conv_debug() {
   return on;
 }
 
-bool conv_pair_enabled() {
-  static const bool on = [] { const char* e = std::getenv("OCRS_B200_CONV_PAIR"); return e != nullptr && e[0] == '1'; }();
-  return on;
+// 128-channel layers: 0 = single-CTA kernel, 1 = CTA pair, 2 (default) = CTA pair + halo reuse (its activation
+// maps have a 10-row box).  OCRS_B200_CONV_MODE selects; the other layers always run the single-CTA kernel.
+int conv_mode() {
+  static const int m = [] {
+    const char* e = std::getenv("OCRS_B200_CONV_MODE");
+    if (e != nullptr) return std::atoi(e);
+    const char* p = std::getenv("OCRS_B200_CONV_PAIR");
+    return (p != nullptr && p[0] == '1') ? 1 : 2;
+  }();
+  return m;
 }
 
-template <int COUT>
+
+template <int KC, int COUT, bool HALO>
+struct PairSel {
+  using Cfg = PairCfg<COUT>;
+  static auto kernel() { return conv3x3_pair_kernel<COUT>; }
+};
+template <int KC, int COUT>
+struct PairSel<KC, COUT, true> {
+  using Cfg = HaloCfg<KC, COUT>;
+  static auto kernel() { return conv3x3_halo_kernel<KC, COUT>; }
+};
+
+template <int KC, int COUT, bool HALO>
 void launch_conv_pair(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
                       const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
-  using C = PairCfg<COUT>;
+  using C = typename PairSel<KC, COUT, HALO>::Cfg;
+  static_assert(HALO || KC == 64, "the plain CTA-pair kernel is built for 64-channel k-blocks");
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const int Cin = w.Cin;
   uint64_t wd[2] = {(uint64_t)9 * Cin, (uint64_t)COUT};
   uint64_t ws[1] = {(uint64_t)9 * Cin * 2};
   uint32_t wb[2] = {(uint32_t)C::kKC, (uint32_t)(COUT / 2)};  // each CTA loads its half of the output channels
-  CUtensorMap tm_w_hi = make_map(w.w_hi.ptr, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap tm_w_lo = make_map(w.w_lo.ptr, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
-  OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_pair_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  CUtensorMap tm_w_hi = make_map(w.w_hi.ptr, 2, wd, ws, wb, swz);
+  CUtensorMap tm_w_lo = make_map(w.w_lo.ptr, 2, wd, ws, wb, swz);
+  auto kern = PairSel<KC, COUT, HALO>::kernel();
+  OCRS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   const int n_pairs = (n_tiles + 1) / 2;
   const int grid = 2 * std::max(1, std::min(n_pairs, sm_count() / 2));
   unsigned long long* d_dbg = nullptr;
@@ -1122,9 +1762,8 @@ void launch_conv_pair(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int
     OCRS_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_dbg), 16 * sizeof(unsigned long long), st));
     OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 16 * sizeof(unsigned long long), st));
   }
-  conv3x3_pair_kernel<COUT><<<grid, C::kThreads, C::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles,
-                                                                       d_counter, w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph,
-                                                                       pw, promo_scale(), ovf, d_dbg);
+  kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles, d_counter,
+                                                  w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph, pw, promo_scale(), ovf, d_dbg);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
   if (d_dbg) {
@@ -1134,10 +1773,37 @@ void launch_conv_pair(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int
     OCRS_CUDA_CHECK(cudaFreeAsync(d_dbg, st));
     const double kb = (double)std::max<unsigned long long>(h[1], 1), cl = (double)std::max<unsigned long long>(h[9], 1);
     fprintf(stderr,
-            "[conv dbg PAIR] Cin %d Cout %d pool %dx%d: %llu tiles, %d groups, %.0f clusters | per k-block of M=256 (cycles): ring %.0f, "
-            "x_empty %.0f, hh_empty %.0f, operands %.0f, issue %.0f | loop total %.0f (per cluster %.0f cycles)\n",
-            Cin, COUT, ph, pw, h[0], n_groups, cl, h[2] / kb, h[3] / kb, h[4] / kb, h[5] / kb, h[6] / kb, h[8] / kb, h[8] / cl);
+            "[conv dbg PAIR%s] Cin %d Cout %d pool %dx%d: %llu tiles, %d groups, %.0f clusters | per k-block of M=256 (cycles): ring %.0f, "
+            "x_empty %.0f, hh_empty %.0f, operands %.0f, issue %.0f | loop total %.0f (per cluster %.0f cycles)",
+            HALO ? "+HALO" : "", Cin, COUT, ph, pw, h[0], n_groups, cl, h[2] / kb, h[3] / kb, h[4] / kb, h[5] / kb, h[6] / kb, h[8] / kb,
+            h[8] / cl);
+    if (h[15]) {
+      const double tl = (double)h[15];
+      fprintf(stderr, " | promotion warp 0 of every CTA, per TILE: ring %.0f, wait hh_full %.0f, promote %.0f, wait x_full %.0f, X + epilogue %.0f",
+              h[10] / tl, h[11] / tl, h[12] / tl, h[13] / tl, h[14] / tl);
+    }
+    fprintf(stderr, "\n");
   }
+}
+
+template <int KC, int COUT>
+void launch_conv_res(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
+                     const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
+  using C = ResCfg<KC, COUT>;
+  const int Cin = w.Cin;
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  uint64_t wd[2] = {(uint64_t)9 * Cin, (uint64_t)COUT};
+  uint64_t ws[1] = {(uint64_t)9 * Cin * 2};
+  uint32_t wb[2] = {(uint32_t)KC, (uint32_t)COUT};
+  CUtensorMap tm_w_hi = make_map(w.w_hi.ptr, 2, wd, ws, wb, swz);
+  CUtensorMap tm_w_lo = make_map(w.w_lo.ptr, 2, wd, ws, wb, swz);
+  OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_res_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  const int grid = std::max(1, std::min(n_tiles, sm_count()));
+  conv3x3_res_kernel<KC, COUT><<<grid, C::kThreads, C::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles, d_counter,
+                                                                         w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph, pw, promo_scale(),
+                                                                         ovf);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
 }
 
 template <int KC, int COUT>
@@ -1289,12 +1955,24 @@ void conv_fill_tiles(RaggedDesc* d) {
   d->tiles_h = (int)ceil_div(d->H, kTH);
 }
 
-void make_act_maps(const act_t* hi, const act_t* lo, int N, int H, int W, int Cin, CUtensorMap out[2]) {
+// the layers the CTA-pair + halo kernel runs: the 128-channel ones.  (Instantiated for the 32 -> 64 layer it was no
+// faster per SM, and with three batches in flight the benchmark stopped making progress, cause not found:
+// profiles/r02n_halo32.md.  That layer runs the resident-weights kernel instead.)
+bool conv_uses_halo(int Cin, int Cout) { return conv_mode() == 2 && Cin % 64 == 0 && Cout == 128; }
+// the 32 -> 64 layer: resident weights + 10-row activation boxes (OCRS_B200_CONV_RES=0: the streaming kernel)
+bool conv_uses_res(int Cin, int Cout) {
+  static const bool on = [] { const char* e = std::getenv("OCRS_B200_CONV_RES"); return e == nullptr || e[0] != '0'; }();
+  return on && Cin == 32 && Cout == 64;
+}
+
+void make_act_maps(const act_t* hi, const act_t* lo, int N, int H, int W, int Cin, CUtensorMap out[2], int Cout) {
   const int KC = (Cin % 64 == 0) ? 64 : 32;
   const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-  uint32_t xb[4] = {(uint32_t)KC, (uint32_t)kTW, (uint32_t)kTH, 1};
+  // the halo kernel loads 10-row boxes (rows h0-1 .. h0+8), the others 8-row boxes per tap
+  const bool halo = conv_uses_halo(Cin, Cout) || conv_uses_res(Cin, Cout);
+  uint32_t xb[4] = {(uint32_t)KC, (uint32_t)kTW, (uint32_t)(halo ? kTH + 2 : kTH), 1};
   out[0] = make_map(hi, 4, xd, xs, xb, swz);
   out[1] = make_map(lo, 4, xd, xs, xb, swz);
 }
@@ -1304,8 +1982,16 @@ void conv3x3_ragged(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n
   if (n_tiles == 0 || n_groups == 0) return;
   OCRS_CHECK((ph == 1 || ph == 2) && (pw == 1 || pw == 2), kInternal, "conv3x3 (tensor core): fused pool must be 1 or 2");
   const bool k64 = (w.Cin % 64 == 0);
-  if (k64 && w.Cout == 128 && conv_pair_enabled()) {
-    launch_conv_pair<128>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+  if (conv_uses_res(w.Cin, w.Cout)) {
+    launch_conv_res<32, 64>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+    return;
+  }
+  if (conv_uses_halo(w.Cin, w.Cout)) {
+    launch_conv_pair<64, 128, true>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
+    return;
+  }
+  if (k64 && w.Cout == 128 && conv_mode() == 1) {
+    launch_conv_pair<64, 128, false>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
     return;
   }
   if (k64 && w.Cout == 128) launch_conv<64, 128>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
@@ -1320,7 +2006,7 @@ void conv3x3(const act_t* x_hi, const act_t* x_lo, const ConvWeightsTC& w, act_t
   if (N == 0 || H == 0 || W == 0) return;
   // one-group ragged launch: [maps hi, lo | desc | counter] in one stream-ordered blob
   struct Blob { CUtensorMap maps[2]; RaggedDesc d; int counter; int pad[3]; } blob;
-  make_act_maps(x_hi, x_lo, N, H, W, w.Cin, blob.maps);
+  make_act_maps(x_hi, x_lo, N, H, W, w.Cin, blob.maps, w.Cout);
   blob.d = RaggedDesc{};
   blob.d.N = N; blob.d.H = H; blob.d.W = W; blob.d.OH = H / ph; blob.d.OW = W / pw;
   conv_fill_tiles(&blob.d);

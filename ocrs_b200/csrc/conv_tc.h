@@ -78,7 +78,9 @@ static_assert(sizeof(RaggedDesc) == 48, "RaggedDesc layout");
 int conv_tiles(int N, int H, int W);      // tiles of one group in a conv launch
 void conv_fill_tiles(RaggedDesc* d);      // sets tiles_w / tiles_h from H / W
 // TMA tensor maps {hi, lo} of a group's NHWC input [N,H,W,Cin] (host side; copy them to the device array).
-void make_act_maps(const act_t* hi, const act_t* lo, int N, int H, int W, int Cin, CUtensorMap out[2]);
+// `Cout` of the consuming layer selects the box shape (the CTA-pair + halo kernel of the 128-channel layers,
+// OCRS_B200_CONV_MODE=2, loads 10-row boxes).
+void make_act_maps(const act_t* hi, const act_t* lo, int N, int H, int W, int Cin, CUtensorMap out[2], int Cout = 0);
 // d_maps: device [2 * n_groups]; d_counter: device int, zero before the launch (tile scheduler).
 void conv3x3_ragged(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
                     const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st);

@@ -410,7 +410,7 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
       rs_bytes += 4.0 * ((double)in.H * in.W + (double)plane);
       OCRS_CHECK(in.device == device_, kInvalidArg, "input lives on another device");
       int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
-      tab[i] = img::PageResizeIn{in.grey(), in.H, in.W, in.H + pb, in.W + pr};
+      tab[i] = img::PageResizeIn{in.grey(), in.H, in.W, in.H + pb, in.W + pr, img::resize_scale(in.H + pb, in_h), img::resize_scale(in.W + pr, in_w)};
     }
     tab_in_.reserve(tab.size() * sizeof(img::PageResizeIn));
     OCRS_CUDA_CHECK(cudaMemcpyAsync(tab_in_.ptr, tab.data(), tab.size() * sizeof(img::PageResizeIn), cudaMemcpyHostToDevice, st_));
@@ -436,7 +436,8 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
       const OcrInput& in = *pages[i];
       PageScratch& s = scratch_for(i, in.H, in.W);
       int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
-      tab[i] = img::PageResizeOut{out.data + i * plane, nullptr, s.mask.as<uint8_t>(), s.bits.as<uint32_t>(), in_h - pb, in_w - pr, in.H, in.W};
+      tab[i] = img::PageResizeOut{out.data + i * plane, nullptr, s.mask.as<uint8_t>(), s.bits.as<uint32_t>(), in_h - pb, in_w - pr, in.H, in.W,
+                                   img::resize_scale(in_h - pb, in.H), img::resize_scale(in_w - pr, in.W)};
       max_h = std::max(max_h, in.H);
       max_w = std::max(max_w, in.W);
       rt_bytes += 4.0 * (in_h - pb) * (in_w - pr) + (double)in.H * in.W;
@@ -933,7 +934,7 @@ std::vector<Engine::TextPixels> Engine::detect_text_pixels_batch(const std::vect
       const OcrInput& in = *pages[i];
       OCRS_CHECK(in.device == device_, kInvalidArg, "input lives on another device");
       int pb = std::max(in_h - in.H, 0), pr = std::max(in_w - in.W, 0);
-      tab[i] = img::PageResizeIn{in.grey(), in.H, in.W, in.H + pb, in.W + pr};
+      tab[i] = img::PageResizeIn{in.grey(), in.H, in.W, in.H + pb, in.W + pr, img::resize_scale(in.H + pb, in_h), img::resize_scale(in.W + pr, in_w)};
     }
     tab_in_.reserve(tab.size() * sizeof(img::PageResizeIn));
     OCRS_CUDA_CHECK(cudaMemcpyAsync(tab_in_.ptr, tab.data(), tab.size() * sizeof(img::PageResizeIn), cudaMemcpyHostToDevice, st_));

@@ -1500,7 +1500,8 @@ DTensor Model::run_prefix_packed(const std::vector<PrefixGroup>& groups, int in_
     OCRS_CHECK(Cin == layer_c[(size_t)u], kRunFailed, "Conv: channel mismatch");
     for (int g = 0; g < G; ++g) {
       const tc::RaggedDesc& d = descs[(size_t)(u + 1) * G + g];
-      tc::make_act_maps(hi_of(u) + d.in_off * Cin, lo_of(u) + d.in_off * Cin, d.N, d.H, d.W, Cin, hmaps + ((size_t)u * G + g) * 2);
+      tc::make_act_maps(hi_of(u) + d.in_off * Cin, lo_of(u) + d.in_off * Cin, d.N, d.H, d.W, Cin, hmaps + ((size_t)u * G + g) * 2,
+                        ch.units[(size_t)u].w->Cout);
     }
   }
   auto blob_dev = std::make_shared<Storage>(blob.size() + 128, st);

@@ -45,103 +45,165 @@ __global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restr
 
 // ------------------------------------------------------------------------------------------
 // C[M, Ntot] (f32) = A[M, K] * B[Ntot, K]^T + bias[Ntot]; A, B split bf16, K-major.
-// Tile 128 x 128, K chunks of 32 (64-byte-swizzled rows), 3 stages of 32 KB: ~98 KB of shared memory and 128
-// TMEM columns per CTA, so TWO CTAs share an SM -- the kernel is a short main loop (K = 128 or 512) between a
-// prologue and an epilogue that nothing else overlaps, and a second resident CTA hides them.
+// Persistent, warp-specialised: one CTA per SM walks 128 x 128 tiles (the N tiles of one M tile are adjacent in
+// the walk, so the A rows come from DRAM once and from L2 for the other N tiles).
+//   warp 0   TMA producer: K chunks of 32 (64-byte-swizzled rows), 5 stages of 32 KB;
+//   warp 1   MMA issuer: hi*hi + hi*lo + lo*hi into one of TWO tensor-memory accumulators (128 columns each), so
+//            the MMAs of tile i+1 run while tile i is drained;
+//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time, + bias, through a 128B-swizzled shared-memory staging
+//            tile so that every global store instruction writes whole 128-byte lines (a thread owns a ROW of the
+//            accumulator; storing straight from registers writes 16-byte pieces 6 KB apart).
+// (The first form -- one tile per CTA, two CTAs per SM, the same four warps loading, issuing and storing in turn --
+// ran the layer-1 / layer-2 input projections at 20% / 47% of the tensor peak: profiles/r02i_batch_ncu_table.md.)
 // ------------------------------------------------------------------------------------------
-constexpr int kGemmStages = 3;
+// persistent grid: one CTA per SM of the current device
+inline int gemm_ctas() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  OCRS_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    OCRS_CUDA_CHECK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+constexpr int kGemmStages = 5;
 constexpr int kGemmBK = 32;
 constexpr int kGemmTile = 128 * kGemmBK * 2;            // one operand plane of one stage (8 KB)
 constexpr int kGemmStageBytes = 4 * kGemmTile;          // A_hi, A_lo, B_hi, B_lo
-constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + 1024 + 256;
+constexpr int kGemmEpiWarps = 4;
+constexpr int kGemmStagingBytes = 32 * 128;             // per epilogue warp: 32 rows x 32 floats
+constexpr int kGemmThreads = 32 * (2 + kGemmEpiWarps);
+constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + kGemmEpiWarps * kGemmStagingBytes + 1024 + 256;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const float* __restrict__ bias, float* __restrict__ Cout, int M, int Ntot, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + kGemmStages * kGemmStageBytes;
+  const uint32_t staging0 = base + kGemmStages * kGemmStageBytes;
+  const uint32_t bar_base = staging0 + kGemmEpiWarps * kGemmStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kGemmStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kGemmStages);
-  const uint32_t tmem_slot = tmem_full_bar + 8u;
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * kGemmStages + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * kGemmStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kGemmStages + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGemmStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), kGemmEpiWarps);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const int nkb = K / kGemmBK;
+  const int n_tiles_n = Ntot / 128;
+  const int n_tiles = ((M + 127) / 128) * n_tiles_n;
 
-  if (warp == 0 && lane == 0) {
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kGemmStages;
-      const uint32_t ph = (kb / kGemmStages) & 1;
-      mbar_wait(empty_bar(s), ph ^ 1);
-      const uint32_t st = base + s * kGemmStageBytes;
-      mbar_expect_tx(full_bar(s), kGemmStageBytes);
-      tma_load_2d(st, &tm_a_hi, kb * kGemmBK, m0, full_bar(s));
-      tma_load_2d(st + kGemmTile, &tm_a_lo, kb * kGemmBK, m0, full_bar(s));
-      tma_load_2d(st + 2 * kGemmTile, &tm_b_hi, kb * kGemmBK, n0, full_bar(s));
-      tma_load_2d(st + 3 * kGemmTile, &tm_b_lo, kb * kGemmBK, n0, full_bar(s));
-    }
-  } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kGemmStages;
-      const uint32_t ph = (kb / kGemmStages) & 1;
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      const uint32_t st = base + s * kGemmStageBytes;
-#pragma unroll
-      for (int k = 0; k < kGemmBK / 16; ++k) {
-        const uint32_t koff = k * 32;
-        const uint64_t da_hi = make_desc<32>(st + koff), da_lo = make_desc<32>(st + kGemmTile + koff);
-        const uint64_t db_hi = make_desc<32>(st + 2 * kGemmTile + koff), db_lo = make_desc<32>(st + 3 * kGemmTile + koff);
-        umma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
-        umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
-        umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles_n) * 128, n0 = (t % n_tiles_n) * 128;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t st = base + s * kGemmStageBytes;
+          mbar_expect_tx(full_bar(s), kGemmStageBytes);
+          tma_load_2d(st, &tm_a_hi, kb * kGemmBK, m0, full_bar(s));
+          tma_load_2d(st + kGemmTile, &tm_a_lo, kb * kGemmBK, m0, full_bar(s));
+          tma_load_2d(st + 2 * kGemmTile, &tm_b_hi, kb * kGemmBK, n0, full_bar(s));
+          tma_load_2d(st + 3 * kGemmTile, &tm_b_lo, kb * kGemmBK, n0, full_bar(s));
+          if (++s == kGemmStages) { s = 0; ph ^= 1; }
+        }
       }
-      umma_commit(empty_bar(s));
     }
-    umma_commit(tmem_full_bar);
-  }
-  __syncwarp();
-  mbar_wait(tmem_full_bar, 0);
-  tc_fence_after();
-  const int row = m0 + warp * 32 + lane;
-#pragma unroll 1
-  for (int c0 = 0; c0 < 128; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-    if (row < M) {
-      float4* dst = reinterpret_cast<float4*>(Cout + (size_t)row * Ntot + n0 + c0);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t s = 0, ph = 0, it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const uint32_t a = it & 1;
+        mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + a * 128;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t st = base + s * kGemmStageBytes;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 v;
-        v.x = __uint_as_float(r[4 * q]) + bias[n0 + c0 + 4 * q];
-        v.y = __uint_as_float(r[4 * q + 1]) + bias[n0 + c0 + 4 * q + 1];
-        v.z = __uint_as_float(r[4 * q + 2]) + bias[n0 + c0 + 4 * q + 2];
-        v.w = __uint_as_float(r[4 * q + 3]) + bias[n0 + c0 + 4 * q + 3];
-        dst[q] = v;
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            const uint32_t koff = k * 32;
+            const uint64_t da_hi = make_desc<32>(st + koff), da_lo = make_desc<32>(st + kGemmTile + koff);
+            const uint64_t db_hi = make_desc<32>(st + 2 * kGemmTile + koff), db_lo = make_desc<32>(st + 3 * kGemmTile + koff);
+            umma_bf16(d, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(d, da_hi, db_lo, idesc, 1u);
+            umma_bf16(d, da_lo, db_hi, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
+          if (++s == kGemmStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(acc_full(a));
+      }
+    }
+  } else {
+    // epilogue warp: TMEM lane quadrant q = warp % 4 (rows 32q .. 32q+31 of the tile)
+    const int q = warp & 3;
+    const uint32_t stg = staging0 + (uint32_t)(warp - 2) * kGemmStagingBytes;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int m0 = (t / n_tiles_n) * 128, n0 = (t % n_tiles_n) * 128;
+      const uint32_t a = it & 1;
+      mbar_wait(acc_full(a), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 128 + (uint32_t)c0, r);
+        if (c0 == 96) {  // the accumulator is in registers: hand it back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(a));
+        }
+        // row `lane` of the warp's 32 x 32 block -> staging, 16-byte chunk c at (c ^ (lane & 7))
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + 4 * c));
+          const float4 v = make_float4(__uint_as_float(r[4 * c]) + b4.x, __uint_as_float(r[4 * c + 1]) + b4.y,
+                                       __uint_as_float(r[4 * c + 2]) + b4.z, __uint_as_float(r[4 * c + 3]) + b4.w);
+          const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+        __syncwarp();
+        // 8 lanes per row, 4 rows per instruction: every row segment is one full 128-byte line
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3), c = lane & 7;
+          const uint32_t addr = stg + (uint32_t)rr * 128u + (uint32_t)((c ^ (rr & 7)) << 4);
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+          const int row = m0 + q * 32 + rr;
+          if (row < M) *reinterpret_cast<float4*>(Cout + (size_t)row * Ntot + n0 + c0 + 4 * c) = v;
+        }
+        __syncwarp();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -789,8 +851,8 @@ void gemm_split_bf16(const float* X, int64_t M, int K, const void* w_hi, const v
   CUtensorMap tb_hi = make_map(w_hi, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
   CUtensorMap tb_lo = make_map(w_lo, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
   OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-  dim3 grid((unsigned)ceil_div(M, 128), (unsigned)(Ntot / 128));
-  gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, bias, out, (int)M, Ntot, K);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(M, 128) * (Ntot / 128), gemm_ctas()));
+  gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, bias, out, (int)M, Ntot, K);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -847,8 +909,8 @@ void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* 
     CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
     CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
     OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)(Ntot / 128));
-    gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)M, Ntot, I);
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(M, 128) * (Ntot / 128), gemm_ctas()));
+    gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)M, Ntot, I);
     count_launch();
   }
   // (3) recurrence
@@ -892,8 +954,8 @@ void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, cons
     CUtensorMap tb_hi = make_map(w.w_hi.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
     CUtensorMap tb_lo = make_map(w.w_lo.ptr, 2, bd, as, box, CU_TENSOR_MAP_SWIZZLE_64B);
     OCRS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-    dim3 grid((unsigned)ceil_div(rows, 128), (unsigned)(Ntot / 128));
-    gemm_tc_kernel<<<grid, 128, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)rows, Ntot, I);
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(rows, 128) * (Ntot / 128), gemm_ctas()));
+    gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)rows, Ntot, I);
     count_launch();
   }
   const int n_tiles = (int)ceil_div(n_lines, NL);

@@ -72,6 +72,16 @@ __device__ __forceinline__ AxisTap axis_tap(int d, int n_in, int n_out) {
   t.w = src - (float)t.i0;
   return t;
 }
+// same with the scale (float)n_in / (float)n_out computed once on the host (one IEEE division, same bits)
+__device__ __forceinline__ AxisTap axis_tap_s(int d, int n_in, float scale) {
+  float src = scale * ((float)d + 0.5f) - 0.5f;
+  src = fminf(fmaxf(src, 0.0f), (float)(n_in - 1));
+  AxisTap t;
+  t.i0 = (int)src;
+  t.i1 = min(t.i0 + 1, n_in - 1);
+  t.w = src - (float)t.i0;
+  return t;
+}
 __device__ __forceinline__ float lerp2(float tl, float tr, float bl, float br, float wx, float wy) {
   float top = (1.0f - wx) * tl + wx * tr;
   float bot = (1.0f - wx) * bl + wx * br;
@@ -118,8 +128,8 @@ __global__ void resize_padded_batch_kernel(const PageResizeIn* __restrict__ tab,
   if (ox >= OW) return;
   const float* s = pg.src;
   const int H = pg.H, W = pg.W;
-  AxisTap ty = axis_tap(oy, pg.padH, OH);
-  AxisTap tx = axis_tap(ox, pg.padW, OW);
+  AxisTap ty = axis_tap_s(oy, pg.padH, pg.sy);
+  AxisTap tx = axis_tap_s(ox, pg.padW, pg.sx);
   auto at = [&](int y, int x) -> float { return (y < H && x < W) ? __ldg(s + (int64_t)y * W + x) : pad_value; };
   float v = lerp2(at(ty.i0, tx.i0), at(ty.i0, tx.i1), at(ty.i1, tx.i0), at(ty.i1, tx.i1), tx.w, ty.w);
   dst[(int64_t)blockIdx.z * dst_stride + (int64_t)oy * OW + ox] = v;
@@ -133,8 +143,8 @@ __global__ void resize_threshold_batch_kernel(const PageResizeOut* __restrict__ 
   const bool in = ox < pg.W;
   bool fg = false;
   if (in) {
-    AxisTap ty = axis_tap(oy, pg.sliceH, pg.H);
-    AxisTap tx = axis_tap(ox, pg.sliceW, pg.W);
+    AxisTap ty = axis_tap_s(oy, pg.sliceH, pg.sy);
+    AxisTap tx = axis_tap_s(ox, pg.sliceW, pg.sx);
     const float* r0 = pg.net + (int64_t)ty.i0 * inW;
     const float* r1 = pg.net + (int64_t)ty.i1 * inW;
     float v = lerp2(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), tx.w, ty.w);
@@ -386,9 +396,16 @@ __global__ void __launch_bounds__(kCclWarps * 32) ccl_flatten_kernel(const CclPa
 // ---------------------------------------------------------------------------------------------
 // Per component: Suzuki-Abe outer border following -> RDP -> hull -> min-area rect.
 // ---------------------------------------------------------------------------------------------
-__constant__ int kDy[8] = {0, 1, 1, 1, 0, -1, -1, -1};  // clockwise from E (image coords)
-__constant__ int kDx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-__constant__ int kDirOf[9] = {5, 6, 7, 4, -1, 0, 3, 2, 1};  // [(dy+1)*3 + (dx+1)]
+// direction tables, packed into immediates (a __constant__ table lookup with a computed index costs a
+// dependent constant-cache access on the critical path of every border step):
+//   d:  0 E, 1 SE, 2 S, 3 SW, 4 W, 5 NW, 6 N, 7 NE  (clockwise in image coordinates)
+//   dy = {0, 1, 1, 1, 0, -1, -1, -1}, dx = {1, 1, 0, -1, -1, -1, 0, 1}, two bits each (+1)
+//   dir_of[(dy+1)*3 + (dx+1)] = {5, 6, 7, 4, -, 0, 3, 2, 1}, four bits each
+__device__ __forceinline__ int dir_dy(int d) { return (int)((0x01A9u >> (2 * d)) & 3u) - 1; }
+__device__ __forceinline__ int dir_dx(int d) { return (int)((0x901Au >> (2 * d)) & 3u) - 1; }
+__device__ __forceinline__ int dir_of(int dy, int dx) {
+  return (int)((0x1230F4765ull >> (4 * ((dy + 1) * 3 + (dx + 1)))) & 15ull);
+}
 
 struct BitView {
   const uint32_t* bits;
@@ -404,10 +421,9 @@ struct BitView {
     const uint64_t both = lo | (hi << 32);
     return (uint32_t)(both >> (x0 & 31)) & 7u;  // bits beyond W are 0 in the packed mask
   }
-  // 8-neighbourhood of (y, x): bit d = neighbour in direction d (kDy / kDx order)
+  // 8-neighbourhood of (y, x): bit d = neighbour in direction d
   __device__ __forceinline__ uint32_t nb8(int y, int x) const {
     const uint32_t a = row3(y - 1, x), b = row3(y, x), c = row3(y + 1, x);
-    // directions: 0 E (0,+1), 1 SE (+1,+1), 2 S (+1,0), 3 SW (+1,-1), 4 W (0,-1), 5 NW (-1,-1), 6 N (-1,0), 7 NE (-1,+1)
     return ((b >> 2) & 1u) | (((c >> 2) & 1u) << 1) | (((c >> 1) & 1u) << 2) | ((c & 1u) << 3) | ((b & 1u) << 4) |
            ((a & 1u) << 5) | (((a >> 1) & 1u) << 6) | (((a >> 2) & 1u) << 7);
   }
@@ -428,13 +444,13 @@ __device__ int trace_border(const BitView& mv, int i, int j, int16_t* out, int64
       return 1;
     }
     const int d = (4 + (__ffs(w) - 1)) & 7;
-    i1 = i + kDy[d];
-    j1 = j + kDx[d];
+    i1 = i + dir_dy(d);
+    j1 = j + dir_dx(d);
   }
   int i2 = i1, j2 = j1, i3 = i, j3 = j;
   int n = 0;
   while (true) {
-    const int d0 = kDirOf[(i2 - i3 + 1) * 3 + (j2 - j3 + 1)];
+    const int d0 = dir_of(i2 - i3, j2 - j3);
     // counter-clockwise from the direction after d0: d = d0-1, d0-2, ..., d0-8
     const uint32_t nb = mv.nb8(i3, j3);
     const uint32_t t = nb | (nb << 8);
@@ -442,8 +458,8 @@ __device__ int trace_border(const BitView& mv, int i, int j, int16_t* out, int64
     int i4 = i3, j4 = j3;
     if (w) {
       const int d = (d0 + (31 - __clz(w))) & 7;
-      i4 = i3 + kDy[d];
-      j4 = j3 + kDx[d];
+      i4 = i3 + dir_dy(d);
+      j4 = j3 + dir_dx(d);
     }
     if (n >= limit) return -1;
     if (out) { out[2 * n] = (int16_t)j3; out[2 * n + 1] = (int16_t)i3; }
@@ -454,78 +470,147 @@ __device__ int trace_border(const BitView& mv, int i, int j, int16_t* out, int64
   return n;
 }
 
-__global__ void component_rects_kernel(const CclPage* __restrict__ pages, float eps, float expand, float min_area) {
+// One WARP per component, components drawn from a per-page counter (the component count is only known on the
+// device, so a fixed grid of warps pulls work until the page's list is exhausted):
+//   lane 0 follows the border ONCE, into a shared-memory point buffer (borders longer than the buffer are counted
+//   first and traced into the global pool, the old two-pass form);
+//   the Ramer-Douglas-Peucker scan for the farthest point of a span runs over the 32 lanes (the span order, the
+//   distance function and the "last of the farthest" tie rule are those of the sequential form, so the kept points
+//   are identical); lane 0 owns the explicit stack;
+//   hull + min-area rectangle (a few dozen points) stay on lane 0, on shared-memory copies of the points.
+constexpr int kRectWarps = 4;            // warps per block
+constexpr int kRectBlocksPerPage = 74;   // x pages x 4 warps: 8 pages put 16 warps on every SM
+constexpr int kRectSmemPts = 1024;       // border points per warp kept in shared memory (4 KB)
+constexpr int kRectSmemSimp = 128;       // simplified points per warp kept in shared memory (2 x 1 KB)
+
+__global__ void __launch_bounds__(kRectWarps * 32)
+component_rects_kernel(const CclPage* __restrict__ pages, float eps, float expand, float min_area) {
+  __shared__ int16_t s_pts[kRectWarps][2 * kRectSmemPts];
+  __shared__ geom::PointF s_fp[kRectWarps][kRectSmemSimp];
+  __shared__ geom::PointF s_hull[kRectWarps][kRectSmemSimp];
   const CclPage pg = pages[blockIdx.y];
   const ComponentBuffers& b = pg.bufs;
   const int H = pg.H, W = pg.W;
-  int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  int n_comps = min(b.counters[0], b.max_comps);
-  if (ci >= n_comps) return;
-  int root = b.comp_roots[ci];
-  int i = root / W, j = root - i * W;
-  // outermost-border rule (Suzuki-Abe App. II): the 0-pixel left of the first pixel must belong
-  // to the background component that touches the frame.
-  if (j > 0 && pg.labels[(int64_t)i * W + run_start(pg.bits, pg.wstart, pg.wd, i, j - 1)] != pg.labels[(int64_t)H * W]) return;
-  BitView mv{pg.bits, H, W, pg.wd};
-  int n = trace_border(mv, i, j, nullptr, b.pool_cap);
-  if (n < 0) { atomicExch(&b.counters[2], 2); return; }
-  int64_t off = (int64_t)atomicAdd((unsigned long long*)(void*)&b.counters[4], (unsigned long long)(n + 2));
-  if (off + n + 2 > b.pool_cap) { atomicExch(&b.counters[2], 2); return; }
-  int16_t* pts = b.pts + 2 * off;
-  trace_border(mv, i, j, pts, n);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_comps = min(b.counters[0], b.max_comps);
+  const BitView mv{pg.bits, H, W, pg.wd};
+  const int bg_label = pg.labels[(int64_t)H * W];
 
-  // ---- RDP on the closed polyline P[0..n], P[n] == P[0] (simplify_polygon) ----
-  int32_t* simp = b.simp_idx + off;
-  int32_t* stack = b.stack + 3 * off;
-  auto P = [&](int idx) -> geom::PointF {
-    if (idx == n) idx = 0;
-    return geom::PointF{(float)pts[2 * idx], (float)pts[2 * idx + 1]};
-  };
-  int sp = 0, m = 0;
-  stack[0] = 0; stack[1] = n; stack[2] = 1;
-  sp = 1;
-  while (sp > 0) {
-    --sp;
-    int s = stack[3 * sp], e = stack[3 * sp + 1], keep = stack[3 * sp + 2];
-    if (e - s + 1 <= 1) {
-      simp[m++] = s;
-      continue;
+  while (true) {
+    int ci = 0;
+    if (lane == 0) ci = atomicAdd(&b.counters[6], 1);
+    ci = __shfl_sync(0xffffffffu, ci, 0);
+    if (ci >= n_comps) return;
+    const int root = b.comp_roots[ci];
+    const int i = root / W, j = root - i * W;
+
+    // ---- border following (lane 0) ----
+    int n = 0;
+    long long off = -1;
+    bool in_smem = true;
+    if (lane == 0) {
+      // outermost-border rule (Suzuki-Abe App. II): the 0-pixel left of the first pixel must belong
+      // to the background component that touches the frame.
+      if (j > 0 && pg.labels[(int64_t)i * W + run_start(pg.bits, pg.wstart, pg.wd, i, j - 1)] != bg_label) {
+        n = 0;
+      } else {
+        n = trace_border(mv, i, j, s_pts[warp], kRectSmemPts);
+        if (n < 0) {  // longer than the shared buffer: count, then trace into the pool
+          in_smem = false;
+          n = trace_border(mv, i, j, nullptr, b.pool_cap);
+          if (n < 0) atomicExch(&b.counters[2], 2);
+        }
+        if (n > 0) {
+          off = (long long)atomicAdd((unsigned long long*)(void*)&b.counters[4], (unsigned long long)(n + 2));
+          if (off + n + 2 > b.pool_cap) {
+            atomicExch(&b.counters[2], 2);
+            n = -1;
+          } else if (!in_smem) {
+            trace_border(mv, i, j, b.pts + 2 * off, n);
+          }
+        }
+      }
     }
-    geom::LineF seg{P(s), P(e)};
-    int max_i = s;  // "0" relative to the slice
-    float max_d = 0.0f;
-    for (int k = s + 1; k < e; ++k) {
-      float d = geom::line_distance(seg, P(k));
-      if (d >= max_d) { max_i = k; max_d = d; }
+    n = __shfl_sync(0xffffffffu, n, 0);
+    if (n <= 0) continue;
+    off = __shfl_sync(0xffffffffu, off, 0);
+    in_smem = __shfl_sync(0xffffffffu, (int)in_smem, 0) != 0;
+    __syncwarp();
+    const int16_t* pts = in_smem ? s_pts[warp] : (b.pts + 2 * off);
+
+    // ---- RDP on the closed polyline P[0..n], P[n] == P[0] (simplify_polygon) ----
+    int32_t* simp = b.simp_idx + off;
+    int32_t* stack = b.stack + 3 * off;
+    auto P = [&](int idx) -> geom::PointF {
+      if (idx == n) idx = 0;
+      return geom::PointF{(float)pts[2 * idx], (float)pts[2 * idx + 1]};
+    };
+    int sp = 1, m = 0;  // warp-uniform
+    if (lane == 0) { stack[0] = 0; stack[1] = n; stack[2] = 1; }
+    while (sp > 0) {
+      --sp;
+      int s = 0, e = 0, keep = 0;
+      if (lane == 0) { s = stack[3 * sp]; e = stack[3 * sp + 1]; keep = stack[3 * sp + 2]; }
+      s = __shfl_sync(0xffffffffu, s, 0);
+      e = __shfl_sync(0xffffffffu, e, 0);
+      keep = __shfl_sync(0xffffffffu, keep, 0);
+      if (e - s + 1 <= 1) {
+        if (lane == 0) simp[m] = s;
+        ++m;
+        continue;
+      }
+      const geom::LineF seg{P(s), P(e)};
+      // sequential rule: max_i = s, max_d = 0; for k in (s, e): if (d >= max_d) take k  ==  the LAST k among the
+      // farthest points.  Per lane the same rule over k = s+1+lane, +32, ...; across lanes (larger d, then larger k).
+      int max_i = s;
+      float max_d = 0.0f;
+      for (int k = s + 1 + lane; k < e; k += 32) {
+        const float d = geom::line_distance(seg, P(k));
+        if (d >= max_d) { max_i = k; max_d = d; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, max_d, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, max_i, o);
+        if (od > max_d || (od == max_d && oi > max_i)) { max_d = od; max_i = oi; }
+      }
+      if (max_d > eps) {
+        if (lane == 0) {  // left half first: push right, then left
+          stack[3 * sp] = max_i; stack[3 * sp + 1] = e; stack[3 * sp + 2] = keep;
+          stack[3 * sp + 3] = s; stack[3 * sp + 4] = max_i; stack[3 * sp + 5] = 0;
+        }
+        sp += 2;
+      } else {
+        if (lane == 0) {
+          simp[m] = s;
+          if (keep) simp[m + 1] = e;
+        }
+        m += keep ? 2 : 1;
+      }
     }
-    if (max_d > eps) {
-      // left half first: push right, then left
-      stack[3 * sp] = max_i; stack[3 * sp + 1] = e; stack[3 * sp + 2] = keep; ++sp;
-      stack[3 * sp] = s; stack[3 * sp + 1] = max_i; stack[3 * sp + 2] = 0; ++sp;
-    } else {
-      simp[m++] = s;
-      if (keep) simp[m++] = e;
+    m -= 1;  // drop the duplicated closing point
+    if (m < 1) continue;
+    __syncwarp();  // simp[] (written by lane 0) is read by every lane below
+    const bool small = m <= kRectSmemSimp;
+    geom::PointF* fpts = small ? s_fp[warp] : reinterpret_cast<geom::PointF*>(b.fpts + 2 * off);
+    geom::PointF* hull = small ? s_hull[warp] : reinterpret_cast<geom::PointF*>(b.hull + 2 * off);
+    for (int k = lane; k < m; k += 32) fpts[k] = P(simp[k]);
+    __syncwarp();
+    if (lane == 0) {
+      const int hm = geom::convex_hull(fpts, m, hull);
+      geom::RotatedRect rr;
+      if (geom::min_area_rect_of_hull(hull, hm, &rr)) {
+        rr.w = rr.w + 2.0f * expand;  // detection.rs:53-57
+        rr.h = rr.h + 2.0f * expand;
+        if (geom::rr_area(rr) >= min_area) {  // detection.rs:60
+          const int slot = atomicAdd(&b.counters[3], 1);
+          b.rects[slot] = rr;
+          b.rect_root[slot] = root;
+        }
+      }
     }
+    __syncwarp();  // the shared buffers are reused by the next component
   }
-  m -= 1;  // drop the duplicated closing point
-  if (m < 1) return;
-  float* fp = b.fpts + 2 * off;
-  for (int k = 0; k < m; ++k) {
-    geom::PointF q = P(simp[k]);
-    fp[2 * k] = q.x;
-    fp[2 * k + 1] = q.y;
-  }
-  geom::PointF* fpts = reinterpret_cast<geom::PointF*>(fp);
-  geom::PointF* hull = reinterpret_cast<geom::PointF*>(b.hull + 2 * off);
-  int hm = geom::convex_hull(fpts, m, hull);
-  geom::RotatedRect rr;
-  if (!geom::min_area_rect_of_hull(hull, hm, &rr)) return;
-  rr.w = rr.w + 2.0f * expand;  // detection.rs:53-57
-  rr.h = rr.h + 2.0f * expand;
-  if (!(geom::rr_area(rr) >= min_area)) return;  // detection.rs:60
-  int slot = atomicAdd(&b.counters[3], 1);
-  b.rects[slot] = rr;
-  b.rect_root[slot] = root;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -557,34 +642,64 @@ __global__ void line_crossings_kernel(const LineDesc* __restrict__ lines, int n_
   row[0] = cnt;
 }
 
-__global__ void crop_resize_kernel(const float* const* __restrict__ pages, const int* __restrict__ page_h,
-                                   const int* __restrict__ page_w, const LineDesc* __restrict__ lines, int n_lines,
-                                   const int32_t* __restrict__ cross, float* __restrict__ dst, int out_h) {
-  int li = blockIdx.z;
+// One block = 128 output columns of one line, ALL output rows: the column taps, the page bounds and the line
+// record are set up once per thread instead of once per output pixel, and the line's whole crossing table
+// ([lh][max_cross + 1] ints, a few KB) is staged in shared memory once per block (from global memory when it
+// does not fit).  Per output pixel: the row taps from shared memory, four inside tests, four loads, one store.
+constexpr int kCropSmemInts = 6144;  // 24 KB of crossings
+constexpr int kCropRowTaps = 128;    // row taps kept in shared memory (the recognition height is 64)
+
+__global__ void __launch_bounds__(128) crop_resize_kernel(const float* const* __restrict__ pages, const int* __restrict__ page_h,
+                                                          const int* __restrict__ page_w, const LineDesc* __restrict__ lines,
+                                                          int n_lines, const int32_t* __restrict__ cross, float* __restrict__ dst,
+                                                          int out_h) {
+  __shared__ int32_t s_cross[kCropSmemInts];
+  __shared__ AxisTap s_ty[kCropRowTaps];
+  const int li = blockIdx.y;
   if (li >= n_lines) return;
   const LineDesc L = lines[li];
-  int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  int oy = blockIdx.y;
-  if (ox >= L.group_width) return;
-  float v = kBlackValue;
-  if (ox < L.resized_width && L.lh > 0 && L.lw > 0) {
-    const float* page = pages[L.page];
-    const int PH = page_h[L.page], PW = page_w[L.page];
-    AxisTap ty = axis_tap(oy, L.lh, out_h);
-    AxisTap tx = axis_tap(ox, L.lw, L.resized_width);
-    auto canvas = [&](int cy, int cx) -> float {
-      int py = cy + L.top, px = cx + L.left;
-      // both points are tested against the page index rect (recognition.rs:112)
-      if (py < 0 || py > PH - 1 || px < 0 || px > PW - 1) return kBlackValue;
-      if (cy < 0 || cy > PH - 1 || cx < 0 || cx > PW - 1) return kBlackValue;
-      const int32_t* row = cross + L.cross_off + (int64_t)cy * (L.max_cross + 1);
-      int cnt = row[0], inside = 0;
-      for (int k = 0; k < cnt; ++k) inside += (row[1 + k] <= px) ? 1 : 0;
-      return (inside & 1) ? page[(int64_t)py * PW + px] : kBlackValue;
-    };
-    v = lerp2(canvas(ty.i0, tx.i0), canvas(ty.i0, tx.i1), canvas(ty.i1, tx.i0), canvas(ty.i1, tx.i1), tx.w, ty.w);
+  if ((int)(blockIdx.x * blockDim.x) >= L.group_width) return;  // block-uniform
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool has_src = L.lh > 0 && L.lw > 0;
+  const int stride = L.max_cross + 1;
+  const int32_t* ctab = cross + L.cross_off;
+  if (has_src) {
+    const int n_ints = L.lh * stride;
+    if (n_ints <= kCropSmemInts) {
+      for (int k = threadIdx.x; k < n_ints; k += blockDim.x) s_cross[k] = ctab[k];
+      ctab = s_cross;
+    }
+    for (int r = threadIdx.x; r < min(out_h, kCropRowTaps); r += blockDim.x) s_ty[r] = axis_tap(r, L.lh, out_h);
   }
-  dst[L.dst_off + (int64_t)oy * L.group_width + ox] = v;
+  __syncthreads();
+  if (ox >= L.group_width) return;
+  float* out = dst + L.dst_off + ox;
+  if (!(ox < L.resized_width && has_src)) {
+    for (int oy = 0; oy < out_h; ++oy) out[(int64_t)oy * L.group_width] = kBlackValue;
+    return;
+  }
+  const float* page = pages[L.page];
+  const int PH = page_h[L.page], PW = page_w[L.page];
+  const AxisTap tx = axis_tap(ox, L.lw, L.resized_width);
+  // both points (canvas and page coordinates) are tested against the page index rect (recognition.rs:112)
+  const int px0 = tx.i0 + L.left, px1 = tx.i1 + L.left;
+  const bool xin0 = !(px0 < 0 || px0 > PW - 1 || tx.i0 < 0 || tx.i0 > PW - 1);
+  const bool xin1 = !(px1 < 0 || px1 > PW - 1 || tx.i1 < 0 || tx.i1 > PW - 1);
+  auto canvas = [&](int cy, int px, bool xin) -> float {
+    const int py = cy + L.top;
+    if (!xin || py < 0 || py > PH - 1 || cy < 0 || cy > PH - 1) return kBlackValue;
+    const int32_t* row = ctab + cy * stride;
+    const int cnt = row[0];
+    int inside = 0;
+    for (int k = 0; k < cnt; ++k) inside += (row[1 + k] <= px) ? 1 : 0;
+    return (inside & 1) ? __ldg(page + (int64_t)py * PW + px) : kBlackValue;
+  };
+  for (int oy = 0; oy < out_h; ++oy) {
+    const AxisTap ty = oy < kCropRowTaps ? s_ty[oy] : axis_tap(oy, L.lh, out_h);
+    const float v = lerp2(canvas(ty.i0, px0, xin0), canvas(ty.i0, px1, xin1), canvas(ty.i1, px0, xin0), canvas(ty.i1, px1, xin1),
+                          tx.w, ty.w);
+    out[(int64_t)oy * L.group_width] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -797,10 +912,11 @@ void find_component_rects_batch(const CclPage* d_pages, const CclPage* h_pages, 
   count_launch();
   ccl_flatten_kernel<<<rows, kCclWarps * 32, 0, st>>>(d_pages);
   count_launch();
-  // one thread per component; the count is only known on the device, so launch for the
-  // theoretical maximum (cheap: threads beyond n_comps exit).
-  dim3 comps(grid1d(max_c, 64), (unsigned)n_pages);
-  component_rects_kernel<<<comps, 64, 0, st>>>(d_pages, eps, expand_dist, min_area);
+  // one warp per component, pulled from a per-page counter (counters[6]); the count is only known on the device,
+  // so a fixed grid of warps per page loops until the page's list is exhausted
+  (void)max_c;
+  dim3 comps((unsigned)kRectBlocksPerPage, (unsigned)n_pages);
+  component_rects_kernel<<<comps, kRectWarps * 32, 0, st>>>(d_pages, eps, expand_dist, min_area);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
 }
@@ -814,7 +930,7 @@ void crop_lines(const float* const* pages, const int* page_h, const int* page_w,
     line_crossings_kernel<<<g1, 64, 0, st>>>(lines, n_lines, poly_xy, cross_scratch);
   count_launch();
   }
-  dim3 g2(grid1d(max_group_width, 128), out_h, n_lines);
+  dim3 g2(grid1d(max_group_width, 128), n_lines);
   crop_resize_kernel<<<g2, 128, 0, st>>>(pages, page_h, page_w, lines, n_lines, cross_scratch, dst, out_h);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());

@@ -38,6 +38,7 @@ void threshold(const float* prob, uint8_t* mask, int64_t n, float thr, cudaStrea
 struct PageResizeIn {   // input of the detection resize: grey page [H, W], virtually padded to [padH, padW]
   const float* src;
   int32_t H, W, padH, padW;
+  float sy, sx;         // (float)padH / (float)OH, (float)padW / (float)OW (fill with resize_scale)
 };
 struct PageResizeOut {  // output of the detection epilogue: slice of the net output -> [H, W] mask (+ prob map)
   const float* net;     // this page's [inH, inW] network output
@@ -45,7 +46,9 @@ struct PageResizeOut {  // output of the detection epilogue: slice of the net ou
   uint8_t* mask;
   uint32_t* bits;       // bit-packed mask [H][ceil(W/32)] (may be null)
   int32_t sliceH, sliceW, H, W;
+  float sy, sx;         // (float)sliceH / (float)H, (float)sliceW / (float)W
 };
+inline float resize_scale(int n_in, int n_out) { return (float)n_in / (float)n_out; }
 struct PagePrepare {    // u8 HWC RGB page -> grey f32
   const void* src;
   float* dst;
