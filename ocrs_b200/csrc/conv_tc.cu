@@ -541,7 +541,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
 //   * the activation is loaded as one 10-row box per horizontal tap kw (rows h0-1 .. h0+8) and the three vertical
 //     taps read it through descriptors advanced by whole tile rows, as in the CTA-pair + halo kernel below:
 //     60 KB per tile instead of 216 KB;
-//   * three hi*hi accumulators + one cross-term accumulator in tensor memory (see the halo kernel).
+//   * three hi*hi accumulators (see the halo kernel) and one accumulator per cross term, each of the three products
+//     of the split issued by its own thread.
 // k-blocks run in (kw, kh) order; promotion groups stay 128 K-elements (4 k-blocks of 32 channels).
 // ------------------------------------------------------------------------------------------
 template <int KC_, int COUT>
@@ -555,9 +556,11 @@ struct ResCfg {
   static constexpr int kGroupKb = 128 / kKC;
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 1024 + kBarBytes;
-  static constexpr int kTmemCols = 4 * COUT;
+  static constexpr int kTmemCols = 8 * COUT;      // HH[3] | X1 | X2 (5 x COUT, rounded up to a power of two)
   static constexpr int kEpiWarps = 4 * (COUT / 32);
-  static constexpr int kThreads = 32 * (kEpiWarps + 2);
+  static constexpr int kMmaWarps = 3;              // hi*hi, hi*lo, lo*hi: one issuing thread each
+  static constexpr int kThreads = 32 * (kEpiWarps + 1 + kMmaWarps);
+  static_assert(kTmemCols <= 512, "tensor memory");
   static_assert(kABox % 1024 == 0 && kBTile % 1024 == 0, "operand tiles must keep the swizzle phase");
   static_assert(kSmemBytes <= 227 * 1024, "resident weights do not fit");
 };
@@ -580,30 +583,34 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   const uint32_t aux = bar_base + 8u * (2 * C::kStages);
   auto hh_full = [&](int b) { return aux + 8u * b; };
   auto hh_empty = [&](int b) { return aux + 8u * (3 + b); };
-  const uint32_t x_full = aux + 8u * 6, x_empty = aux + 8u * 7, b_full = aux + 8u * 8;
-  auto sched_full = [&](int s) { return aux + 8u * (9 + s); };
-  auto sched_empty = [&](int s) { return aux + 8u * (9 + kSched + s); };
-  const uint32_t tmem_slot = aux + 8u * (9 + 2 * kSched);
+  auto x_full = [&](int i) { return aux + 8u * (6 + i); };   // i = 0: hi*lo accumulator, 1: lo*hi accumulator
+  auto x_empty = [&](int i) { return aux + 8u * (8 + i); };
+  const uint32_t b_full = aux + 8u * 10;
+  auto sched_full = [&](int s) { return aux + 8u * (11 + s); };
+  auto sched_empty = [&](int s) { return aux + 8u * (11 + kSched + s); };
+  const uint32_t tmem_slot = aux + 8u * (11 + 2 * kSched);
   const uint32_t ring = tmem_slot + 8u + ((tmem_slot + 8u) & 8u);  // 16-byte aligned
-  static_assert(8 * (2 * C::kStages + 9 + 2 * kSched) + 24 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
+  static_assert(8 * (2 * C::kStages + 11 + 2 * kSched) + 24 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
   TileEntry* ring_p = reinterpret_cast<TileEntry*>(smem_raw + (ring - smem0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), C::kMmaWarps);  // one commit per issuing thread
     }
     for (int b = 0; b < 3; ++b) {
       mbar_init(hh_full(b), 1);
       mbar_init(hh_empty(b), C::kEpiWarps);
     }
-    mbar_init(x_full, 1);
-    mbar_init(x_empty, C::kEpiWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(x_full(i), 1);
+      mbar_init(x_empty(i), C::kEpiWarps);
+    }
     mbar_init(b_full, 1);
     for (int s = 0; s < kSched; ++s) {
       mbar_init(sched_full(s), 1);
-      mbar_init(sched_empty(s), C::kEpiWarps + 1);
+      mbar_init(sched_empty(s), C::kEpiWarps + C::kMmaWarps);
     }
     fence_barrier_init();
   }
@@ -672,12 +679,17 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
         t = t_next;
       }
     }
-  } else if (warp == C::kEpiWarps + 1) {
+  } else if (warp > C::kEpiWarps) {
     if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+      // ---------------- MMA issuers ----------------
+      // A single thread issues one tcgen05.mma per ~53+ cycles whatever its size (profiles/r02a_ubench_mma.log), and
+      // this layer's MMAs are only 32 cycles of tensor work each: the three products of the split go out from three
+      // threads, each into its own accumulator (role 0: hi*hi with the promotion protocol, 1: hi*lo, 2: lo*hi), so
+      // the order of accumulation inside every accumulator is fixed.
+      const int role = warp - (C::kEpiWarps + 1);
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
       uint32_t stage = 0, par = 0, hb = 0, hpar = 0;
-      const uint32_t d_x = tmem_base + 3 * COUT;
+      const uint32_t d_x = tmem_base + (uint32_t)((2 + role) * COUT);  // role 1: column 3*COUT, role 2: 4*COUT
       mbar_wait(b_full, 0);
       const uint64_t db_base = make_desc<KC>(bres);
       for (uint32_t ti = 0;; ++ti) {
@@ -687,6 +699,10 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(g) : "r"(ring + slot * (uint32_t)sizeof(TileEntry)) : "memory");
         mbar_arrive(sched_empty(slot));
         if (g < 0) break;
+        if (role != 0) {
+          mbar_wait(x_empty(role - 1), (ti & 1) ^ 1);
+          tc_fence_after();
+        }
         int kbi = 0;
         for (int kw = 0; kw < 3; ++kw) {
           mbar_wait(full_bar(stage), par);
@@ -694,46 +710,33 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
           const uint64_t d0 = make_desc<KC>(base + stage * C::kStageBytes);
 #pragma unroll 1
           for (int kh = 0; kh < 3; ++kh, ++kbi) {
-            const uint32_t d_hh = tmem_base + hb * COUT;
-            if ((kbi & (C::kGroupKb - 1)) == 0) {
-              mbar_wait(hh_empty(hb), hpar ^ 1);
-              tc_fence_after();
-            }
             const uint64_t da0 = d0 + (uint64_t)((kh * kTW * KC * 2) >> 4);
             const uint64_t db0 = db_base + (uint64_t)(((kh * 3 + kw) * 2 * C::kBTile) >> 4);
-            if (kbi == 0) {
-              // hi*hi of the first k-block goes out before the wait for the cross-term accumulator
+            if (role == 0) {
+              const uint32_t d_hh = tmem_base + hb * COUT;
+              if ((kbi & (C::kGroupKb - 1)) == 0) {
+                mbar_wait(hh_empty(hb), hpar ^ 1);
+                tc_fence_after();
+              }
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k)
-                umma_bf16(d_hh, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
-              mbar_wait(x_empty, (ti & 1) ^ 1);
-              tc_fence_after();
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                const uint64_t da_hi = da0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABox >> 4);
-                const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(C::kBTile >> 4);
-                umma_bf16(d_x, da_hi, db_lo, idesc, k ? 1u : 0u);
-                umma_bf16(d_x, da_lo, db_hi, idesc, 1u);
+                umma_bf16(d_hh, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, ((kbi & (C::kGroupKb - 1)) | k) ? 1u : 0u);
+              if ((kbi & (C::kGroupKb - 1)) == C::kGroupKb - 1 || kbi == nkb - 1) {
+                umma_commit(hh_full(hb));
+                if (++hb == 3) { hb = 0; hpar ^= 1; }
               }
             } else {
+              // role 1: A_hi x B_lo, role 2: A_lo x B_hi
+              const uint64_t da = da0 + (role == 2 ? (uint64_t)(C::kABox >> 4) : 0ull);
+              const uint64_t db = db0 + (role == 1 ? (uint64_t)(C::kBTile >> 4) : 0ull);
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                const uint64_t da_hi = da0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABox >> 4);
-                const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(C::kBTile >> 4);
-                umma_bf16(d_hh, da_hi, db_hi, idesc, ((kbi & (C::kGroupKb - 1)) | k) ? 1u : 0u);
-                umma_bf16(d_x, da_hi, db_lo, idesc, 1u);
-                umma_bf16(d_x, da_lo, db_hi, idesc, 1u);
-              }
-            }
-            if ((kbi & (C::kGroupKb - 1)) == C::kGroupKb - 1 || kbi == nkb - 1) {
-              umma_commit(hh_full(hb));
-              if (++hb == 3) { hb = 0; hpar ^= 1; }
+              for (int k = 0; k < KC / 16; ++k) umma_bf16(d_x, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kbi | k) ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(stage));
           if (++stage == C::kStages) { stage = 0; par ^= 1; }
         }
-        umma_commit(x_full);
+        if (role != 0) umma_commit(x_full(role - 1));
       }
     }
   } else {
@@ -767,17 +770,18 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
         if (lane == 0) mbar_arrive(hh_empty(hb));
         if (++hb == 3) { hb = 0; hpar ^= 1; }
       }
-      mbar_wait(x_full, ti & 1);
-      tc_fence_after();
-      {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {  // + hi*lo, then + lo*hi
+        mbar_wait(x_full(i), ti & 1);
+        tc_fence_after();
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_base + 3 * COUT, r);
+        tmem_ld32(tmem_base + lane_base + (uint32_t)((3 + i) * COUT), r);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(x_empty(i));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(x_empty);
       epilogue_store<COUT>(acc, e, wq, hsel, lane, relu, ph, pw, true, bias, out_hi, out_lo, ovf);
     }
   }
@@ -1163,7 +1167,8 @@ struct HaloCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
   static constexpr int kTmemCols = 4 * COUT;
   static constexpr int kEpiWarps = 4 * (COUT / 32);
-  static constexpr int kThreads = 32 * (kEpiWarps + 2);
+  static constexpr int kMmaWarps = 2;  // one issuing thread for hi*hi, one for the cross terms
+  static constexpr int kThreads = 32 * (kEpiWarps + 1 + kMmaWarps);
   static_assert(kABox % 1024 == 0 && kBHalf % 1024 == 0, "operand tiles must keep the swizzle phase");
 };
 
@@ -1205,7 +1210,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(full_bar(s), 1);   // leader: its producer arms; both CTAs' loads complete_tx on it
-      mbar_init(empty_bar(s), 1);  // one multicast commit
+      mbar_init(empty_bar(s), C::kMmaWarps);  // one multicast commit per issuing thread
     }
     for (int b = 0; b < 3; ++b) {
       mbar_init(hh_full(b), 1);
@@ -1215,7 +1220,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_co
     mbar_init(x_empty, 2 * C::kEpiWarps);
     for (int s = 0; s < kSched; ++s) {
       mbar_init(sched_full(s), 1);
-      mbar_init(sched_empty(s), 2 * C::kEpiWarps + 2);  // leader: MMA thread + peer's TMA thread + all promotion warps
+      mbar_init(sched_empty(s), 2 * C::kEpiWarps + 1 + C::kMmaWarps);  // leader: MMA threads + peer's TMA thread + all promotion warps
     }
     fence_barrier_init();
   }
@@ -1315,11 +1320,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_co
         pr = pr_next;
       }
     }
-  } else if (warp == C::kEpiWarps + 1) {
+  } else if (warp > C::kEpiWarps) {
     if (lane == 0 && leader) {
-      // ---------------- MMA issuer (leader only) ----------------
+      // ---------------- MMA issuers (leader only) ----------------
+      // TWO issuing threads: role 0 issues the hi*hi MMAs and runs the promotion protocol (hh_empty / hh_full), role 1
+      // issues the cross terms (hi*lo, lo*hi, in that order per 16 K-elements) into the cross-term accumulator.  One
+      // thread issued all twelve MMAs of a k-block at ~53-64 cycles each AND paid every barrier wait (~100-150 cycles
+      // even when satisfied) in series: 1337 cycles per k-block for 768 cycles of tensor work
+      // (profiles/r02p_conv_timers.log).  Each accumulator is written by one thread only, so the order of
+      // accumulation is fixed.  Both threads wait for the operands and both release the stage (two commits).
+      // The waits are CTA-scope (default semantics) although the peer arrives on these barriers too: the peer hands
+      // over no generic-proxy data through them (operands arrive through the async proxy, accumulator buffers are
+      // ordered by the tcgen05 fences).
+      // (Splitting the operand ring into an activation ring and a per-k-block weight ring, to issue loads two
+      // boxes ahead, was slower: three more barrier waits per box cost more than the exposed latency they removed
+      // -- 1630 vs 1337 cycles per k-block, profiles/r02q_conv_split_rings_timers.log.)
       // c_format F32 (bit 4), a/b format F16, N >> 3 at 17, M >> 4 at 24 with M = 256 over the pair
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((256u >> 4) << 24);
+      const int role = warp - (C::kEpiWarps + 1);
       uint32_t stage = 0, par = 0, hb = 0, hpar = 0;  // hb: hi*hi buffer of the current group, hpar: its use parity
       const uint32_t d_x = tmem_base + 3 * COUT;
       unsigned long long c_sched = 0, c_xe = 0, c_hhe = 0, c_full = 0, c_iss = 0, n_tiles_done = 0;
@@ -1334,80 +1352,74 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_co
         mbar_arrive(sched_empty(slot));
         if (g < 0) break;
         if (timing) c_sched += (unsigned long long)(clock64() - c0);
+        if (role == 1) {
+          // the promotion warps read the previous tile's cross terms right after that tile's last commit
+          long long x0 = timing ? clock64() : 0;
+          mbar_wait_trap(x_empty, (ti & 1) ^ 1);
+          tc_fence_after();
+          if (timing) c_xe += (unsigned long long)(clock64() - x0);
+        }
         int kbi = 0;  // k-block of the tile, in (chunk, kw, kh) order; promotion groups = kGroupKb k-blocks
         for (int sidx = 0; sidx < 3 * chunks; ++sidx) {
           long long w0 = timing ? clock64() : 0;
-          mbar_wait_cluster_trap(full_bar(stage), par);
+          mbar_wait_trap(full_bar(stage), par);
           tc_fence_after();
           if (timing) c_full += (unsigned long long)(clock64() - w0);
           const uint64_t d0 = make_desc<KC>(base + stage * C::kStageBytes);
 #pragma unroll 1
           for (int kh = 0; kh < 3; ++kh, ++kbi) {
-            const uint32_t d_hh = tmem_base + hb * COUT;
-            if ((kbi & (C::kGroupKb - 1)) == 0) {
-              long long g0 = timing ? clock64() : 0;
-              mbar_wait_cluster_trap(hh_empty(hb), hpar ^ 1);
-              tc_fence_after();
-              if (timing) c_hhe += (unsigned long long)(clock64() - g0);
-            }
-            long long g1 = timing ? clock64() : 0;
             // A: rows kh .. kh+7 of the 10-row box (16 pixels x 128 B per row); B: the tap's weight half
             const uint64_t da0 = d0 + (uint64_t)((kh * kTW * KC * 2) >> 4);
             const uint64_t db0 = d0 + (uint64_t)((2 * C::kABox + kh * 2 * C::kBHalf) >> 4);
-            if (kbi == 0) {
-              // first k-block of a tile: the hi*hi MMAs go out before the wait for the cross-term accumulator
-              // (the promotion warps read the previous tile's out of it right after that tile's last commit)
+            if (role == 0) {
+              const uint32_t d_hh = tmem_base + hb * COUT;
+              if ((kbi & (C::kGroupKb - 1)) == 0) {
+                long long g0 = timing ? clock64() : 0;
+                mbar_wait_trap(hh_empty(hb), hpar ^ 1);
+                tc_fence_after();
+                if (timing) c_hhe += (unsigned long long)(clock64() - g0);
+              }
+              long long g1 = timing ? clock64() : 0;
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k)
-                umma2_f16(d_hh, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
-              long long x0 = timing ? clock64() : 0;
-              mbar_wait_cluster_trap(x_empty, (ti & 1) ^ 1);
-              tc_fence_after();
-              if (timing) {
-                const unsigned long long xw = (unsigned long long)(clock64() - x0);
-                c_xe += xw;
-                c_iss -= xw;  // the enclosing issue interval contains this wait
+                umma2_f16(d_hh, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, ((kbi & (C::kGroupKb - 1)) | k) ? 1u : 0u);
+              if ((kbi & (C::kGroupKb - 1)) == C::kGroupKb - 1 || kbi == nkb - 1) {
+                umma2_commit_mc(hh_full(hb), 3);
+                if (++hb == 3) { hb = 0; hpar ^= 1; }
               }
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                const uint64_t da_hi = da0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABox >> 4);
-                const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(C::kBHalf >> 4);
-                umma2_f16(d_x, da_hi, db_lo, idesc, k ? 1u : 0u);
-                umma2_f16(d_x, da_lo, db_hi, idesc, 1u);
-              }
+              if (timing) c_iss += (unsigned long long)(clock64() - g1);
             } else {
+              long long g1 = timing ? clock64() : 0;
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k) {
                 const uint64_t da_hi = da0 + (uint64_t)(2 * k), da_lo = da_hi + (uint64_t)(C::kABox >> 4);
                 const uint64_t db_hi = db0 + (uint64_t)(2 * k), db_lo = db_hi + (uint64_t)(C::kBHalf >> 4);
-                umma2_f16(d_hh, da_hi, db_hi, idesc, ((kbi & (C::kGroupKb - 1)) | k) ? 1u : 0u);
-                umma2_f16(d_x, da_hi, db_lo, idesc, 1u);
+                umma2_f16(d_x, da_hi, db_lo, idesc, (kbi | k) ? 1u : 0u);
                 umma2_f16(d_x, da_lo, db_hi, idesc, 1u);
               }
+              if (timing) c_iss += (unsigned long long)(clock64() - g1);
             }
-            if ((kbi & (C::kGroupKb - 1)) == C::kGroupKb - 1 || kbi == nkb - 1) {
-              umma2_commit_mc(hh_full(hb), 3);
-              if (++hb == 3) { hb = 0; hpar ^= 1; }
-            }
-            if (timing) c_iss += (unsigned long long)(clock64() - g1);
           }
           umma2_commit_mc(empty_bar(stage), 3);
           if (++stage == C::kStages) { stage = 0; par ^= 1; }
         }
-        umma2_commit_mc(x_full, 3);
+        if (role == 1) umma2_commit_mc(x_full, 3);
         ++n_tiles_done;
       }
       if (timing) {
-        atomicAdd(dbg + 0, 2 * n_tiles_done);
-        atomicAdd(dbg + 1, n_tiles_done * (unsigned long long)nkb);
-        atomicAdd(dbg + 2, c_sched);
-        atomicAdd(dbg + 3, c_xe);
-        atomicAdd(dbg + 4, c_hhe);
-        atomicAdd(dbg + 5, c_full);
-        atomicAdd(dbg + 6, c_iss);
-        atomicAdd(dbg + 7, 0ull);
-        atomicAdd(dbg + 8, (unsigned long long)(clock64() - t_begin));
-        atomicAdd(dbg + 9, 1ull);
+        // [0..9]: the hi*hi thread; [16..23]: the cross-term thread (same fields)
+        unsigned long long* o = dbg + (role == 0 ? 0 : 16);
+        atomicAdd(o + 0, 2 * n_tiles_done);
+        atomicAdd(o + 1, n_tiles_done * (unsigned long long)nkb);
+        atomicAdd(o + 2, c_sched);
+        atomicAdd(o + 3, c_xe);
+        atomicAdd(o + 4, c_hhe);
+        atomicAdd(o + 5, c_full);
+        atomicAdd(o + 6, c_iss);
+        if (role == 0) {
+          atomicAdd(dbg + 8, (unsigned long long)(clock64() - t_begin));
+          atomicAdd(dbg + 9, 1ull);
+        }
       }
     }
   } else {
@@ -1759,15 +1771,15 @@ void launch_conv_pair(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int
   const int grid = 2 * std::max(1, std::min(n_pairs, sm_count() / 2));
   unsigned long long* d_dbg = nullptr;
   if (conv_debug()) {
-    OCRS_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_dbg), 16 * sizeof(unsigned long long), st));
-    OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 16 * sizeof(unsigned long long), st));
+    OCRS_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_dbg), 24 * sizeof(unsigned long long), st));
+    OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 24 * sizeof(unsigned long long), st));
   }
   kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles, d_counter,
                                                   w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph, pw, promo_scale(), ovf, d_dbg);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
   if (d_dbg) {
-    unsigned long long h[16];
+    unsigned long long h[24];
     OCRS_CUDA_CHECK(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
     OCRS_CUDA_CHECK(cudaStreamSynchronize(st));
     OCRS_CUDA_CHECK(cudaFreeAsync(d_dbg, st));
@@ -1777,6 +1789,10 @@ void launch_conv_pair(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int
             "x_empty %.0f, hh_empty %.0f, operands %.0f, issue %.0f | loop total %.0f (per cluster %.0f cycles)",
             HALO ? "+HALO" : "", Cin, COUT, ph, pw, h[0], n_groups, cl, h[2] / kb, h[3] / kb, h[4] / kb, h[5] / kb, h[6] / kb, h[8] / kb,
             h[8] / cl);
+    if (h[17]) {
+      const double kx = (double)h[17];
+      fprintf(stderr, " | cross-term thread: ring %.0f, x_empty %.0f, operands %.0f, issue %.0f", h[18] / kx, h[19] / kx, h[21] / kx, h[22] / kx);
+    }
     if (h[15]) {
       const double tl = (double)h[15];
       fprintf(stderr, " | promotion warp 0 of every CTA, per TILE: ring %.0f, wait hh_full %.0f, promote %.0f, wait x_full %.0f, X + epilogue %.0f",

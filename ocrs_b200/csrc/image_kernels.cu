@@ -694,11 +694,32 @@ __global__ void __launch_bounds__(128) crop_resize_kernel(const float* const* __
     for (int k = 0; k < cnt; ++k) inside += (row[1 + k] <= px) ? 1 : 0;
     return (inside & 1) ? __ldg(page + (int64_t)py * PW + px) : kBlackValue;
   };
+  // the line is usually magnified: consecutive output rows share their source rows, whose four samples are reused
+  int r0 = -1, r1 = -1;
+  float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
   for (int oy = 0; oy < out_h; ++oy) {
     const AxisTap ty = oy < kCropRowTaps ? s_ty[oy] : axis_tap(oy, L.lh, out_h);
-    const float v = lerp2(canvas(ty.i0, px0, xin0), canvas(ty.i0, px1, xin1), canvas(ty.i1, px0, xin0), canvas(ty.i1, px1, xin1),
-                          tx.w, ty.w);
-    out[(int64_t)oy * L.group_width] = v;
+    if (ty.i0 != r0) {
+      if (ty.i0 == r1) {
+        v00 = v10;
+        v01 = v11;
+      } else {
+        v00 = canvas(ty.i0, px0, xin0);
+        v01 = canvas(ty.i0, px1, xin1);
+      }
+      r0 = ty.i0;
+    }
+    if (ty.i1 != r1) {
+      if (ty.i1 == r0) {
+        v10 = v00;
+        v11 = v01;
+      } else {
+        v10 = canvas(ty.i1, px0, xin0);
+        v11 = canvas(ty.i1, px1, xin1);
+      }
+      r1 = ty.i1;
+    }
+    out[(int64_t)oy * L.group_width] = lerp2(v00, v01, v10, v11, tx.w, ty.w);
   }
 }
 
