@@ -152,12 +152,14 @@ class ClockSampler:
 
 
 def measured_traffic(kernel: str):
-    """DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01b_conv_traffic.json")
+    """DRAM bytes (read + write) per launch of an operator class, from the committed `ncu --set full` capture of one
+    benchmark batch (profiles/r02_kernel_traffic.json, written by tools/make_traffic_json.py)."""
+    path = os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")
     try:
         with open(path) as fp:
             d = json.load(fp)
-        return d if d.get("kernel") == kernel else None
+        e = d["ops"].get(kernel)
+        return None if e is None else dict(e, source=d["source"])
     except Exception:  # noqa: BLE001
         return None
 
@@ -485,15 +487,26 @@ def run_gpu(args):
                         "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
                         "note": "achieved = fp32-equivalent conv/GEMM FLOPs (2*MACs) per launch / CUDA-event time; split "
                                 "operands: three fp16 MMAs per product term, so the kernel's own ceiling is peak/3"}
+            if "recurrence" in dom_name:
+                roofline["note"] += ("; this operator is the GRU recurrence: T dependent timesteps of ~2 us each on 14 clusters of 8 "
+                                     "CTAs -- latency-bound by construction, see DESIGN.md 4.2; the conv stack's figure is in roofline_by_op")
             tr = measured_traffic(dom_name)
             if tr is not None:
-                roofline["traffic"] = tr["dram_bytes_per_algorithmic_byte"] * roofline["algorithmic_bytes_per_launch"]
-                roofline["traffic_source"] = ("DRAM bytes (read+write) per algorithmic byte = %.3f from " % tr["dram_bytes_per_algorithmic_byte"]
-                                              + tr["source"] + ", applied to this run's algorithmic bytes per launch")
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, " + tr["source"]
         else:
             achieved = dom["bytes"] / dom["launches"] / sec_per_launch / 1e9
             roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+
+    # the other operator classes with arithmetic (the dominant one can flip between the conv stack and the recurrence)
+    roofline_by_op = {}
+    for name, v in sorted(ops.items(), key=lambda kv: -kv[1]["ms"])[:6]:
+        if v["launches"] <= 0 or v["flops"] <= 0:
+            continue
+        ach = v["flops"] / (v["ms"] / 1e3) / 1e12
+        roofline_by_op[name] = {"ms_per_step": round(v["ms"] / n_prof, 3), "launches_per_step": v["launches"] / n_prof,
+                                "achieved_tflops": round(ach, 2), "frac_of_bf16_sustained": round(ach / peaks["bf16_tflops_sustained"], 4)}
 
     # ---- CPU baseline: oracle port on a bounded sample (rank 0, N = 1 only) ----
     cpu = None
@@ -525,7 +538,7 @@ def run_gpu(args):
                    "lines_per_page": stats["lines"] / max(1, BATCH * n_prof)},
         "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": res_e["h2d"], "d2h_bytes_per_step": res_e["d2h"],
                 "ms_per_step": ms_e2e / args.steps, "region_ms": reps_e},
-        "gpu_launches": res_r["launches"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "gpu_launches": res_r["launches"], "clocks": clocks, "roofline": roofline, "roofline_by_op": roofline_by_op, "cpu_baseline": cpu, "parity": parity,
         "region_ms": reps_r,
         "stage_ms_per_step": stage_ms, "host_ms_per_step": host_real, "host_ms_per_step_serial_profile": host_ms,
         "wall_ms_per_step": res_r["wall"] / args.steps,

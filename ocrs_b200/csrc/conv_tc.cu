@@ -544,6 +544,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
 //   * three hi*hi accumulators (see the halo kernel) and one accumulator per cross term, each of the three products
 //     of the split issued by its own thread.
 // k-blocks run in (kw, kh) order; promotion groups stay 128 K-elements (4 k-blocks of 32 channels).
+// Measured (profiles/r02t_conv_timers.log): ~6.0 k cycles per tile, of which the issuing threads wait < 0.7 k: the 54
+// MMAs of a tile take ~100 cycles each -- 6 KB of shared-memory operands per MMA of N = 64 in the 64-byte-swizzled
+// layout (32 channels = 64-byte rows) are delivered at ~60 B/clk, about half of what the 128-byte-swizzled operands
+// of the 128-channel layers get.  This layer is bound by shared-memory operand delivery, not by issue or by TMA.
 // ------------------------------------------------------------------------------------------
 template <int KC_, int COUT>
 struct ResCfg {
@@ -556,7 +560,7 @@ struct ResCfg {
   static constexpr int kGroupKb = 128 / kKC;
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 1024 + kBarBytes;
-  static constexpr int kTmemCols = 8 * COUT;      // HH[3] | X1 | X2 (5 x COUT, rounded up to a power of two)
+  static constexpr int kTmemCols = 8 * COUT;      // HH[3] | X1[2] | X2[2] (7 x COUT, rounded up to a power of two)
   static constexpr int kEpiWarps = 4 * (COUT / 32);
   static constexpr int kMmaWarps = 3;              // hi*hi, hi*lo, lo*hi: one issuing thread each
   static constexpr int kThreads = 32 * (kEpiWarps + 1 + kMmaWarps);
@@ -570,7 +574,8 @@ __global__ void __launch_bounds__((ResCfg<KC_, COUT>::kThreads), 1)
 conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                    const CUtensorMap* __restrict__ maps, const RaggedDesc* __restrict__ groups, int n_groups, int n_tiles,
                    int* __restrict__ counter, const float* __restrict__ bias, act_t* __restrict__ out_hi,
-                   act_t* __restrict__ out_lo, int Cin, int relu, int ph, int pw, float promo_scale, int* __restrict__ ovf) {
+                   act_t* __restrict__ out_lo, int Cin, int relu, int ph, int pw, float promo_scale, int* __restrict__ ovf,
+                   unsigned long long* __restrict__ dbg) {
   using C = ResCfg<KC_, COUT>;
   constexpr int KC = C::kKC;
   extern __shared__ uint8_t smem_raw[];
@@ -583,14 +588,16 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   const uint32_t aux = bar_base + 8u * (2 * C::kStages);
   auto hh_full = [&](int b) { return aux + 8u * b; };
   auto hh_empty = [&](int b) { return aux + 8u * (3 + b); };
-  auto x_full = [&](int i) { return aux + 8u * (6 + i); };   // i = 0: hi*lo accumulator, 1: lo*hi accumulator
-  auto x_empty = [&](int i) { return aux + 8u * (8 + i); };
-  const uint32_t b_full = aux + 8u * 10;
-  auto sched_full = [&](int s) { return aux + 8u * (11 + s); };
-  auto sched_empty = [&](int s) { return aux + 8u * (11 + kSched + s); };
-  const uint32_t tmem_slot = aux + 8u * (11 + 2 * kSched);
+  // cross-term accumulators: i = 0 hi*lo, 1 lo*hi; each double-buffered by tile parity tp (the promotion warps read
+  // them at the very end of a tile: with one buffer the cross-term threads idled ~1.0-1.4 k cycles per tile)
+  auto x_full = [&](int i, int tp) { return aux + 8u * (6 + 2 * i + tp); };
+  auto x_empty = [&](int i, int tp) { return aux + 8u * (10 + 2 * i + tp); };
+  const uint32_t b_full = aux + 8u * 14;
+  auto sched_full = [&](int s) { return aux + 8u * (15 + s); };
+  auto sched_empty = [&](int s) { return aux + 8u * (15 + kSched + s); };
+  const uint32_t tmem_slot = aux + 8u * (15 + 2 * kSched);
   const uint32_t ring = tmem_slot + 8u + ((tmem_slot + 8u) & 8u);  // 16-byte aligned
-  static_assert(8 * (2 * C::kStages + 11 + 2 * kSched) + 24 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
+  static_assert(8 * (2 * C::kStages + 15 + 2 * kSched) + 24 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
   TileEntry* ring_p = reinterpret_cast<TileEntry*>(smem_raw + (ring - smem0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -603,10 +610,11 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       mbar_init(hh_full(b), 1);
       mbar_init(hh_empty(b), C::kEpiWarps);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(x_full(i), 1);
-      mbar_init(x_empty(i), C::kEpiWarps);
-    }
+    for (int i = 0; i < 2; ++i)
+      for (int tp = 0; tp < 2; ++tp) {
+        mbar_init(x_full(i, tp), 1);
+        mbar_init(x_empty(i, tp), C::kEpiWarps);
+      }
     mbar_init(b_full, 1);
     for (int s = 0; s < kSched; ++s) {
       mbar_init(sched_full(s), 1);
@@ -635,9 +643,14 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       int cur_g = 0, last_map_g = -1;
       RaggedDesc gd = groups[0];
       int t = atomicAdd(counter, 1);
+      const bool timing = dbg != nullptr;
+      unsigned long long p_slot = 0, p_dec = 0, p_emp = 0;
+      const long long p_begin = timing ? clock64() : 0;
       for (uint32_t ti = 0;; ++ti) {
         const uint32_t slot = ti & (kSched - 1);
+        long long p0 = timing ? clock64() : 0;
         mbar_wait(sched_empty(slot), ((ti / kSched) & 1) ^ 1);
+        long long p1 = timing ? clock64() : 0;
         TileEntry e;
         e.g = -1;
         e.n = e.h0 = e.w0 = e.H = e.W = e.OH = e.OW = 0;
@@ -659,6 +672,10 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
         }
         ring_p[slot] = e;
         mbar_arrive(sched_full(slot));
+        if (timing) {
+          p_slot += (unsigned long long)(p1 - p0);
+          p_dec += (unsigned long long)(clock64() - p1);
+        }
         if (e.g < 0) break;
         const int t_next = atomicAdd(counter, 1);
         const CUtensorMap* m_hi = maps + 2 * e.g;
@@ -669,7 +686,9 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
           last_map_g = e.g;
         }
         for (int kw = 0; kw < 3; ++kw) {
+          long long p2 = timing ? clock64() : 0;
           mbar_wait(empty_bar(stage), par ^ 1);
+          if (timing) p_emp += (unsigned long long)(clock64() - p2);
           const uint32_t st = base + stage * C::kStageBytes;
           mbar_expect_tx(full_bar(stage), C::kStageBytes);
           tma_load_4d(st, m_hi, 0, e.w0 + kw - 1, e.h0 - 1, e.n, full_bar(stage));
@@ -677,6 +696,12 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
           if (++stage == C::kStages) { stage = 0; par ^= 1; }
         }
         t = t_next;
+      }
+      if (timing) {
+        atomicAdd(dbg + 10, p_slot);
+        atomicAdd(dbg + 11, p_dec);
+        atomicAdd(dbg + 12, p_emp);
+        atomicAdd(dbg + 13, (unsigned long long)(clock64() - p_begin));
       }
     }
   } else if (warp > C::kEpiWarps) {
@@ -689,24 +714,36 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       const int role = warp - (C::kEpiWarps + 1);
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
       uint32_t stage = 0, par = 0, hb = 0, hpar = 0;
-      const uint32_t d_x = tmem_base + (uint32_t)((2 + role) * COUT);  // role 1: column 3*COUT, role 2: 4*COUT
       mbar_wait(b_full, 0);
       const uint64_t db_base = make_desc<KC>(bres);
+      const bool timing = dbg != nullptr;
+      unsigned long long c_sched = 0, c_hhe = 0, c_full = 0, c_xe = 0, n_tiles_done = 0;
+      const long long t_begin = timing ? clock64() : 0;
       for (uint32_t ti = 0;; ++ti) {
         const uint32_t slot = ti & (kSched - 1);
+        long long c0 = timing ? clock64() : 0;
         mbar_wait(sched_full(slot), (ti / kSched) & 1);
+        if (timing) c_sched += (unsigned long long)(clock64() - c0);
         int g;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(g) : "r"(ring + slot * (uint32_t)sizeof(TileEntry)) : "memory");
         mbar_arrive(sched_empty(slot));
         if (g < 0) break;
+        const int tp = (int)(ti & 1);
+        // role 1: columns (3 + tp) * COUT, role 2: (5 + tp) * COUT
+        const uint32_t d_x = tmem_base + (uint32_t)((1 + 2 * role + tp) * COUT);
         if (role != 0) {
-          mbar_wait(x_empty(role - 1), (ti & 1) ^ 1);
+          long long x0 = timing ? clock64() : 0;
+          mbar_wait(x_empty(role - 1, tp), ((ti >> 1) & 1) ^ 1);
           tc_fence_after();
+          if (timing) c_xe += (unsigned long long)(clock64() - x0);
         }
+        ++n_tiles_done;
         int kbi = 0;
         for (int kw = 0; kw < 3; ++kw) {
+          long long w0 = timing ? clock64() : 0;
           mbar_wait(full_bar(stage), par);
           tc_fence_after();
+          if (timing) c_full += (unsigned long long)(clock64() - w0);
           const uint64_t d0 = make_desc<KC>(base + stage * C::kStageBytes);
 #pragma unroll 1
           for (int kh = 0; kh < 3; ++kh, ++kbi) {
@@ -715,8 +752,10 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
             if (role == 0) {
               const uint32_t d_hh = tmem_base + hb * COUT;
               if ((kbi & (C::kGroupKb - 1)) == 0) {
+                long long g0 = timing ? clock64() : 0;
                 mbar_wait(hh_empty(hb), hpar ^ 1);
                 tc_fence_after();
+                if (timing) c_hhe += (unsigned long long)(clock64() - g0);
               }
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k)
@@ -736,7 +775,17 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
           umma_commit(empty_bar(stage));
           if (++stage == C::kStages) { stage = 0; par ^= 1; }
         }
-        if (role != 0) umma_commit(x_full(role - 1));
+        if (role != 0) umma_commit(x_full(role - 1, tp));
+      }
+      if (timing) {
+        // per-role sums: [16 + 8 * role + ...]: tiles, ring, x_empty, hh_empty, operands, total
+        unsigned long long* o = dbg + 16 + 8 * role;
+        atomicAdd(o + 0, n_tiles_done);
+        atomicAdd(o + 1, c_sched);
+        atomicAdd(o + 2, c_xe);
+        atomicAdd(o + 3, c_hhe);
+        atomicAdd(o + 4, c_full);
+        atomicAdd(o + 5, (unsigned long long)(clock64() - t_begin));
       }
     }
   } else {
@@ -772,15 +821,16 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {  // + hi*lo, then + lo*hi
-        mbar_wait(x_full(i), ti & 1);
+        const int tp = (int)(ti & 1);
+        mbar_wait(x_full(i, tp), (ti >> 1) & 1);
         tc_fence_after();
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_base + (uint32_t)((3 + i) * COUT), r);
+        tmem_ld32(tmem_base + lane_base + (uint32_t)((3 + 2 * i + tp) * COUT), r);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(x_empty(i));
+        if (lane == 0) mbar_arrive(x_empty(i, tp));
       }
       epilogue_store<COUT>(acc, e, wq, hsel, lane, relu, ph, pw, true, bias, out_hi, out_lo, ovf);
     }
@@ -1334,7 +1384,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_co
       // ordered by the tcgen05 fences).
       // (Splitting the operand ring into an activation ring and a per-k-block weight ring, to issue loads two
       // boxes ahead, was slower: three more barrier waits per box cost more than the exposed latency they removed
-      // -- 1630 vs 1337 cycles per k-block, profiles/r02q_conv_split_rings_timers.log.)
+      // -- 1630 vs 1337 cycles per k-block, profiles/r02q_conv_split_rings_timers.log.  So was a second "full"
+      // barrier per stage for the kh = 1, 2 weight tiles, meant to start a stage's first MMAs before its last bytes
+      // have landed: 1192-1217 vs 1071-1107 cycles, profiles/r02s_conv_second_full_barrier_timers.log.  And two
+      // hi*hi + two cross-term accumulators instead of three + one: 1118-1171, profiles/r02v_conv_2hh2x_timers.log.)
       // c_format F32 (bit 4), a/b format F16, N >> 3 at 17, M >> 4 at 24 with M = 256 over the pair
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((256u >> 4) << 24);
       const int role = warp - (C::kEpiWarps + 1);
@@ -1815,11 +1868,34 @@ void launch_conv_res(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int 
   CUtensorMap tm_w_lo = make_map(w.w_lo.ptr, 2, wd, ws, wb, swz);
   OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_res_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   const int grid = std::max(1, std::min(n_tiles, sm_count()));
+  unsigned long long* d_dbg = nullptr;
+  if (conv_debug()) {
+    OCRS_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_dbg), 40 * sizeof(unsigned long long), st));
+    OCRS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 40 * sizeof(unsigned long long), st));
+  }
   conv3x3_res_kernel<KC, COUT><<<grid, C::kThreads, C::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, d_maps, d_groups, n_groups, n_tiles, d_counter,
                                                                          w.bias.as<float>(), y_hi, y_lo, Cin, relu, ph, pw, promo_scale(),
-                                                                         ovf);
+                                                                         ovf, d_dbg);
   count_launch();
   OCRS_CUDA_CHECK(cudaGetLastError());
+  if (d_dbg) {
+    unsigned long long h[40];
+    OCRS_CUDA_CHECK(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OCRS_CUDA_CHECK(cudaFreeAsync(d_dbg, st));
+    const double tl = (double)std::max<unsigned long long>(h[16], 1);
+    fprintf(stderr,
+            "[conv dbg RES] Cin %d Cout %d pool %dx%d: %llu tiles, %d CTAs | per TILE (cycles): producer: ring slot %.0f, decode %.0f, "
+            "stage waits %.0f, total %.0f",
+            Cin, COUT, ph, pw, h[16], grid, h[10] / tl, h[11] / tl, h[12] / tl, h[13] / tl);
+    const char* names[3] = {"hi*hi", "hi*lo", "lo*hi"};
+    for (int r = 0; r < 3; ++r) {
+      const unsigned long long* o = h + 16 + 8 * r;
+      fprintf(stderr, " | %s thread: ring %.0f, x_empty %.0f, hh_empty %.0f, operands %.0f, total %.0f", names[r], o[1] / tl, o[2] / tl,
+              o[3] / tl, o[4] / tl, o[5] / tl);
+    }
+    fprintf(stderr, "\n");
+  }
 }
 
 template <int KC, int COUT>

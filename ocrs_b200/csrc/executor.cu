@@ -1571,12 +1571,19 @@ DTensor Model::run_seq_head(const float* X, int64_t rows, const std::vector<Pack
       lines[i].y_tstride = (int64_t)ls[i].N * 2 * H;
     }
     auto y_store = std::make_shared<Storage>((size_t)rows * 2 * H * 4, st);
-    int tk = prof ? prof->begin(prof_prefix + "GRU(packed)", st) : -1;
+    // two profiler entries: the input projection of all timesteps (split + GEMM) and the recurrence
+    const double f_proj = 2.0 * w.D * (double)rows * 3.0 * H * w.I, f_rec = 2.0 * w.D * (double)rows * 3.0 * H * H;
+    int tk = prof ? prof->begin(prof_prefix + "GRU input projection(packed)", st) : -1;
+    const std::function<void()> mark = [&] {
+      if (prof) {
+        prof->end(tk, st, f_proj);
+        tk = prof->begin(prof_prefix + "GRU recurrence(packed)", st);
+      }
+    };
     tc::gru_forward_lines(cur, rows, w, lines.data(), (int)lines.size(), reinterpret_cast<float*>(y_store->ptr), H, rev,
-                          alloc, st);
-    double f = 2.0 * w.D * (double)rows * 3.0 * H * (w.I + H);
-    flops += f;
-    if (prof) prof->end(tk, st, f);
+                          alloc, st, &mark);
+    flops += f_proj + f_rec;
+    if (prof) prof->end(tk, st, f_rec);
     cur_store = y_store;
     cur = reinterpret_cast<const float*>(y_store->ptr);
   }

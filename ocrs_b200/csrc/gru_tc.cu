@@ -50,7 +50,9 @@ __global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restr
 //   warp 0   TMA producer: K chunks of 32 (64-byte-swizzled rows), 5 stages of 32 KB;
 //   warp 1   MMA issuer: hi*hi + hi*lo + lo*hi into one of TWO tensor-memory accumulators (128 columns each), so
 //            the MMAs of tile i+1 run while tile i is drained;
-//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time, + bias, through a 128B-swizzled shared-memory staging
+//   warps 2-9 epilogue (lane quadrant = warp % 4, column half = (warp - 2) / 4; with four warps the K = 128
+//            projection was bound by the drain of its 64 KB tiles): tcgen05.ld 32 columns at a time, + bias, through a
+//            128B-swizzled shared-memory staging
 //            tile so that every global store instruction writes whole 128-byte lines (a thread owns a ROW of the
 //            accumulator; storing straight from registers writes 16-byte pieces 6 KB apart).
 // (The first form -- one tile per CTA, two CTAs per SM, the same four warps loading, issuing and storing in turn --
@@ -72,7 +74,7 @@ constexpr int kGemmStages = 5;
 constexpr int kGemmBK = 32;
 constexpr int kGemmTile = 128 * kGemmBK * 2;            // one operand plane of one stage (8 KB)
 constexpr int kGemmStageBytes = 4 * kGemmTile;          // A_hi, A_lo, B_hi, B_lo
-constexpr int kGemmEpiWarps = 4;
+constexpr int kGemmEpiWarps = 8;                        // two per TMEM lane quadrant, 64 columns each
 constexpr int kGemmStagingBytes = 32 * 128;             // per epilogue warp: 32 rows x 32 floats
 constexpr int kGemmThreads = 32 * (2 + kGemmEpiWarps);
 constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + kGemmEpiWarps * kGemmStagingBytes + 1024 + 256;
@@ -159,8 +161,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
     }
   } else {
-    // epilogue warp: TMEM lane quadrant q = warp % 4 (rows 32q .. 32q+31 of the tile)
-    const int q = warp & 3;
+    // epilogue warp: TMEM lane quadrant q = warp % 4 (rows 32q .. 32q+31 of the tile), columns [64 * half, 64 * half + 64)
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t stg = staging0 + (uint32_t)(warp - 2) * kGemmStagingBytes;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
@@ -169,10 +171,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       mbar_wait(acc_full(a), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 128 + (uint32_t)c0, r);
-        if (c0 == 96) {  // the accumulator is in registers: hand it back before the stores
+        if (c0 == 64 * half + 32) {  // this warp's part of the accumulator is in registers: hand it back before the stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty(a));
@@ -520,6 +522,7 @@ constexpr int kSliceTile = NL * 64;            // one plane of one slice: [NL][3
 constexpr int kSliceBoth = 2 * kSliceTile;     // hi | lo
 constexpr int kHBuf3 = kCl * kSliceBoth;       // 32 KB
 constexpr int kMmaWarps3 = 4;
+constexpr int kGruRegsDefault = 96;
 constexpr int kCl3Threads = kGateThreads + 32 * kMmaWarps3;
 constexpr int kCl3Smem = 2 * kHBuf3 + kExBytes + 1024 + 512;
 
@@ -528,7 +531,13 @@ __device__ __forceinline__ uint32_t sw64_off(int l, int u) {
   return (uint32_t)(l * 64 + ((((u >> 3) ^ (l >> 1)) & 3) << 4) + (u & 7) * 2);
 }
 
-__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kCl3Threads, 1)
+// Register cap as a template parameter (OCRS_B200_GRU_REGS = 64 | 72 | 80 | 96, default 96).  The idea behind the
+// smaller caps -- 640 threads x 96 registers leave no room on the SM for the light kernels of the other batches in
+// flight, while the recurrence keeps its 112 SMs mostly idle -- did not pay: each step got slower (3.85 k -> 4.3 k
+// cycles at 64 registers) and the step time of the pipeline did not improve (7.74 / 7.71 / 7.75 / 7.82 ms per step at
+// 96 / 80 / 72 / 64 registers with three batches in flight, 7.34 / 7.36 / 7.44 / 7.51 with four).
+template <int kRegs>
+__global__ void __cluster_dims__(kCl, 1, 1) __maxnreg__(kRegs)
 gru_cluster3_kernel(const __nv_bfloat16* __restrict__ r_hi_g, const __nv_bfloat16* __restrict__ r_lo_g,
                     const float* __restrict__ xw, const float* __restrict__ rb, const float* __restrict__ h0,
                     float* __restrict__ Y, float* __restrict__ Yh, const SeqLine* __restrict__ lines, int n_lines,
@@ -791,10 +800,17 @@ void launch_recurrence(const GruWeightsTC& w, const float* xw, const float* h0, 
                                                           h0, Y, Yh, d_desc, n_lines, w.D, y_dstride, reverse[0],
                                                           w.D > 1 ? reverse[1] : 0, d_dbg);
   } else {
-    OCRS_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCl3Smem));
-    gru_cluster3_kernel<<<grid, kCl3Threads, kCl3Smem, st>>>(w.r_hi.as<__nv_bfloat16>(), w.r_lo.as<__nv_bfloat16>(), xw,
-                                                             w.rb.as<float>(), h0, Y, Yh, d_desc, n_lines, w.D, y_dstride,
-                                                             reverse[0], w.D > 1 ? reverse[1] : 0, d_dbg);
+    // register cap of the recurrent kernel (see its comment); OCRS_B200_GRU_REGS = 64 | 72 | 80 | 96 for experiments
+    static const int regs = [] { const char* e = std::getenv("OCRS_B200_GRU_REGS"); return e ? std::atoi(e) : kGruRegsDefault; }();
+    auto launch = [&](auto kern) {
+      OCRS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCl3Smem));
+      kern<<<grid, kCl3Threads, kCl3Smem, st>>>(w.r_hi.as<__nv_bfloat16>(), w.r_lo.as<__nv_bfloat16>(), xw, w.rb.as<float>(), h0, Y, Yh,
+                                               d_desc, n_lines, w.D, y_dstride, reverse[0], w.D > 1 ? reverse[1] : 0, d_dbg);
+    };
+    if (regs == 64) launch(gru_cluster3_kernel<64>);
+    else if (regs == 72) launch(gru_cluster3_kernel<72>);
+    else if (regs == 80) launch(gru_cluster3_kernel<80>);
+    else launch(gru_cluster3_kernel<96>);
   }
   count_launch();
 }
@@ -934,7 +950,8 @@ void gru_forward(const float* X, const GruWeightsTC& w, const float* h0, float* 
 }
 
 void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, const SeqLine* lines_host, int n_lines,
-                       float* Y, int64_t y_dstride, const int* reverse, const ScratchAlloc& alloc, cudaStream_t st) {
+                       float* Y, int64_t y_dstride, const int* reverse, const ScratchAlloc& alloc, cudaStream_t st,
+                       const std::function<void()>* after_projection) {
   if (rows == 0 || n_lines == 0) return;
   const int D = w.D, H = w.H, I = w.I;
   const int Ntot = D * 3 * H;
@@ -958,6 +975,7 @@ void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, cons
     gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, w.wb.as<float>(), xw, (int)rows, Ntot, I);
     count_launch();
   }
+  if (after_projection != nullptr && *after_projection) (*after_projection)();
   const int n_tiles = (int)ceil_div(n_lines, NL);
   std::vector<SeqLine> desc((size_t)n_tiles * NL);
   for (int i = 0; i < n_tiles * NL; ++i) {

@@ -62,8 +62,11 @@ struct SeqLine {
 
 // Ragged GRU layer over `rows` packed input rows X [rows, I]: writes Y with the strides given per line.
 // `lines` must be ordered by T descending (tiles of 32 lines run max-T steps).
+// `after_projection` (optional) is called between the launch of the input-projection GEMM and the recurrent kernel
+// (the executor's profiler times the two separately).
 void gru_forward_lines(const float* X, int64_t rows, const GruWeightsTC& w, const SeqLine* lines_host, int n_lines,
-                       float* Y, int64_t y_dstride, const int* reverse, const ScratchAlloc& alloc, cudaStream_t st);
+                       float* Y, int64_t y_dstride, const int* reverse, const ScratchAlloc& alloc, cudaStream_t st,
+                       const std::function<void()>* after_projection = nullptr);
 
 }  // namespace tc
 }  // namespace ocrs
