@@ -158,6 +158,7 @@ Engine::~Engine() {
   rec_.reset();
   if (ev_a_) cudaEventDestroy(ev_a_);
   if (ev_copy_) cudaEventDestroy(ev_copy_);
+  if (ev_wait_) cudaEventDestroy(ev_wait_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   for (auto e : aux_done_) cudaEventDestroy(e);
   for (auto s2 : aux_) cudaStreamDestroy(s2);
@@ -179,7 +180,21 @@ void Engine::ensure_aux(int n) {
 
 void Engine::synchronize() {
   OCRS_CUDA_CHECK(cudaSetDevice(device_));
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  wait_stream();
+}
+
+// Host wait for everything queued on the engine's stream.  Spinning (cudaStreamSynchronize) has the lowest latency
+// and is right for a single engine; the pool's workers -- up to ten per GPU, most of their time waiting for their
+// batch -- block on an event created with cudaEventBlockingSync instead, so that a waiting worker does not hold a
+// host core (eight ranks x ten workers would otherwise spin on 80 of the box's cores).
+void Engine::wait_stream() {
+  if (!blocking_sync_) {
+    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+    return;
+  }
+  if (!ev_wait_) OCRS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_wait_, cudaEventBlockingSync | cudaEventDisableTiming));
+  OCRS_CUDA_CHECK(cudaEventRecord(ev_wait_, st_));
+  OCRS_CUDA_CHECK(cudaEventSynchronize(ev_wait_));
 }
 
 void Engine::set_profiling(bool on) {
@@ -190,7 +205,7 @@ void Engine::set_profiling(bool on) {
 std::string Engine::profile_json(bool reset) {
   std::lock_guard<std::mutex> lk(mu_);
   OCRS_CUDA_CHECK(cudaSetDevice(device_));
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  wait_stream();
   prof_.collect();
   std::string j = "{";
   bool first = true;
@@ -364,7 +379,7 @@ std::vector<float> Engine::detect_text_pixels(const OcrInput& in) {
   int tok = det_->tc_token();
   DTensor out = det_->run(wrap_tensor(det_in_.as<float>(), {1, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_);
   if (tok) {  // tensor-core chains in the detection model: check the fp16 range flag, rerun in fp32 if raised
-    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+    wait_stream();
     if (det_->take_tc_overflow(tok)) out = det_->run(wrap_tensor(det_in_.as<float>(), {1, shp[1] < 0 ? 1 : shp[1], in_h, in_w}), st_);
   }
   OCRS_CHECK(out.shape.size() == 4 && out.numel() == (int64_t)in_h * in_w, kWrongOutput,
@@ -375,7 +390,7 @@ std::vector<float> Engine::detect_text_pixels(const OcrInput& in) {
                         s.mask.as<uint8_t>(), H, W, text_threshold_, st_);
   std::vector<float> host((size_t)H * W);
   OCRS_CUDA_CHECK(cudaMemcpyAsync(host.data(), s.prob.ptr, host.size() * 4, cudaMemcpyDeviceToHost, st_));
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  wait_stream();
   return host;
 }
 
@@ -474,7 +489,7 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
       d2h_bytes_ += 32;
     }
   }
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  wait_stream();
   std::vector<std::vector<int32_t>> roots((size_t)N);
   for (int i = 0; i < N; ++i) {
     const int32_t* c = h_counters + 8 * i;
@@ -491,7 +506,7 @@ std::vector<std::vector<RotatedRect>> Engine::detect_words_locked(const std::vec
       d2h_bytes_ += (int64_t)n * (sizeof(RotatedRect) + 4);
     }
   }
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  wait_stream();
   for (int i = 0; i < N; ++i) {
     // restore contour discovery (raster) order: layout depends on it (layout_analysis.rs:116-119)
     size_t n = result[i].size();
@@ -633,7 +648,7 @@ std::vector<std::vector<TextLine>> Engine::recognize_text_locked(
   // host vectors must outlive the async copies
   {
     HostTimer ht(this, "rec_sync_after_crop");
-    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+    wait_stream();
   }
   auto ht_launch = std::make_unique<HostTimer>(this, "rec_enqueue_networks");
 
@@ -830,7 +845,7 @@ std::vector<std::vector<TextLine>> Engine::recognize_text_locked(
   ht_launch.reset();
   {
     HostTimer ht(this, "rec_sync_wait_gpu");
-    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+    wait_stream();
   }
   HostTimer ht_asm(this, "rec_assemble_text");
 
@@ -909,7 +924,7 @@ std::vector<float> Engine::prepare_recognition_input(const OcrInput& in, const s
                   cross_.as<int32_t>(), rec_batch_.as<float>(), rec_h, (int)rw, d.lh, st_);
   std::vector<float> out((size_t)rec_h * rw);
   OCRS_CUDA_CHECK(cudaMemcpyAsync(out.data(), rec_batch_.ptr, out.size() * 4, cudaMemcpyDeviceToHost, st_));
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  wait_stream();
   *out_h = rec_h;
   *out_w = (int)rw;
   return out;
@@ -944,7 +959,7 @@ std::vector<Engine::TextPixels> Engine::detect_text_pixels_batch(const std::vect
   const int tok = det_->tc_token();
   DTensor out = run_net();
   if (tok) {
-    OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+    wait_stream();
     if (det_->take_tc_overflow(tok)) out = run_net();
   }
   OCRS_CHECK(out.shape.size() == 4 && out.numel() == (int64_t)N * plane, kWrongOutput, "detection output must be [N,1,H,W]");
@@ -969,7 +984,7 @@ std::vector<Engine::TextPixels> Engine::detect_text_pixels_batch(const std::vect
       d2h_bytes_ += (int64_t)hw;
     }
   }
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  wait_stream();
   return result;
 }
 
@@ -1032,7 +1047,7 @@ Engine::LineImages Engine::prepare_recognition_inputs(const OcrInput& in,
   out.images.resize((size_t)dst_total);
   OCRS_CUDA_CHECK(cudaMemcpyAsync(out.images.data(), rec_batch_.ptr, out.images.size() * 4, cudaMemcpyDeviceToHost, st_));
   d2h_bytes_ += dst_total * 4;
-  OCRS_CUDA_CHECK(cudaStreamSynchronize(st_));
+  wait_stream();
   return out;
 }
 

@@ -133,6 +133,8 @@ class Engine {
   void synchronize();
   // host threads used by ocr_pages for layout analysis (pages of a batch in parallel); default 8
   void set_layout_threads(int n) { layout_threads_ = n < 1 ? 1 : n; }
+  // host waits block on an event instead of spinning (the pool sets this for its workers)
+  void set_blocking_sync(bool on) { blocking_sync_ = on; }
 
   // CUDA-event profiling of stages and of every operator of the two networks
   void set_profiling(bool on);
@@ -170,6 +172,9 @@ class Engine {
   std::vector<cudaStream_t> aux_;       // per-page side streams for detection post-processing
   std::vector<cudaEvent_t> aux_done_;
   cudaEvent_t ev_fork_ = nullptr;
+  cudaEvent_t ev_wait_ = nullptr;
+  bool blocking_sync_ = false;
+  void wait_stream();
   void ensure_aux(int n);
   int64_t d2h_bytes_ = 0, h2d_bytes_ = 0;
   int layout_threads_ = 8;

@@ -535,7 +535,9 @@ __device__ __forceinline__ uint32_t sw64_off(int l, int u) {
 // smaller caps -- 640 threads x 96 registers leave no room on the SM for the light kernels of the other batches in
 // flight, while the recurrence keeps its 112 SMs mostly idle -- did not pay: each step got slower (3.85 k -> 4.3 k
 // cycles at 64 registers) and the step time of the pipeline did not improve (7.74 / 7.71 / 7.75 / 7.82 ms per step at
-// 96 / 80 / 72 / 64 registers with three batches in flight, 7.34 / 7.36 / 7.44 / 7.51 with four).
+// 96 / 80 / 72 / 64 registers with three batches in flight, 7.34 / 7.36 / 7.44 / 7.51 with four).  With ten batches in
+// flight the capped variants showed occasional timed regions 1.5-5x longer than the rest (light kernels of other
+// batches sharing the recurrence's SMs), the 96-register kernel none: profiles/r02aa_bench_r*.json.
 template <int kRegs>
 __global__ void __cluster_dims__(kCl, 1, 1) __maxnreg__(kRegs)
 gru_cluster3_kernel(const __nv_bfloat16* __restrict__ r_hi_g, const __nv_bfloat16* __restrict__ r_lo_g,

@@ -3,6 +3,8 @@
 // conv_tc.cu / gru_tc.cu when those are enabled (DESIGN.md "Kernels").
 #include "nn_kernels.h"
 
+#include <cstdlib>
+
 #include <cfloat>
 
 #include "common.h"
@@ -285,6 +287,92 @@ __global__ void __launch_bounds__(128) dwpw_pixel_kernel(SepParams p) {
     float v = acc[k];
     if (p.relu) v = fmaxf(v, 0.f);
     yn[(int64_t)k * ohw] = v;
+  }
+}
+
+// Two vertically adjacent output pixels per thread: their 3x3 windows share rows (S + 3 input rows instead of 6), so a
+// channel costs 12 (stride 1) or 15 (stride 2) loads instead of 18, and the depthwise / pointwise weights are read
+// from shared memory once for both pixels.  Consecutive threads are consecutive pixels of a row, as in the
+// one-pixel kernel, so loads and stores stay coalesced.  Per pixel the arithmetic (order of the FMAs) is unchanged.
+template <int KOUT, int S>
+__global__ void __launch_bounds__(128) dwpw_pixel2_kernel(SepParams p) {
+  constexpr int R = S + 3;  // input rows of the pair
+  extern __shared__ float sm[];
+  float* s_dw = sm;                   // [C][9]
+  float* s_db = s_dw + p.C * 9;       // [C]
+  float* s_pw = s_db + p.C;           // [C][KOUT]  (transposed for broadcast reads)
+  float* s_pb = s_pw + p.C * KOUT;    // [KOUT]
+  for (int i = threadIdx.x; i < p.C * 9; i += blockDim.x) s_dw[i] = p.dw_w[i];
+  for (int i = threadIdx.x; i < p.C; i += blockDim.x) s_db[i] = p.dw_b ? p.dw_b[i] : 0.f;
+  for (int i = threadIdx.x; i < p.C * KOUT; i += blockDim.x) {
+    int c = i / KOUT, k = i - c * KOUT;
+    s_pw[i] = p.pw_w[k * p.C + c];
+  }
+  for (int i = threadIdx.x; i < KOUT; i += blockDim.x) s_pb[i] = p.pw_b ? p.pw_b[i] : 0.f;
+  __syncthreads();
+  const int ohw = p.OH * p.OW;
+  const int pairs = ((p.OH + 1) / 2) * p.OW;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (idx >= pairs) return;
+  const int oy = 2 * (idx / p.OW), ox = idx % p.OW;
+  const bool second = oy + 1 < p.OH;
+  float acc0[KOUT], acc1[KOUT];
+#pragma unroll
+  for (int k = 0; k < KOUT; ++k) acc0[k] = acc1[k] = s_pb[k];
+  const int iy0 = oy * S - 1, ix0 = ox * S - 1;
+  int c = 0;
+#pragma unroll 1
+  for (int si = 0; si < p.n_src; ++si) {
+    const SepSrc s = p.src[si];
+    const float* xs = s.x + (int64_t)n * s.C * s.H * s.W;
+    // tap validity is the same for every channel of the source
+    bool inside[R * 3], real[R * 3];
+    int off[R * 3];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int iy = iy0 + r, ix = ix0 + q;
+        inside[r * 3 + q] = iy >= 0 && iy < p.Hv && ix >= 0 && ix < p.Wv;
+        real[r * 3 + q] = inside[r * 3 + q] && iy < s.H && ix < s.W;
+        off[r * 3 + q] = iy * s.W + ix;
+      }
+    for (int cs = 0; cs < s.C; ++cs, ++c) {
+      const float* xc = xs + (int64_t)cs * s.H * s.W;
+      const float* wd = s_dw + c * 9;
+      float x[R * 3];
+#pragma unroll
+      for (int t = 0; t < R * 3; ++t) x[t] = real[t] ? __ldg(xc + off[t]) : (inside[t] ? s.pad : 0.f);
+      float w9[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) w9[t] = wd[t];
+      float v0 = s_db[c], v1 = v0;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        v0 = fmaf(x[t], w9[t], v0);
+        v1 = fmaf(x[S * 3 + t], w9[t], v1);
+      }
+      const float* wp = s_pw + c * KOUT;
+#pragma unroll
+      for (int k = 0; k < KOUT; ++k) {
+        const float w = wp[k];
+        acc0[k] = fmaf(v0, w, acc0[k]);
+        acc1[k] = fmaf(v1, w, acc1[k]);
+      }
+    }
+  }
+  float* yn = p.y + (int64_t)n * KOUT * ohw + (int64_t)oy * p.OW + ox;
+#pragma unroll
+  for (int k = 0; k < KOUT; ++k) {
+    float v = acc0[k];
+    if (p.relu) v = fmaxf(v, 0.f);
+    yn[(int64_t)k * ohw] = v;
+    if (second) {
+      float u = acc1[k];
+      if (p.relu) u = fmaxf(u, 0.f);
+      yn[(int64_t)k * ohw + p.OW] = u;
+    }
   }
 }
 
@@ -776,11 +864,25 @@ void launch_sep(const SepParams& p, cudaStream_t st) {
   // bits whether it runs alone or in a batch of eight
   if (p.mode == 0 && p.C <= 64 && (p.KO == 8 || p.KO == 16 || p.KO == 32) && (int64_t)p.OH * p.OW >= 4096) {
     // shallow levels: thread per pixel
-    dim3 grid((unsigned)ceil_div((int64_t)p.OH * p.OW, 128), (unsigned)p.N);
     const size_t smem = (size_t)(p.C * 9 + p.C + p.C * p.KO + p.KO) * sizeof(float);
-    if (p.KO == 8) dwpw_pixel_kernel<8><<<grid, 128, smem, st>>>(p);
-    else if (p.KO == 16) dwpw_pixel_kernel<16><<<grid, 128, smem, st>>>(p);
-    else dwpw_pixel_kernel<32><<<grid, 128, smem, st>>>(p);
+    static const bool one_px = std::getenv("OCRS_B200_DWPW_ONE_PIXEL") != nullptr;  // the one-pixel-per-thread form
+    if (!one_px && (p.stride == 1 || p.stride == 2)) {
+      dim3 grid((unsigned)ceil_div((int64_t)((p.OH + 1) / 2) * p.OW, 128), (unsigned)p.N);
+      if (p.stride == 1) {
+        if (p.KO == 8) dwpw_pixel2_kernel<8, 1><<<grid, 128, smem, st>>>(p);
+        else if (p.KO == 16) dwpw_pixel2_kernel<16, 1><<<grid, 128, smem, st>>>(p);
+        else dwpw_pixel2_kernel<32, 1><<<grid, 128, smem, st>>>(p);
+      } else {
+        if (p.KO == 8) dwpw_pixel2_kernel<8, 2><<<grid, 128, smem, st>>>(p);
+        else if (p.KO == 16) dwpw_pixel2_kernel<16, 2><<<grid, 128, smem, st>>>(p);
+        else dwpw_pixel2_kernel<32, 2><<<grid, 128, smem, st>>>(p);
+      }
+    } else {
+      dim3 grid((unsigned)ceil_div((int64_t)p.OH * p.OW, 128), (unsigned)p.N);
+      if (p.KO == 8) dwpw_pixel_kernel<8><<<grid, 128, smem, st>>>(p);
+      else if (p.KO == 16) dwpw_pixel_kernel<16><<<grid, 128, smem, st>>>(p);
+      else dwpw_pixel_kernel<32><<<grid, 128, smem, st>>>(p);
+    }
     count_launch();
     OCRS_CHECK(cudaGetLastError() == cudaSuccess, kCuda, "dwpw_pixel_kernel launch failed");
     return;

@@ -1,6 +1,8 @@
 // Engine pool (see pool.h).
 #include "pool.h"
 
+#include <cstdlib>
+
 #include <pthread.h>
 #include <sched.h>
 
@@ -97,6 +99,11 @@ Pool::Pool(const PoolParams& p) {
       ep.device = devices_[d];
       w->engine = std::make_shared<Engine>(ep);
       w->engine->set_layout_threads(p.layout_threads);
+      {
+        // workers wait for their batch without holding a core; OCRS_B200_SPIN_SYNC=1 keeps the spinning wait
+        static const bool spin = [] { const char* e = std::getenv("OCRS_B200_SPIN_SYNC"); return e != nullptr && e[0] == '1'; }();
+        w->engine->set_blocking_sync(!spin);
+      }
       workers_.push_back(std::move(w));
     }
   for (auto& w : workers_) w->thread = std::thread([this, wp = w.get()] { run_worker(wp); });
