@@ -159,7 +159,7 @@ def measured_traffic(kernel: str):
         with open(path) as fp:
             d = json.load(fp)
         e = d["ops"].get(kernel)
-        return None if e is None else dict(e, source=d["source"])
+        return None if e is None else dict(e, source=e.get("source", d["source"]))
     except Exception:  # noqa: BLE001
         return None
 

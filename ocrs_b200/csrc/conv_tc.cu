@@ -842,6 +842,278 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
+// Weights-stationary, transposed form for the 32 -> 64 layer with a fused 2x2 pool (`conv3x3_ws_kernel`).
+// The resident-weights kernel above is bound by shared-memory operand delivery: an MMA of N = 64 reads 4 KB of
+// pixels + 2 KB of weights (64-byte-swizzled rows, ~60 B/clk) for 32 cycles of tensor work.  Here the roles are swapped,
+// D^T[c_out][pixel] = W x X^T:
+//   * A = [W_hi (64 rows); W_lo (64 rows)] of all nine taps lives in TENSOR MEMORY (lane = row, 144 columns), loaded
+//     once per CTA -- no shared-memory reads for it at all;
+//   * B = the activation box in shared memory (128 pixels x 16 channels = 4 KB per MMA of 64 cycles);
+//   * TWO MMAs per 16 K-elements instead of three:  [W_hi; W_lo] x X_hi  ->  D1 = [hi*hi ; lo*hi]  (lanes 0-63 / 64-127)
+//                                                    [W_hi;  .  ] x X_lo  ->  D2 = [hi*lo ;  .   ]
+//     one issuing thread per accumulator.
+// Tensor memory: A 160 + D1 128 + D2 128 columns.  There is no room for the promotion double buffer (that would be 528
+// columns), and this layer does not need it: K = 288 is 18 MMAs per accumulator, i.e. a truncation bias of at most
+// 9 ulp of the running sum (the promotion exists for the K = 576 / 1152 layers); the expected bias is scaled out like
+// in the other kernels.  The accumulators are single-buffered: the MMAs of the next tile wait until the 16 epilogue
+// warps have pulled the tile into registers (a bubble of a few hundred cycles per tile), the epilogue arithmetic and
+// stores then overlap the next tile's MMAs.  A first version with N = 64 and the promotion protocol was parity-green but
+// slower than the resident-weights kernel (per-tile fixed costs; profiles/r02ad_ws_kernel.md).
+// Output lanes are channels and registers are pixels: warp (lane quadrant q, pixel chunk pc) holds channel
+// 32*(q%2) + lane for tile rows 2pc, 2pc+1 -- one 2x2 pooling row pair, so the pool is a max over registers.  The lo*hi
+// sums (quadrants 2, 3) reach the warps that own the channel (quadrants 0, 1) through shared memory, double-buffered
+// by tile parity, one named barrier per warp pair.
+// ------------------------------------------------------------------------------------------
+struct WsCfg {
+  static constexpr int kKC = 32, kCout = 64, kN = kTH * kTW;                   // 128 pixels
+  static constexpr int kABox = (kTH + 2) * kTW * kKC * 2;                      // one plane of the 10 x 16 pixel box: 10 KB
+  static constexpr int kStageBytes = 2 * kABox;
+  static constexpr int kStages = 4;
+  static constexpr int kXchBytes = 2 * 2 * 4 * 32 * 32 * 4;                    // [parity][channel half][pixel chunk][px][lane] f32
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kXchBytes + 1024 + kBarBytes;
+  static constexpr int kColA = 0, kColD1 = 192, kColD2 = 320, kTmemCols = 512;  // A: 144 (5 x 32 stored) | D1 128 | D2 128
+  static constexpr int kEpiWarps = 16;
+  static constexpr int kThreads = 32 * (kEpiWarps + 3);                         // + TMA / scheduler, D1 issuer, D2 issuer
+  static_assert(kABox % 512 == 0, "box planes must keep the 64-byte swizzle phase");
+};
+
+__global__ void __launch_bounds__(WsCfg::kThreads, 1)
+conv3x3_ws_kernel(const CUtensorMap* __restrict__ maps, const RaggedDesc* __restrict__ groups, int n_groups, int n_tiles,
+                  int* __restrict__ counter, const act_t* __restrict__ w_hi, const act_t* __restrict__ w_lo,
+                  const float* __restrict__ bias, act_t* __restrict__ out_hi, act_t* __restrict__ out_lo, int relu,
+                  float debias_scale, int* __restrict__ ovf) {
+  using C = WsCfg;
+  constexpr int KC = C::kKC, COUT = C::kCout;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t base = (smem0 + 1023u) & ~1023u;
+  const uint32_t xch = base + C::kStages * C::kStageBytes;
+  const uint32_t bar_base = xch + C::kXchBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  const uint32_t aux = bar_base + 8u * (2 * C::kStages);
+  const uint32_t d1_full = aux, d1_empty = aux + 8u, d2_full = aux + 16u, d2_empty = aux + 24u;
+  auto sched_full = [&](int s) { return aux + 8u * (4 + s); };
+  auto sched_empty = [&](int s) { return aux + 8u * (4 + kSched + s); };
+  const uint32_t tmem_slot = aux + 8u * (4 + 2 * kSched);
+  const uint32_t ring = tmem_slot + 16u;
+  static_assert(8 * (2 * C::kStages + 4 + 2 * kSched) + 16 + kSched * (int)sizeof(TileEntry) <= C::kBarBytes, "barrier area");
+  TileEntry* ring_p = reinterpret_cast<TileEntry*>(smem_raw + (ring - smem0));
+  float* xch_p = reinterpret_cast<float*>(smem_raw + (xch - smem0));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 2);  // one commit per issuing thread
+    }
+    mbar_init(d1_full, 1);
+    mbar_init(d1_empty, C::kEpiWarps);
+    mbar_init(d2_full, 1);
+    mbar_init(d2_empty, C::kEpiWarps / 2);  // only the channel-owning warps read D2
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(sched_full(s), 1);
+      mbar_init(sched_empty(s), C::kEpiWarps + 2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == C::kEpiWarps) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // ---- one-time: the weights become the MMA A operand in tensor memory.  Lane = row (quadrants 0, 1: W_hi rows
+    // 0..63; quadrants 2, 3: W_lo rows 0..63), columns = packed fp16 pairs along k = tap * 32 + channel (144 words).
+    const act_t* src = (warp < 2 ? w_hi : w_lo) + (size_t)((warp & 1) * 32 + lane) * (9 * KC);
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);  // a row is 576 B = 36 x 16 B
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)C::kColA;
+#pragma unroll 1
+    for (int c = 0; c < 5; ++c) {  // 5 x 32 columns; the last 16 of the 160 are padding
+      uint32_t r[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = c * 8 + j;
+        const uint4 v = q < 36 ? __ldg(src4 + q) : make_uint4(0, 0, 0, 0);
+        r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+      }
+      tmem_st32(lane_base + (uint32_t)(c * 32), r);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // c_format F32 (bit 4), a/b format F16, N >> 3 at 17, M >> 4 at 24
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(C::kN >> 3) << 17) | ((128u >> 4) << 24);
+
+  if (warp == C::kEpiWarps) {
+    if (lane == 0) {
+      // ---------------- tile scheduler + TMA producer ----------------
+      uint32_t stage = 0, par = 0;
+      int cur_g = 0, last_map_g = -1;
+      RaggedDesc gd = groups[0];
+      int t = atomicAdd(counter, 1);
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        mbar_wait(sched_empty(slot), ((ti / kSched) & 1) ^ 1);
+        TileEntry e;
+        e.g = -1;
+        e.n = e.h0 = e.w0 = e.H = e.W = e.OH = e.OW = 0;
+        e.out_off = 0;
+        e.pad = 0;
+        if (t < n_tiles) {
+          while (cur_g + 1 < n_groups && __ldg(&groups[cur_g + 1].first) <= t) {
+            ++cur_g;
+            gd = groups[cur_g];
+          }
+          int l = t - gd.first;
+          e.g = cur_g;
+          e.w0 = (l % gd.tiles_w) * kTW;
+          l /= gd.tiles_w;
+          e.h0 = (l % gd.tiles_h) * kTH;
+          e.n = l / gd.tiles_h;
+          e.H = gd.H; e.W = gd.W; e.OH = gd.OH; e.OW = gd.OW;
+          e.out_off = gd.out_off;
+        }
+        ring_p[slot] = e;
+        mbar_arrive(sched_full(slot));
+        if (e.g < 0) break;
+        const int t_next = atomicAdd(counter, 1);
+        const CUtensorMap* m_hi = maps + 2 * e.g;
+        const CUtensorMap* m_lo = m_hi + 1;
+        if (e.g != last_map_g) {
+          fence_tensormap_acquire(m_hi);
+          fence_tensormap_acquire(m_lo);
+          last_map_g = e.g;
+        }
+        for (int kw = 0; kw < 3; ++kw) {
+          mbar_wait(empty_bar(stage), par ^ 1);
+          const uint32_t st = base + stage * C::kStageBytes;
+          mbar_expect_tx(full_bar(stage), C::kStageBytes);
+          tma_load_4d(st, m_hi, 0, e.w0 + kw - 1, e.h0 - 1, e.n, full_bar(stage));
+          tma_load_4d(st + C::kABox, m_lo, 0, e.w0 + kw - 1, e.h0 - 1, e.n, full_bar(stage));
+          if (++stage == C::kStages) { stage = 0; par ^= 1; }
+        }
+        t = t_next;
+      }
+    }
+  } else if (warp > C::kEpiWarps) {
+    if (lane == 0) {
+      // ---------------- MMA issuers: role 0 -> D1 = [W_hi; W_lo] x X_hi, role 1 -> D2 = [W_hi; .] x X_lo ----------------
+      const int role = warp - (C::kEpiWarps + 1);
+      const uint32_t d = tmem_base + (uint32_t)(role == 0 ? C::kColD1 : C::kColD2);
+      const uint32_t d_empty = role == 0 ? d1_empty : d2_empty, d_full = role == 0 ? d1_full : d2_full;
+      uint32_t stage = 0, par = 0;
+      for (uint32_t ti = 0;; ++ti) {
+        const uint32_t slot = ti & (kSched - 1);
+        mbar_wait(sched_full(slot), (ti / kSched) & 1);
+        int g;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(g) : "r"(ring + slot * (uint32_t)sizeof(TileEntry)) : "memory");
+        mbar_arrive(sched_empty(slot));
+        if (g < 0) break;
+        mbar_wait(d_empty, (ti & 1) ^ 1);  // the epilogue warps have the previous tile in registers
+        tc_fence_after();
+        for (int kw = 0; kw < 3; ++kw) {
+          mbar_wait(full_bar(stage), par);
+          tc_fence_after();
+          // B operand: the pixel rows kh .. kh+7 of the box (16 pixels x 64 B per row), hi plane for D1, lo plane for D2
+          const uint64_t d0 = make_desc<KC>(base + stage * C::kStageBytes + (role == 1 ? C::kABox : 0));
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint64_t db0 = d0 + (uint64_t)((kh * kTW * KC * 2) >> 4);
+            const uint32_t ta0 = tmem_base + (uint32_t)(C::kColA + (kh * 3 + kw) * 16);  // 2 k-steps x 8 columns per tap
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              umma_bf16_ts(d, ta0 + (uint32_t)(8 * k), db0 + (uint64_t)(2 * k), idesc, (kw | kh | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == C::kStages) { stage = 0; par ^= 1; }
+        }
+        umma_commit(d_full);
+      }
+    }
+  } else {
+    // ---------------- epilogue: warp = (lane quadrant q, pixel chunk pc) ----------------
+    const int q = warp & 3, pc = warp >> 2;
+    const bool owner = q < 2;           // quadrants 0, 1: hi*hi lanes = the warps that own channel 32*q + lane
+    const int ch = (q & 1) * 32 + lane;  // output channel of this thread
+    const uint32_t lane_base = ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * pc);
+    const float bias_c = bias[ch];
+    const float scale = owner ? debias_scale : 1.0f;  // the de-bias scale belongs to the hi*hi sums only
+    const int bar_id = 1 + (q & 1) * 4 + pc;          // one named barrier per (channel half, pixel chunk) warp pair
+    for (uint32_t ti = 0;; ++ti) {
+      const uint32_t slot = ti & (kSched - 1);
+      mbar_wait(sched_full(slot), (ti / kSched) & 1);
+      const TileEntry e = ring_p[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sched_empty(slot));
+      if (e.g < 0) break;
+      const uint32_t tp = ti & 1;
+      float acc[32];
+      mbar_wait(d1_full, tp);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)C::kColD1, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]) * scale;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d1_empty);
+      // exchange slot of this (tile parity, channel half, pixel chunk): [pixel j][lane]
+      float* xs = xch_p + (size_t)(((tp * 2 + (q & 1)) * 4 + pc) * 32 * 32);
+      if (!owner) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xs[j * 32 + lane] = acc[j];
+        named_bar_sync(bar_id, 64);
+        continue;
+      }
+      mbar_wait(d2_full, tp);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)C::kColD2, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);  // + hi*lo
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty);
+      named_bar_sync(bar_id, 64);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += xs[j * 32 + lane];        // + lo*hi
+      // bias, ReLU, 2x2 max-pool over the thread's two tile rows (registers j and 16 + j), fp16 split, NHWC store
+      const int oh = (e.h0 + 2 * pc) >> 1;
+      if (oh < e.OH) {
+        const size_t row_pix = (size_t)e.out_off + ((size_t)e.n * e.OH + oh) * e.OW;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int ow = (e.w0 >> 1) + jj;
+          float v = fmaxf(fmaxf(acc[2 * jj], acc[2 * jj + 1]), fmaxf(acc[16 + 2 * jj], acc[16 + 2 * jj + 1])) + bias_c;
+          if (relu) v = fmaxf(v, 0.f);
+          uint16_t hi, lo;
+          split1(v, hi, lo, ovf);
+          if (ow < e.OW) {
+            out_hi[(row_pix + ow) * COUT + ch] = __ushort_as_half(hi);
+            out_lo[(row_pix + ow) * COUT + ch] = __ushort_as_half(lo);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::kEpiWarps) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
 // CTA-pair form of the kernel for the COUT = 128, KC = 64 layers: two CTAs of a cluster (the two SMs of a
 // TPC) run ONE tcgen05.mma.cta_group::2 of M = 256 per step -- each CTA owns its own 128-pixel tile (A
 // operand, its own TMEM accumulators) and HALF of the weight tile (64 of the 128 output channels); the
@@ -1855,6 +2127,19 @@ void launch_conv_pair(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int
   }
 }
 
+void launch_conv_ws(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
+                    const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int* ovf, cudaStream_t st) {
+  using C = WsCfg;
+  OCRS_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  const int grid = std::max(1, std::min(n_tiles, sm_count()));
+  // expected truncation of the 18 MMAs behind a hi*hi sum, like promo_scale() for the 8 behind a promotion group
+  const float debias = 1.0f + (promo_scale() - 1.0f) * (18.0f / 8.0f);
+  conv3x3_ws_kernel<<<grid, C::kThreads, C::kSmemBytes, st>>>(d_maps, d_groups, n_groups, n_tiles, d_counter, w.w_hi.as<act_t>(),
+                                                              w.w_lo.as<act_t>(), w.bias.as<float>(), y_hi, y_lo, relu, debias, ovf);
+  count_launch();
+  OCRS_CUDA_CHECK(cudaGetLastError());
+}
+
 template <int KC, int COUT>
 void launch_conv_res(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n_groups, int n_tiles, int* d_counter,
                      const ConvWeightsTC& w, act_t* y_hi, act_t* y_lo, int relu, int ph, int pw, int* ovf, cudaStream_t st) {
@@ -2051,6 +2336,12 @@ void conv_fill_tiles(RaggedDesc* d) {
 // faster per SM, and with three batches in flight the benchmark stopped making progress, cause not found:
 // profiles/r02n_halo32.md.  That layer runs the resident-weights kernel instead.)
 bool conv_uses_halo(int Cin, int Cout) { return conv_mode() == 2 && Cin % 64 == 0 && Cout == 128; }
+// the 32 -> 64 layer with a fused 2x2 pool: the weights-stationary transposed kernel (same 8 x 16 tiles and 10-row boxes
+// as the resident-weights kernel; OCRS_B200_CONV_WS=0 selects that one)
+bool conv_ws_enabled() {
+  static const bool on = [] { const char* e = std::getenv("OCRS_B200_CONV_WS"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
 // the 32 -> 64 layer: resident weights + 10-row activation boxes (OCRS_B200_CONV_RES=0: the streaming kernel)
 bool conv_uses_res(int Cin, int Cout) {
   static const bool on = [] { const char* e = std::getenv("OCRS_B200_CONV_RES"); return e == nullptr || e[0] != '0'; }();
@@ -2074,6 +2365,10 @@ void conv3x3_ragged(const CUtensorMap* d_maps, const RaggedDesc* d_groups, int n
   if (n_tiles == 0 || n_groups == 0) return;
   OCRS_CHECK((ph == 1 || ph == 2) && (pw == 1 || pw == 2), kInternal, "conv3x3 (tensor core): fused pool must be 1 or 2");
   const bool k64 = (w.Cin % 64 == 0);
+  if (conv_uses_res(w.Cin, w.Cout) && ph == 2 && pw == 2 && conv_ws_enabled()) {
+    launch_conv_ws(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ovf, st);
+    return;
+  }
   if (conv_uses_res(w.Cin, w.Cout)) {
     launch_conv_res<32, 64>(d_maps, d_groups, n_groups, n_tiles, d_counter, w, y_hi, y_lo, relu, ph, pw, ovf, st);
     return;

@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OPS = {
-    "rec/conv3x3_tc_kernel": ["conv3x3_res_kernel", "conv3x3_halo_kernel", "conv3x3_tc_kernel", "conv3x3_pair_kernel"],
+    "rec/conv3x3_tc_kernel": ["conv3x3_ws_kernel", "conv3x3_res_kernel", "conv3x3_halo_kernel", "conv3x3_tc_kernel", "conv3x3_pair_kernel"],
     "rec/GRU recurrence(packed)": ["gru_cluster3_kernel", "gru_cluster_kernel"],
     "rec/stem_kernel": ["stem_kernel"],
 }
