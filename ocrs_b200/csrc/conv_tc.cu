@@ -548,6 +548,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
 // MMAs of a tile take ~100 cycles each -- 6 KB of shared-memory operands per MMA of N = 64 in the 64-byte-swizzled
 // layout (32 channels = 64-byte rows) are delivered at ~60 B/clk, about half of what the 128-byte-swizzled operands
 // of the 128-channel layers get.  This layer is bound by shared-memory operand delivery, not by issue or by TMA.
+// Since `conv3x3_ws_kernel` (below) this kernel only runs the layer when its pooling is not 2x2, or with
+// OCRS_B200_CONV_WS=0.
 // ------------------------------------------------------------------------------------------
 template <int KC_, int COUT>
 struct ResCfg {
